@@ -1,0 +1,368 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[M,N] (row-major) (+)= A_op[M,K] * B_op[N,K]^T (+ bias[N])
+//
+// Each operand may be stored K-major (reduction dim contiguous) or MN-major (M / N contiguous), so the
+// one kernel covers the three GEMMs of a linear layer without any transposes in memory:
+//   forward  y  = x  W^T : A = x  (K-major),  B = W  (K-major)
+//   dgrad    dx = dy W   : A = dy (K-major),  B = W  (MN-major)
+//   wgrad    dW = dy^T x : A = dy (MN-major), B = x  (MN-major)
+//
+// Structure (one CTA per SM, or one CTA *pair* per 2 SMs with cta_group::2):
+//   warp 0   : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier full/empty)
+//   warp 1   : MMA issuer     (one elected thread; tcgen05.mma kind::f16, fp32 accumulators in TMEM)
+//   warp 2   : TMEM allocator (512 columns = 2 accumulator stages of 128 lanes x 256 columns)
+//   warps 4-7: epilogue       (tcgen05.ld -> registers -> bias/accumulate/cast -> 16B global stores)
+// The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the mainloop of tile i+1.
+// With kCluster == 2 the pair computes a 256x256 tile: each CTA stages its own 128 rows of A and 128 of the
+// 256 rows of B, halving shared-memory and L2 traffic per FLOP; only the leader CTA issues MMAs.
+//
+// Reference parity: replaces the cuBLAS GEMMs the reference reaches through nn.Linear
+// (reference torchacc/__init__.py:97-98 forces XLA onto cuBLAS; eager path uses cuBLASLt).
+#include <stdio.h>
+
+#include "../common/ptx.cuh"
+#include "../common/tensormap.h"
+#include "gemm.h"
+
+namespace tb {
+
+constexpr int kBlockMCta = 128;  // accumulator rows per CTA (TMEM lanes)
+constexpr int kBlockN = 256;     // UMMA N
+constexpr int kBlockK = 64;      // 128 bytes of bf16 = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kNumThreads = 256;
+constexpr int kGroupM = 8;       // tile rasterisation: sweep 8 row-tiles before moving along N
+
+struct GemmArgs {
+  void* D;
+  const __nv_bfloat16* bias;
+  int M, N, K;
+  long long ldd;
+  int accumulate;  // D += result
+  int out_fp32;
+  int num_m_tiles, num_n_tiles;
+};
+
+template <int kCluster>
+struct GemmSmem {
+  static constexpr int kLoadN = kBlockN / kCluster;
+  static constexpr int kABytes = kBlockMCta * kBlockK * 2;
+  static constexpr int kBBytes = kLoadN * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (kCluster == 2) ? 6 : 4;
+  static constexpr int kBarrierBytes = 1024;
+  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // +1024 alignment slack
+};
+
+__device__ __forceinline__ void tile_coords(int t, int num_m_tiles, int num_n_tiles, int& tm, int& tn) {
+  const int per_group = kGroupM * num_n_tiles;
+  const int g = t / per_group;
+  const int first_m = g * kGroupM;
+  const int gsize = min(kGroupM, num_m_tiles - first_m);
+  const int r = t - g * per_group;
+  tm = first_m + (r % gsize);
+  tn = r / gsize;
+}
+
+template <int kCluster, Major kAMajor, Major kBMajor>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmArgs args) {
+  using S = GemmSmem<kCluster>;
+  constexpr int kStages = S::kStages;
+  constexpr int kLoadN = S::kLoadN;
+  constexpr uint32_t kUmmaM = kBlockMCta * kCluster;
+  constexpr uint32_t kIdesc = make_idesc_f16(kUmmaM, kBlockN, kAMajor, kBMajor, true);
+
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment.
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * S::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  auto smem_a = [&](int s) { return smem_base + s * S::kStageBytes; };
+  auto smem_b = [&](int s) { return smem_base + s * S::kStageBytes + S::kABytes; };
+
+  const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const uint32_t lane = lane_id();
+  const uint32_t cta_rank = (kCluster == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+
+  const int num_tiles = args.num_m_tiles * args.num_n_tiles;
+  const int num_k_blocks = (args.K + kBlockK - 1) / kBlockK;
+  const int cluster_id = blockIdx.x / kCluster;
+  const int num_clusters = gridDim.x / kCluster;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4 * kCluster);  // one arrive per epilogue warp (of both CTAs)
+    }
+    fence_mbar_init();
+  }
+  if (warp_idx == 2) tmem_alloc<kCluster>(tmem_slot, 512);
+  tc_fence_before();
+  if constexpr (kCluster == 2) cluster_sync(); else __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp_idx == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int it = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        int tm, tn;
+        tile_coords(t, args.num_m_tiles, args.num_n_tiles, tm, tn);
+        const int m0 = tm * (int)kUmmaM + (int)cta_rank * kBlockMCta;
+        const int n0 = tn * kBlockN + (int)cta_rank * kLoadN;
+        for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          if (is_leader) mbar_arrive_expect_tx(full_bar(s), S::kStageBytes * kCluster);
+          const int k0 = kb * kBlockK;
+          auto load = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1) {
+            if constexpr (kCluster == 2) tma_load_2d_2sm(dst, map, full_bar(s), c0, c1);
+            else tma_load_2d(dst, map, full_bar(s), c0, c1);
+          };
+          if constexpr (kAMajor == Major::K) {
+            load(smem_a(s), &tmap_a, k0, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < kBlockMCta / 64; ++i) load(smem_a(s) + i * 8192, &tmap_a, m0 + i * 64, k0);
+          }
+          if constexpr (kBMajor == Major::K) {
+            load(smem_b(s), &tmap_b, k0, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < kLoadN / 64; ++i) load(smem_b(s) + i * 8192, &tmap_b, n0 + i * 64, k0);
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ================================ MMA issuer ================================
+    if (is_leader && lane == 0) {
+      int it = 0, lt = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++lt) {
+        const int as = lt & 1;
+        const uint32_t aph = (lt >> 1) & 1;
+        if constexpr (kCluster == 2) mbar_wait_cluster(tempty_bar(as), aph ^ 1);
+        else mbar_wait(tempty_bar(as), aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * kBlockN;
+        for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = (kAMajor == Major::K) ? desc_kmajor_sw128(smem_a(s), k)
+                                                       : desc_mnmajor_sw128(smem_a(s), k, 8192);
+            const uint64_t db = (kBMajor == Major::K) ? desc_kmajor_sw128(smem_b(s), k)
+                                                       : desc_mnmajor_sw128(smem_b(s), k, 8192);
+            umma_ss_f16<kCluster>(tmem_d, da, db, kIdesc, (kb | k) != 0);
+          }
+          // Release the smem slot once the MMAs that read it retire.
+          if constexpr (kCluster == 2) umma_commit_2sm(empty_bar(s), 0x3);
+          else umma_commit(empty_bar(s));
+        }
+        if constexpr (kCluster == 2) umma_commit_2sm(tfull_bar(as), 0x3);
+        else umma_commit(tfull_bar(as));
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ================================ Epilogue ================================
+    const uint32_t q = warp_idx & 3;  // TMEM lane quarter this warp may read
+    const uint32_t tempty_leader =
+        (kCluster == 2) ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);  // barrier lives in the leader CTA
+    int lt = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++lt) {
+      int tm, tn;
+      tile_coords(t, args.num_m_tiles, args.num_n_tiles, tm, tn);
+      const int as = lt & 1;
+      const uint32_t aph = (lt >> 1) & 1;
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after();
+      const long long grow = (long long)tm * kUmmaM + cta_rank * kBlockMCta + q * 32 + lane;
+      const int n0 = tn * kBlockN;
+      const bool row_ok = grow < args.M;
+#pragma unroll 1
+      for (int c = 0; c < kBlockN / 32; ++c) {
+        __syncwarp();  // tcgen05.ld is warp-collective (.sync.aligned): reconverge after the guarded stores
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((q * 32u) << 16) + as * kBlockN + c * 32, r);
+        tmem_ld_wait();
+        const int gcol = n0 + c * 32;
+        if (!row_ok || gcol >= args.N) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const bool full = gcol + 32 <= args.N;
+        if (args.bias != nullptr) {
+          if (full) {
+            const uint4* bp = reinterpret_cast<const uint4*>(args.bias + gcol);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 b = __ldg(bp + j);
+              float2 f0 = unpack_bf16x2(b.x), f1 = unpack_bf16x2(b.y), f2 = unpack_bf16x2(b.z), f3 = unpack_bf16x2(b.w);
+              v[8 * j + 0] += f0.x; v[8 * j + 1] += f0.y; v[8 * j + 2] += f1.x; v[8 * j + 3] += f1.y;
+              v[8 * j + 4] += f2.x; v[8 * j + 5] += f2.y; v[8 * j + 6] += f3.x; v[8 * j + 7] += f3.y;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (gcol + j < args.N) v[j] += __bfloat162float(args.bias[gcol + j]);
+          }
+        }
+        if (args.out_fp32) {
+          float* dp = reinterpret_cast<float*>(args.D) + grow * args.ldd + gcol;
+          if (full) {
+            float4* d4 = reinterpret_cast<float4*>(dp);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (args.accumulate) {
+                float4 old = d4[j];
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              d4[j] = o;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (gcol + j < args.N) dp[j] = v[j] + (args.accumulate ? dp[j] : 0.f);
+          }
+        } else {
+          __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(args.D) + grow * args.ldd + gcol;
+          if (full) {
+            uint4* d4 = reinterpret_cast<uint4*>(dp);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (args.accumulate) {
+                uint4 old = d4[j];
+                float2 f0 = unpack_bf16x2(old.x), f1 = unpack_bf16x2(old.y), f2 = unpack_bf16x2(old.z), f3 = unpack_bf16x2(old.w);
+                v[8 * j + 0] += f0.x; v[8 * j + 1] += f0.y; v[8 * j + 2] += f1.x; v[8 * j + 3] += f1.y;
+                v[8 * j + 4] += f2.x; v[8 * j + 5] += f2.y; v[8 * j + 6] += f3.x; v[8 * j + 7] += f3.y;
+              }
+              uint4 o;
+              o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+              o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              d4[j] = o;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (gcol + j < args.N)
+                dp[j] = __float2bfloat16(v[j] + (args.accumulate ? __bfloat162float(dp[j]) : 0.f));
+          }
+        }
+      }
+      // All TMEM reads of this accumulator stage are complete: hand it back to the MMA warp.
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kCluster == 2) mbar_arrive_cluster(tempty_leader + 8u * as);
+        else mbar_arrive(tempty_leader + 8u * as);
+      }
+    }
+  }
+
+  // ================================ Teardown ================================
+  __syncwarp();  // single-lane role loops: reconverge each warp before the aligned barrier
+  tc_fence_before();
+  if constexpr (kCluster == 2) cluster_sync(); else __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc<kCluster>(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Host launcher
+// ------------------------------------------------------------------------------------------------------
+template <int kCluster, Major kAMajor, Major kBMajor>
+static cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb_, const GemmArgs& args, int num_sms,
+                              cudaStream_t stream) {
+  using S = GemmSmem<kCluster>;
+  auto kern = gemm_bf16_kernel<kCluster, kAMajor, kBMajor>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int num_tiles = args.num_m_tiles * args.num_n_tiles;
+  int clusters = num_sms / kCluster;
+  if (clusters > num_tiles) clusters = num_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * kCluster);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, ta, tb_, args);
+}
+
+cudaError_t gemm_bf16(const void* A, const void* B, void* D, const void* bias, int M, int N, int K, long long lda,
+                      long long ldb, long long ldd, bool a_mn_major, bool b_mn_major, bool out_fp32, bool accumulate,
+                      int cluster, int num_sms, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return cudaSuccess;
+  if (K <= 0) return cudaErrorInvalidValue;
+  if (cluster != 1 && cluster != 2) return cudaErrorInvalidValue;
+  const int load_n = kBlockN / cluster;
+  CUtensorMap ta, tbm;
+  try {
+    // K-major: matrix [MN][K]; MN-major: matrix [K][MN].  Inner box is always 64 elements = 128 B.
+    ta = a_mn_major ? make_map_2d_bf16(A, K, M, lda, 64, kBlockK) : make_map_2d_bf16(A, M, K, lda, kBlockK, kBlockMCta);
+    tbm = b_mn_major ? make_map_2d_bf16(B, K, N, ldb, 64, kBlockK) : make_map_2d_bf16(B, N, K, ldb, kBlockK, load_n);
+  } catch (const std::exception& e) {
+    fprintf(stderr, "%s\n", e.what());
+    return cudaErrorInvalidValue;
+  }
+  GemmArgs args;
+  args.D = D;
+  args.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  args.M = M; args.N = N; args.K = K;
+  args.ldd = ldd;
+  args.accumulate = accumulate ? 1 : 0;
+  args.out_fp32 = out_fp32 ? 1 : 0;
+  const int tile_m = kBlockMCta * cluster;
+  args.num_m_tiles = (M + tile_m - 1) / tile_m;
+  args.num_n_tiles = (N + kBlockN - 1) / kBlockN;
+
+#define TB_DISPATCH(CL, AM, BM) return launch_one<CL, AM, BM>(ta, tbm, args, num_sms, stream)
+  if (cluster == 2) {
+    if (!a_mn_major && !b_mn_major) TB_DISPATCH(2, Major::K, Major::K);
+    if (!a_mn_major && b_mn_major) TB_DISPATCH(2, Major::K, Major::MN);
+    if (a_mn_major && !b_mn_major) TB_DISPATCH(2, Major::MN, Major::K);
+    TB_DISPATCH(2, Major::MN, Major::MN);
+  } else {
+    if (!a_mn_major && !b_mn_major) TB_DISPATCH(1, Major::K, Major::K);
+    if (!a_mn_major && b_mn_major) TB_DISPATCH(1, Major::K, Major::MN);
+    if (a_mn_major && !b_mn_major) TB_DISPATCH(1, Major::MN, Major::K);
+    TB_DISPATCH(1, Major::MN, Major::MN);
+  }
+#undef TB_DISPATCH
+}
+
+}  // namespace tb

@@ -1,0 +1,322 @@
+// Bandwidth-bound transformer ops for sm_100a: RMSNorm (+fused residual add) fwd/bwd, RoPE fwd/bwd (in place,
+// strided so it runs directly on the fused-QKV GEMM output), SwiGLU fwd/bwd.
+// All kernels move 16 bytes per thread per access and keep rows in registers between the reduction and the
+// normalisation pass, so each tensor is read exactly once and written exactly once.
+// Replaces the Triton liger kernels the reference patches in (reference torchacc/ops/liger.py:10-28,69-70).
+#include "../common/ptx.cuh"
+#include "ops.h"
+
+namespace tb {
+
+constexpr int kNormThreads = 256;
+constexpr int kMaxVec = 8;  // H <= 256 * 8 * 8 = 16384
+
+struct alignas(16) bf16x8 {
+  uint4 u;
+};
+
+TB_DEVICE void unpack8(const uint4& u, float (&f)[8]) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+TB_DEVICE uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+template <int kThreads>
+TB_DEVICE float block_reduce_sum(float v, float* red) {
+  v = warp_reduce_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < kThreads / 32) ? red[l] : 0.f;
+  t = warp_reduce_sum(t);
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// RMSNorm forward.  y = (x [+ res]) * rstd * w ;  optionally writes h = x + res (the new residual stream).
+// ---------------------------------------------------------------------------------------------------
+template <int kVpt>
+__global__ void __launch_bounds__(kNormThreads)
+rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                   const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y,
+                   __nv_bfloat16* __restrict__ h_out, float* __restrict__ rstd_out, int rows, int H, float eps) {
+  __shared__ float red[32];
+  const int nvec = H >> 3;
+  float wv[kVpt][8];
+#pragma unroll
+  for (int i = 0; i < kVpt; ++i) {
+    const int v = threadIdx.x + i * kNormThreads;
+    if (v < nvec) unpack8(__ldg(reinterpret_cast<const uint4*>(w) + v), wv[i]);
+  }
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * H);
+    const uint4* rr = res ? reinterpret_cast<const uint4*>(res + (size_t)row * H) : nullptr;
+    float xv[kVpt][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVpt; ++i) {
+      const int v = threadIdx.x + i * kNormThreads;
+      if (v < nvec) {
+        unpack8(xr[v], xv[i]);
+        if (rr) {
+          float rv[8];
+          unpack8(rr[v], rv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xv[i][j] += rv[j];
+          uint4 hp = pack8(xv[i]);
+          if (h_out) reinterpret_cast<uint4*>(h_out + (size_t)row * H)[v] = hp;
+          unpack8(hp, xv[i]);  // normalise exactly what the residual stream stores (bf16-rounded)
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += xv[i][j] * xv[i][j];
+      }
+    }
+    ss = block_reduce_sum<kNormThreads>(ss, red);
+    const float rstd = rsqrtf(ss / (float)H + eps);
+    if (threadIdx.x == 0 && rstd_out) rstd_out[row] = rstd;
+#pragma unroll
+    for (int i = 0; i < kVpt; ++i) {
+      const int v = threadIdx.x + i * kNormThreads;
+      if (v < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = xv[i][j] * rstd * wv[i][j];
+        reinterpret_cast<uint4*>(y + (size_t)row * H)[v] = pack8(o);
+      }
+    }
+  }
+}
+
+// RMSNorm backward.  dx = rstd * (dy*w - xhat * mean(dy*w*xhat)) [+ dres];  dw += sum_rows dy * xhat (fp32 atomics,
+// one atomic per column per CTA).
+template <int kVpt>
+__global__ void __launch_bounds__(kNormThreads)
+rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                   const __nv_bfloat16* __restrict__ w, const float* __restrict__ rstd,
+                   const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ dw,
+                   int rows, int H) {
+  __shared__ float red[32];
+  const int nvec = H >> 3;
+  float wv[kVpt][8], dwv[kVpt][8];
+#pragma unroll
+  for (int i = 0; i < kVpt; ++i) {
+    const int v = threadIdx.x + i * kNormThreads;
+    if (v < nvec) unpack8(__ldg(reinterpret_cast<const uint4*>(w) + v), wv[i]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dwv[i][j] = 0.f;
+  }
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * H);
+    const uint4* gr = reinterpret_cast<const uint4*>(dy + (size_t)row * H);
+    const float rs = rstd[row];
+    float xh[kVpt][8], gw[kVpt][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVpt; ++i) {
+      const int v = threadIdx.x + i * kNormThreads;
+      if (v < nvec) {
+        float g[8];
+        unpack8(xr[v], xh[i]);
+        unpack8(gr[v], g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] *= rs;
+          dwv[i][j] += g[j] * xh[i][j];
+          gw[i][j] = g[j] * wv[i][j];
+          dot += gw[i][j] * xh[i][j];
+        }
+      }
+    }
+    dot = block_reduce_sum<kNormThreads>(dot, red) / (float)H;
+#pragma unroll
+    for (int i = 0; i < kVpt; ++i) {
+      const int v = threadIdx.x + i * kNormThreads;
+      if (v < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rs * (gw[i][j] - xh[i][j] * dot);
+        if (dres) {
+          float r[8];
+          unpack8(reinterpret_cast<const uint4*>(dres + (size_t)row * H)[v], r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += r[j];
+        }
+        reinterpret_cast<uint4*>(dx + (size_t)row * H)[v] = pack8(o);
+      }
+    }
+  }
+  if (dw) {
+#pragma unroll
+    for (int i = 0; i < kVpt; ++i) {
+      const int v = threadIdx.x + i * kNormThreads;
+      if (v < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(dw + v * 8 + j, dwv[i][j]);
+      }
+    }
+  }
+}
+
+cudaError_t rmsnorm_fwd(const void* x, const void* res, const void* w, void* y, void* h_out, float* rstd, int rows,
+                        int H, float eps, int num_sms, cudaStream_t stream) {
+  if (rows == 0) return cudaSuccess;
+  if (H % 8 != 0 || H > kNormThreads * 8 * kMaxVec) return cudaErrorInvalidValue;
+  int grid = rows < num_sms * 8 ? rows : num_sms * 8;
+  const int vpt = (H / 8 + kNormThreads - 1) / kNormThreads;
+#define TB_LAUNCH(V)                                                                                            \
+  rmsnorm_fwd_kernel<V><<<grid, kNormThreads, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res,  \
+                                                           (const __nv_bfloat16*)w, (__nv_bfloat16*)y,          \
+                                                           (__nv_bfloat16*)h_out, rstd, rows, H, eps)
+  if (vpt <= 1) TB_LAUNCH(1); else if (vpt <= 2) TB_LAUNCH(2); else if (vpt <= 4) TB_LAUNCH(4); else TB_LAUNCH(8);
+#undef TB_LAUNCH
+  return cudaGetLastError();
+}
+
+cudaError_t rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx,
+                        float* dw, int rows, int H, int num_sms, cudaStream_t stream) {
+  if (rows == 0) return cudaSuccess;
+  if (H % 8 != 0 || H > kNormThreads * 8 * kMaxVec) return cudaErrorInvalidValue;
+  int grid = rows < num_sms * 4 ? rows : num_sms * 4;
+  const int vpt = (H / 8 + kNormThreads - 1) / kNormThreads;
+#define TB_LAUNCH(V)                                                                                            \
+  rmsnorm_bwd_kernel<V><<<grid, kNormThreads, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,   \
+                                                           (const __nv_bfloat16*)w, rstd,                       \
+                                                           (const __nv_bfloat16*)dres, (__nv_bfloat16*)dx, dw,  \
+                                                           rows, H)
+  if (vpt <= 1) TB_LAUNCH(1); else if (vpt <= 2) TB_LAUNCH(2); else if (vpt <= 4) TB_LAUNCH(4); else TB_LAUNCH(8);
+#undef TB_LAUNCH
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// RoPE (rotate-half convention, HF Llama): in place on x[T, nheads, D] with token stride `ts` elements.
+//   out[:D/2] = x1*cos - x2*sin ; out[D/2:] = x2*cos + x1*sin        (backward: sin -> -sin)
+// cos/sin tables are fp32 [max_pos, D/2]; position of token t is positions[t] or (t % seq_len).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rope_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+            const int* __restrict__ positions, long long T, int nheads, int D, long long ts, int seq_len,
+            float sin_sign) {
+  const int half = D >> 1;
+  const int vec_per_head = half >> 3;  // 8 elements per thread from each half
+  const long long total = T * nheads * vec_per_head;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vec_per_head);
+    const long long th = i / vec_per_head;
+    const int hd = (int)(th % nheads);
+    const long long t = th / nheads;
+    const int pos = positions ? positions[t] : (int)(t % seq_len);
+    __nv_bfloat16* base = x + t * ts + (long long)hd * D + v * 8;
+    uint4 u1 = *reinterpret_cast<uint4*>(base);
+    uint4 u2 = *reinterpret_cast<uint4*>(base + half);
+    float a[8], b[8], c[8], s[8];
+    unpack8(u1, a);
+    unpack8(u2, b);
+    const float4* cp = reinterpret_cast<const float4*>(cos_t + (size_t)pos * half + v * 8);
+    const float4* sp = reinterpret_cast<const float4*>(sin_t + (size_t)pos * half + v * 8);
+    float4 c0 = __ldg(cp), c1 = __ldg(cp + 1), s0 = __ldg(sp), s1 = __ldg(sp + 1);
+    c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+    s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
+    float o1[8], o2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float sn = s[j] * sin_sign;
+      o1[j] = a[j] * c[j] - b[j] * sn;
+      o2[j] = b[j] * c[j] + a[j] * sn;
+    }
+    *reinterpret_cast<uint4*>(base) = pack8(o1);
+    *reinterpret_cast<uint4*>(base + half) = pack8(o2);
+  }
+}
+
+cudaError_t rope_inplace(void* x, const float* cos_t, const float* sin_t, const int* positions, long long T,
+                         int nheads, int D, long long token_stride, int seq_len, bool backward, int num_sms,
+                         cudaStream_t stream) {
+  if (T == 0 || nheads == 0) return cudaSuccess;
+  if (D % 16 != 0 || token_stride % 8 != 0) return cudaErrorInvalidValue;
+  long long total = T * nheads * (D / 16);
+  long long blocks = (total + 255) / 256;
+  int grid = (int)(blocks < (long long)num_sms * 16 ? blocks : (long long)num_sms * 16);
+  rope_kernel<<<grid, 256, 0, stream>>>((__nv_bfloat16*)x, cos_t, sin_t, positions, T, nheads, D, token_stride,
+                                         seq_len, backward ? -1.f : 1.f);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SwiGLU: h = silu(g) * u with g = gu[:, :F], u = gu[:, F:] (row stride ld_gu), h row stride F.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ h, long long T, int F,
+                  long long ld_gu) {
+  const int vpr = F >> 3;
+  const long long total = T * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long t = i / vpr;
+    const int v = (int)(i - t * vpr);
+    const __nv_bfloat16* row = gu + t * ld_gu;
+    float g[8], u[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(row + v * 8), g);
+    unpack8(*reinterpret_cast<const uint4*>(row + F + v * 8), u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = g[j] / (1.f + __expf(-g[j])) * u[j];
+    *reinterpret_cast<uint4*>(h + t * F + v * 8) = pack8(o);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ gu,
+                  __nv_bfloat16* __restrict__ dgu, long long T, int F, long long ld_gu, long long ld_dgu) {
+  const int vpr = F >> 3;
+  const long long total = T * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long t = i / vpr;
+    const int v = (int)(i - t * vpr);
+    const __nv_bfloat16* row = gu + t * ld_gu;
+    float g[8], u[8], d[8], dg[8], du[8];
+    unpack8(*reinterpret_cast<const uint4*>(row + v * 8), g);
+    unpack8(*reinterpret_cast<const uint4*>(row + F + v * 8), u);
+    unpack8(*reinterpret_cast<const uint4*>(dh + t * F + v * 8), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float sg = 1.f / (1.f + __expf(-g[j]));
+      const float silu = g[j] * sg;
+      du[j] = d[j] * silu;
+      dg[j] = d[j] * u[j] * (sg + silu * (1.f - sg));
+    }
+    __nv_bfloat16* orow = dgu + t * ld_dgu;
+    *reinterpret_cast<uint4*>(orow + v * 8) = pack8(dg);
+    *reinterpret_cast<uint4*>(orow + F + v * 8) = pack8(du);
+  }
+}
+
+cudaError_t swiglu_fwd(const void* gu, void* h, long long T, int F, long long ld_gu, int num_sms,
+                       cudaStream_t stream) {
+  if (T == 0) return cudaSuccess;
+  if (F % 8 != 0 || ld_gu % 8 != 0) return cudaErrorInvalidValue;
+  long long blocks = (T * (F / 8) + 255) / 256;
+  int grid = (int)(blocks < (long long)num_sms * 16 ? blocks : (long long)num_sms * 16);
+  swiglu_fwd_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)gu, (__nv_bfloat16*)h, T, F, ld_gu);
+  return cudaGetLastError();
+}
+
+cudaError_t swiglu_bwd(const void* dh, const void* gu, void* dgu, long long T, int F, long long ld_gu,
+                       long long ld_dgu, int num_sms, cudaStream_t stream) {
+  if (T == 0) return cudaSuccess;
+  if (F % 8 != 0 || ld_gu % 8 != 0 || ld_dgu % 8 != 0) return cudaErrorInvalidValue;
+  long long blocks = (T * (F / 8) + 255) / 256;
+  int grid = (int)(blocks < (long long)num_sms * 16 ? blocks : (long long)num_sms * 16);
+  swiglu_bwd_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)dh, (const __nv_bfloat16*)gu,
+                                               (__nv_bfloat16*)dgu, T, F, ld_gu, ld_dgu);
+  return cudaGetLastError();
+}
+
+}  // namespace tb
