@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Flagship benchmark: Llama-3-8B, FSDP (ZeRO-3) + gradient checkpointing, bf16, seq 4096, synthetic tokens.
+
+    python bench.py --gpus N --steps K --warmup W            # ours (torchrun launches N ranks for N > 1)
+    python bench.py --impl reference --gpus N ...            # unmodified reference from baseline/_ref
+
+Metric (BASELINE.json): training tokens/s for the WHOLE job, device-timed with CUDA events, max over ranks.
+Weak scaling: the per-GPU batch is fixed (``--mbs``, default 2 sequences of 4096 tokens).
+Each timed step = forward + backward + global grad-norm clip + AdamW update (nothing skipped, full 32 layers).
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+A100_TOKENS_PER_S_PER_GPU = 4044.8   # BASELINE.md row 1 (8x A100-80G, TorchAcc XLA-FSDP, seq 4096)
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--model", default="llama3-8b")
+    p.add_argument("--seq-len", type=int, default=4096)
+    p.add_argument("--mbs", type=int, default=2, help="sequences per GPU per step")
+    p.add_argument("--layers", type=int, default=None, help="debug only: override the layer count (invalidates the number)")
+    p.add_argument("--no-gc", action="store_true")
+    p.add_argument("--attn", default=None, help="attention backend override (native|sdpa)")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self.t.start()
+        return self
+
+    def stop(self) -> dict:
+        self._stop.set()
+        self.t.join(timeout=3)
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def timed_loop(step_fn, steps, warmup, device, world):
+    import torch
+    import torch.distributed as dist
+    for _ in range(warmup):
+        step_fn()
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[device.index])
+        torch.cuda.synchronize(device)
+
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step_fn()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our implementation
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import torchacc_b200 as ta
+    from torchacc_b200 import _native as nat
+    from torchacc_b200.models import build_llama, llama_config
+
+    rank, local_rank, world = dist_env()
+    assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if a.attn:
+        ta.ops.set_attention_backend(a.attn)
+
+    over = {}
+    if a.layers is not None:
+        over["num_hidden_layers"] = a.layers
+    mcfg = llama_config(a.model, max_position_embeddings=max(a.seq_len, 8192), **over)
+    torch.manual_seed(1234)
+    with torch.device(device):
+        model = build_llama(mcfg, dtype=torch.bfloat16)
+
+    cfg = ta.Config()
+    cfg.compute.bf16 = True
+    cfg.memory.gc = not a.no_gc
+    cfg.memory.gc_cls = {"LlamaDecoderLayer"}
+    cfg.dist.fsdp.size = world
+    cfg.dist.fsdp.wrap_layer_cls = {"LlamaDecoderLayer"}
+
+    # synthetic data: random tokens, pinned host memory (e2e loop uploads them every step through AsyncLoader)
+    g = torch.Generator().manual_seed(rank)
+    n_batches = a.warmup + a.steps + 2
+    host = [{"input_ids": torch.randint(0, mcfg.vocab_size, (a.mbs, a.seq_len), generator=g).pin_memory()}
+            for _ in range(4)]
+    for b in host:
+        b["labels"] = b["input_ids"]
+
+    class Synth:
+        def __len__(self):
+            return n_batches
+
+        def __iter__(self):
+            for i in range(n_batches):
+                yield host[i % len(host)]
+
+    model, loader = ta.accelerate(model, Synth(), cfg)
+    opt = ta.optim.FusedAdamW(model.parameters(), lr=1e-5, betas=(0.9, 0.95), weight_decay=0.1)
+
+    dev_batch = {k: v.to(device) for k, v in host[0].items()}
+    last = {}
+
+    def step(batch=dev_batch):
+        out = model(**batch)
+        loss = out["loss"]
+        loss.backward()
+        model.clip_grad_norm_(1.0)
+        opt.step()
+        model.zero_grad()
+        last["loss"] = loss
+        return loss
+
+    # ---- device-timed region --------------------------------------------------------------------------------
+    sampler = None
+    for _ in range(a.warmup):
+        step()
+    torch.cuda.synchronize(device)
+    if rank == 0:
+        sampler = ClockSampler(local_rank).start()
+    l0 = nat.LAUNCHES
+    ms = timed_loop(step, a.steps, 0, device, world)
+    launches = nat.LAUNCHES - l0
+    clocks = sampler.stop() if sampler else None
+    tokens = a.mbs * a.seq_len * world * a.steps
+    value = tokens / (ms / 1e3)
+
+    # ---- end-to-end through the public API: AsyncLoader H2D every step + loss D2H every step ---------------------
+    e2e = None
+    if not a.no_e2e:
+        it = iter(loader)
+        for _ in range(2):
+            float(step(next(it)))
+        if world > 1:
+            dist.barrier(device_ids=[device.index])
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            loss_val = float(step(next(it)))          # device -> host read of the step's loss
+        e1.record()
+        torch.cuda.synchronize(device)
+        wall = (time.perf_counter() - t0) * 1e3
+        ems = torch.tensor([max(e0.elapsed_time(e1), wall)], device=device)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": tokens / (float(ems) / 1e3), "unit": "tokens/s",
+               "h2d_bytes_per_step": int(2 * a.mbs * a.seq_len * 8), "d2h_bytes_per_step": 4,
+               "last_loss": loss_val}
+
+    if rank == 0:
+        res = {
+            "metric": "Llama-3-8B FSDP bf16 training throughput (whole job, device-timed, max over ranks)",
+            "value": value, "unit": "tokens/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": value / (A100_TOKENS_PER_S_PER_GPU * world), "dtype": "bf16", "data": "synthetic",
+            "impl": "ours",
+            "config": {"model": a.model, "global_batch": a.mbs * world, "seq_len": a.seq_len,
+                       "parallelism": f"fsdp{world}" + ("" if a.no_gc else "+gc"), "layers": mcfg.num_hidden_layers,
+                       "optimizer": "FusedAdamW + clip_grad_norm(1.0)", "attention": ta.ops.get_attention_backend(),
+                       "l2": "no explicit flush: each step streams >16 GB of weights/activations (>> 126 MB L2)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "mfu_model_flops": mcfg.flops_per_token(a.seq_len) * value / world / 1e12,
+            "loss": float(last["loss"]),
+        }
+        print(json.dumps(res), flush=True)
+    if world > 1:
+        dist.barrier(device_ids=[device.index])
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm: unmodified AlibabaPAI/torchacc from baseline/_ref, its own public API and eager code path
+# ----------------------------------------------------------------------------------------------------------------
+def run_reference(a):
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    rank, local_rank, world = dist_env()
+
+    def unavailable(why):
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": why}), flush=True)
+        sys.exit(0)
+
+    if not os.path.isdir(os.path.join(ref_dir, "torchacc")):
+        unavailable("baseline/_ref/torchacc not installed (see DESIGN.md: offline install outcome)")
+    sys.path.insert(0, ref_dir)
+    sys.path.insert(0, os.path.join(ROOT, "baseline", "shims"))   # stand-in for the missing `accelerate` dependency
+    try:
+        import torch
+        import torch.distributed as dist
+        import torchacc as ref_ta
+        from transformers import LlamaConfig, LlamaForCausalLM
+    except Exception as e:  # noqa: BLE001
+        unavailable(f"import failed: {type(e).__name__}: {e}"[:300])
+
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    hf = LlamaConfig(vocab_size=128256, hidden_size=4096, intermediate_size=14336,
+                     num_hidden_layers=a.layers or 32, num_attention_heads=32, num_key_value_heads=8,
+                     max_position_embeddings=max(a.seq_len, 8192), rope_theta=500000.0, rms_norm_eps=1e-5,
+                     tie_word_embeddings=False, attn_implementation="flash_attention_2", use_cache=False)
+    torch.manual_seed(1234)
+    try:
+        with torch.device("meta"):
+            model = LlamaForCausalLM(hf)
+        model = model.to_empty(device="cpu" if world > 1 else device)
+        with torch.no_grad():
+            for p in model.parameters():
+                p.normal_(0, 0.02)
+        if not a.no_gc:
+            model.gradient_checkpointing_enable()   # the reference's eager path has no working GC of its own
+        cfg = ref_ta.Config()
+        cfg.backend = "eager"
+        cfg.compute.bf16 = True
+        cfg.memory.gc = False
+        cfg.dist.fsdp.size = world
+        cfg.dist.fsdp.wrap_layer_cls = {"LlamaDecoderLayer"}
+        model = ref_ta.accelerate(model, config=cfg)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-5, betas=(0.9, 0.95), weight_decay=0.1, fused=True)
+    except Exception as e:  # noqa: BLE001
+        unavailable(f"setup failed: {type(e).__name__}: {e}"[:300])
+
+    g = torch.Generator().manual_seed(rank)
+    host = torch.randint(0, 128256, (a.mbs, a.seq_len), generator=g).pin_memory()
+    ids = host.to(device)
+    last = {}
+
+    def step(x=ids):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = model(input_ids=x, labels=x)
+        loss = out.loss if hasattr(out, "loss") else out["loss"]
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0) if world == 1 else model.clip_grad_norm_(1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        last["loss"] = loss
+        return loss
+
+    try:
+        for _ in range(a.warmup):
+            step()
+        torch.cuda.synchronize(device)
+        sampler = ClockSampler(local_rank).start() if rank == 0 else None
+        ms = timed_loop(step, a.steps, 0, device, world)
+        clocks = sampler.stop() if sampler else None
+    except Exception as e:  # noqa: BLE001
+        unavailable(f"run failed: {type(e).__name__}: {e}"[:300])
+    tokens = a.mbs * a.seq_len * world * a.steps
+    value = tokens / (ms / 1e3)
+    e2e = None
+    if not a.no_e2e:
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            loss_val = float(step(host.to(device, non_blocking=True)))
+        torch.cuda.synchronize(device)
+        wall = torch.tensor([(time.perf_counter() - t0) * 1e3], device=device)
+        if world > 1:
+            dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        e2e = {"value": tokens / (float(wall) / 1e3), "unit": "tokens/s",
+               "h2d_bytes_per_step": int(a.mbs * a.seq_len * 8), "d2h_bytes_per_step": 4, "last_loss": loss_val}
+    if rank == 0:
+        print(json.dumps({
+            "metric": "Llama-3-8B FSDP bf16 training throughput (whole job, device-timed, max over ranks)",
+            "value": value, "unit": "tokens/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": value / (A100_TOKENS_PER_S_PER_GPU * world), "dtype": "bf16", "data": "synthetic",
+            "impl": "reference",
+            "config": {"model": a.model, "global_batch": a.mbs * world, "seq_len": a.seq_len,
+                       "parallelism": f"fsdp{world}" + ("" if a.no_gc else "+gc(hf)"),
+                       "stack": "torchacc eager: torch FSDP1 + cuBLAS + flash-attn2 + liger"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": 0, "loss": float(last["loss"])}), flush=True)
+    if world > 1:
+        dist.barrier(device_ids=[device.index])
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

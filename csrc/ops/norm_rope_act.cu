@@ -250,21 +250,21 @@ cudaError_t rope_inplace(void* x, const float* cos_t, const float* sin_t, const 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// SwiGLU: h = silu(g) * u with g = gu[:, :F], u = gu[:, F:] (row stride ld_gu), h row stride F.
+// SwiGLU: h = silu(g) * u.  g and u are separate row-strided matrices [T, F] (for the fused gate|up projection
+// u = g + F and both strides are 2F); h is [T, F] contiguous.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ h, long long T, int F,
-                  long long ld_gu) {
+swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ g_, const __nv_bfloat16* __restrict__ u_,
+                  __nv_bfloat16* __restrict__ h, long long T, int F, long long ldg, long long ldu) {
   const int vpr = F >> 3;
   const long long total = T * vpr;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long t = i / vpr;
     const int v = (int)(i - t * vpr);
-    const __nv_bfloat16* row = gu + t * ld_gu;
     float g[8], u[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(row + v * 8), g);
-    unpack8(*reinterpret_cast<const uint4*>(row + F + v * 8), u);
+    unpack8(*reinterpret_cast<const uint4*>(g_ + t * ldg + v * 8), g);
+    unpack8(*reinterpret_cast<const uint4*>(u_ + t * ldu + v * 8), u);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = g[j] / (1.f + __expf(-g[j])) * u[j];
     *reinterpret_cast<uint4*>(h + t * F + v * 8) = pack8(o);
@@ -272,18 +272,19 @@ swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restric
 }
 
 __global__ void __launch_bounds__(256)
-swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ gu,
-                  __nv_bfloat16* __restrict__ dgu, long long T, int F, long long ld_gu, long long ld_dgu) {
+swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ g_,
+                  const __nv_bfloat16* __restrict__ u_, __nv_bfloat16* __restrict__ dg_,
+                  __nv_bfloat16* __restrict__ du_, long long T, int F, long long ldg, long long ldu, long long lddg,
+                  long long lddu) {
   const int vpr = F >> 3;
   const long long total = T * vpr;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long t = i / vpr;
     const int v = (int)(i - t * vpr);
-    const __nv_bfloat16* row = gu + t * ld_gu;
     float g[8], u[8], d[8], dg[8], du[8];
-    unpack8(*reinterpret_cast<const uint4*>(row + v * 8), g);
-    unpack8(*reinterpret_cast<const uint4*>(row + F + v * 8), u);
+    unpack8(*reinterpret_cast<const uint4*>(g_ + t * ldg + v * 8), g);
+    unpack8(*reinterpret_cast<const uint4*>(u_ + t * ldu + v * 8), u);
     unpack8(*reinterpret_cast<const uint4*>(dh + t * F + v * 8), d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -292,30 +293,32 @@ swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __r
       du[j] = d[j] * silu;
       dg[j] = d[j] * u[j] * (sg + silu * (1.f - sg));
     }
-    __nv_bfloat16* orow = dgu + t * ld_dgu;
-    *reinterpret_cast<uint4*>(orow + v * 8) = pack8(dg);
-    *reinterpret_cast<uint4*>(orow + F + v * 8) = pack8(du);
+    *reinterpret_cast<uint4*>(dg_ + t * lddg + v * 8) = pack8(dg);
+    *reinterpret_cast<uint4*>(du_ + t * lddu + v * 8) = pack8(du);
   }
 }
 
-cudaError_t swiglu_fwd(const void* gu, void* h, long long T, int F, long long ld_gu, int num_sms,
-                       cudaStream_t stream) {
+cudaError_t swiglu_fwd(const void* g, const void* u, void* h, long long T, int F, long long ldg, long long ldu,
+                       int num_sms, cudaStream_t stream) {
   if (T == 0) return cudaSuccess;
-  if (F % 8 != 0 || ld_gu % 8 != 0) return cudaErrorInvalidValue;
+  if (F % 8 != 0 || ldg % 8 != 0 || ldu % 8 != 0) return cudaErrorInvalidValue;
   long long blocks = (T * (F / 8) + 255) / 256;
   int grid = (int)(blocks < (long long)num_sms * 16 ? blocks : (long long)num_sms * 16);
-  swiglu_fwd_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)gu, (__nv_bfloat16*)h, T, F, ld_gu);
+  swiglu_fwd_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)u, (__nv_bfloat16*)h, T,
+                                               F, ldg, ldu);
   return cudaGetLastError();
 }
 
-cudaError_t swiglu_bwd(const void* dh, const void* gu, void* dgu, long long T, int F, long long ld_gu,
-                       long long ld_dgu, int num_sms, cudaStream_t stream) {
+cudaError_t swiglu_bwd(const void* dh, const void* g, const void* u, void* dg, void* du, long long T, int F,
+                       long long ldg, long long ldu, long long lddg, long long lddu, int num_sms,
+                       cudaStream_t stream) {
   if (T == 0) return cudaSuccess;
-  if (F % 8 != 0 || ld_gu % 8 != 0 || ld_dgu % 8 != 0) return cudaErrorInvalidValue;
+  if (F % 8 != 0 || ldg % 8 != 0 || ldu % 8 != 0 || lddg % 8 != 0 || lddu % 8 != 0) return cudaErrorInvalidValue;
   long long blocks = (T * (F / 8) + 255) / 256;
   int grid = (int)(blocks < (long long)num_sms * 16 ? blocks : (long long)num_sms * 16);
-  swiglu_bwd_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)dh, (const __nv_bfloat16*)gu,
-                                               (__nv_bfloat16*)dgu, T, F, ld_gu, ld_dgu);
+  swiglu_bwd_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)dh, (const __nv_bfloat16*)g,
+                                               (const __nv_bfloat16*)u, (__nv_bfloat16*)dg, (__nv_bfloat16*)du, T, F,
+                                               ldg, ldu, lddg, lddu);
   return cudaGetLastError();
 }
 

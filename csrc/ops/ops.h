@@ -11,9 +11,11 @@ cudaError_t rmsnorm_bwd(const void* dy, const void* x, const void* w, const floa
 cudaError_t rope_inplace(void* x, const float* cos_t, const float* sin_t, const int* positions, long long T,
                          int nheads, int D, long long token_stride, int seq_len, bool backward, int num_sms,
                          cudaStream_t stream);
-cudaError_t swiglu_fwd(const void* gu, void* h, long long T, int F, long long ld_gu, int num_sms, cudaStream_t stream);
-cudaError_t swiglu_bwd(const void* dh, const void* gu, void* dgu, long long T, int F, long long ld_gu,
-                       long long ld_dgu, int num_sms, cudaStream_t stream);
+cudaError_t swiglu_fwd(const void* g, const void* u, void* h, long long T, int F, long long ldg, long long ldu,
+                       int num_sms, cudaStream_t stream);
+cudaError_t swiglu_bwd(const void* dh, const void* g, const void* u, void* dg, void* du, long long T, int F,
+                       long long ldg, long long ldu, long long lddg, long long lddu, int num_sms,
+                       cudaStream_t stream);
 cudaError_t cross_entropy_fwd_bwd(void* logits, const long long* labels, float* loss_rows, float* lse_rows, int n,
                                   int V, long long ld, int ignore_index, const float* scale_ptr, float scale_val,
                                   bool write_grad, cudaStream_t stream);

@@ -1,0 +1,217 @@
+"""Numerics of every sm_100a kernel against a plain PyTorch fp32 reference of the same op."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+def _close(a, b, rtol, atol, what=""):
+    a, b = a.float(), b.float()
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    bad = (err > tol).sum().item()
+    assert bad == 0, f"{what}: {bad}/{a.numel()} mismatches, max err {err.max().item():.4g}, max ref {b.abs().max().item():.4g}"
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 512, 128), (1000, 776, 328), (4096, 4096, 1024), (77, 136, 72)])
+@pytest.mark.parametrize("bias", [False, True])
+def test_linear_fwd_bwd(M, N, K, bias):
+    from torchacc_b200.ops.linear import linear
+    from torchacc_b200 import _native as nat
+    assert nat.available()
+    torch.manual_seed(0)
+    x = (torch.randn(M, K, device=_dev()) * 0.5).bfloat16().requires_grad_()
+    w = (torch.randn(N, K, device=_dev()) * 0.1).bfloat16().requires_grad_()
+    b = (torch.randn(N, device=_dev())).bfloat16().requires_grad_() if bias else None
+    n0 = nat.LAUNCHES
+    y = linear(x, w, b)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    assert nat.LAUNCHES - n0 >= 3, "native GEMM was not used"
+    xf, wf = x.detach().float().requires_grad_(), w.detach().float().requires_grad_()
+    bf = b.detach().float().requires_grad_() if bias else None
+    yr = F.linear(xf, wf, bf)
+    yr.backward(dy.float())
+    _close(y, yr, 1e-2, 1e-2 * math.sqrt(K) * 0.05 + 1e-2, "y")
+    _close(x.grad, xf.grad, 2e-2, 2e-2 * math.sqrt(N) * 0.1 + 1e-2, "dx")
+    _close(w.grad, wf.grad, 2e-2, 2e-2 * math.sqrt(M) * 0.5 + 1e-2, "dw")
+    if bias:
+        _close(b.grad, bf.grad, 2e-2, 0.5, "db")
+
+
+def test_gemm_accumulate_into_view():
+    from torchacc_b200.ops.linear import gemm
+    torch.manual_seed(1)
+    a = torch.randn(512, 256, device=_dev()).bfloat16()
+    b = torch.randn(384, 256, device=_dev()).bfloat16()
+    flat = torch.zeros(384 * 512 + 64, device=_dev(), dtype=torch.bfloat16)
+    view = flat[64:].view(512, 384)
+    gemm(a, b, out=view)
+    gemm(a, b, out=view, accumulate=True)
+    ref = 2 * (a.float() @ b.float().t())
+    _close(view, ref, 2e-2, 0.5, "accumulate")
+    out32 = torch.zeros(512, 384, device=_dev(), dtype=torch.float32)
+    gemm(a, b, out=out32)
+    _close(out32, ref / 2, 1e-3, 1e-2, "fp32 out")
+
+
+@pytest.mark.parametrize("H", [256, 4096, 8192, 1000 * 8])
+@pytest.mark.parametrize("residual", [False, True])
+def test_rmsnorm(H, residual):
+    from torchacc_b200.ops.rmsnorm import rmsnorm, rmsnorm_ref
+    torch.manual_seed(0)
+    T = 333
+    x = torch.randn(T, H, device=_dev()).bfloat16().requires_grad_()
+    r = torch.randn(T, H, device=_dev()).bfloat16().requires_grad_() if residual else None
+    w = (1 + 0.1 * torch.randn(H, device=_dev())).bfloat16().requires_grad_()
+    y, h = rmsnorm(x, w, 1e-5, r)
+    dy = torch.randn_like(y)
+    dh = torch.randn_like(y) if residual else None
+    if residual:
+        torch.autograd.backward([y, h], [dy, dh])
+    else:
+        y.backward(dy)
+    xf = x.detach().float().requires_grad_()
+    rf = r.detach().float().requires_grad_() if residual else None
+    wf = w.detach().float().requires_grad_()
+    hf = xf + rf if residual else xf
+    if residual:
+        hf = hf.bfloat16().float() + (hf - hf.detach())  # reference normalises the bf16-rounded stream too
+    yr = hf * torch.rsqrt(hf.pow(2).mean(-1, keepdim=True) + 1e-5) * wf
+    if residual:
+        torch.autograd.backward([yr, hf], [dy.float(), dh.float()])
+    else:
+        yr.backward(dy.float())
+    _close(y, yr, 2e-2, 2e-2, "y")
+    _close(x.grad, xf.grad, 3e-2, 3e-2, "dx")
+    _close(w.grad, wf.grad, 3e-2, 0.3, "dw")
+    if residual:
+        _close(r.grad, rf.grad, 3e-2, 3e-2, "dres")
+
+
+def test_rope_qkv_inplace_matches_reference():
+    from torchacc_b200.ops.rope import rope_qkv_, rope_tables, _rope_ref
+    torch.manual_seed(0)
+    B, S, hq, hk, D = 2, 96, 8, 2, 128
+    T = B * S
+    cos, sin = rope_tables(256, D, 500000.0, _dev())
+    qkv0 = torch.randn(T, (hq + 2 * hk) * D, device=_dev()).bfloat16()
+    src = qkv0.clone().requires_grad_()
+    qkv = rope_qkv_(src * 1.0, hq, hk, D, cos, sin, None, S)
+    pos = torch.arange(T, device=_dev()) % S
+    q_ref = _rope_ref(qkv0[:, :hq * D].reshape(T, hq, D), cos, sin, pos, 1.0)
+    k_ref = _rope_ref(qkv0[:, hq * D:(hq + hk) * D].reshape(T, hk, D), cos, sin, pos, 1.0)
+    _close(qkv[:, :hq * D].reshape(T, hq, D), q_ref, 1e-2, 1e-2, "q")
+    _close(qkv[:, hq * D:(hq + hk) * D].reshape(T, hk, D), k_ref, 1e-2, 1e-2, "k")
+    assert torch.equal(qkv[:, (hq + hk) * D:], qkv0[:, (hq + hk) * D:])
+    g = torch.randn_like(qkv)
+    qkv.backward(g)
+    gq = _rope_ref(g[:, :hq * D].reshape(T, hq, D), cos, sin, pos, -1.0)
+    _close(src.grad[:, :hq * D].reshape(T, hq, D), gq, 1e-2, 1e-2, "dq")
+    assert torch.equal(src.grad[:, (hq + hk) * D:], g[:, (hq + hk) * D:])
+    # explicit positions
+    p = torch.randint(0, 200, (T,), device=_dev(), dtype=torch.int32)
+    q2 = rope_qkv_(qkv0.clone(), hq, hk, D, cos, sin, p, S)
+    _close(q2[:, :hq * D].reshape(T, hq, D), _rope_ref(qkv0[:, :hq * D].reshape(T, hq, D), cos, sin, p, 1.0), 1e-2, 1e-2)
+
+
+def test_swiglu():
+    from torchacc_b200.ops.swiglu import swiglu, swiglu_separate
+    torch.manual_seed(0)
+    T, Fd = 300, 1408
+    gu = torch.randn(T, 2 * Fd, device=_dev()).bfloat16().requires_grad_()
+    h = swiglu(gu)
+    dh = torch.randn_like(h)
+    h.backward(dh)
+    guf = gu.detach().float().requires_grad_()
+    hr = F.silu(guf[:, :Fd]) * guf[:, Fd:]
+    hr.backward(dh.float())
+    _close(h, hr, 1e-2, 1e-2, "h")
+    _close(gu.grad, guf.grad, 2e-2, 2e-2, "dgu")
+    g = torch.randn(T, Fd, device=_dev()).bfloat16().requires_grad_()
+    u = torch.randn(T, Fd, device=_dev()).bfloat16().requires_grad_()
+    h2 = swiglu_separate(g, u)
+    h2.backward(dh)
+    gf, uf = g.detach().float().requires_grad_(), u.detach().float().requires_grad_()
+    (F.silu(gf) * uf).backward(dh.float())
+    _close(g.grad, gf.grad, 2e-2, 2e-2, "dg")
+    _close(u.grad, uf.grad, 2e-2, 2e-2, "du")
+
+
+@pytest.mark.parametrize("V", [1024, 128256, 50264])
+def test_cross_entropy(V):
+    from torchacc_b200.ops.cross_entropy import cross_entropy
+    torch.manual_seed(0)
+    n = 64
+    logits = (torch.randn(n, V, device=_dev()) * 2).bfloat16().requires_grad_()
+    labels = torch.randint(0, V, (n,), device=_dev())
+    labels[::7] = -100
+    loss = cross_entropy(logits, labels)
+    loss.backward()
+    lf = logits.detach().float().requires_grad_()
+    lr = F.cross_entropy(lf, labels, ignore_index=-100)
+    lr.backward()
+    assert abs(float(loss) - float(lr)) < 2e-3 * max(1.0, abs(float(lr)))
+    _close(logits.grad, lf.grad, 2e-2, 2e-4, "dlogits")
+
+
+def test_fused_linear_cross_entropy():
+    from torchacc_b200.ops.cross_entropy import fused_linear_cross_entropy
+    torch.manual_seed(0)
+    T, H, V = 700, 512, 4096
+    h = torch.randn(T, H, device=_dev()).bfloat16().requires_grad_()
+    w = (torch.randn(V, H, device=_dev()) * 0.05).bfloat16().requires_grad_()
+    labels = torch.randint(0, V, (T,), device=_dev())
+    labels[:50] = -100
+    loss = fused_linear_cross_entropy(h, w, labels, chunk_tokens=256)
+    loss.backward()
+    hf, wf = h.detach().float().requires_grad_(), w.detach().float().requires_grad_()
+    lr = F.cross_entropy(F.linear(hf, wf), labels, ignore_index=-100)
+    lr.backward()
+    assert abs(float(loss) - float(lr)) < 5e-3 * max(1.0, abs(float(lr))), (float(loss), float(lr))
+    _close(h.grad, hf.grad, 5e-2, 5e-5, "dh")
+    _close(w.grad, wf.grad, 5e-2, 5e-5, "dw")
+
+
+@pytest.mark.parametrize("gdtype", [torch.bfloat16, torch.float32])
+def test_fused_adamw_matches_torch(gdtype):
+    from torchacc_b200.ops.optim import FusedAdamW
+    torch.manual_seed(0)
+    n = 100003
+    p0 = torch.randn(n, device=_dev())
+    p = torch.nn.Parameter(p0.clone())
+    lp = torch.zeros(n, device=_dev(), dtype=torch.bfloat16)
+    p._tb_lp_shard = lp
+    pr = torch.nn.Parameter(p0.clone())
+    opt = FusedAdamW([p], lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
+    ref = torch.optim.AdamW([pr], lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
+    for _ in range(4):
+        g = torch.randn(n, device=_dev()).to(gdtype)
+        p._tb_grad = g
+        pr.grad = g.float()
+        opt.step()
+        ref.step()
+    _close(p, pr, 1e-4, 1e-5, "param")
+    _close(lp, pr, 1e-2, 1e-2, "bf16 copy")
+
+
+def test_sqnorm_and_clip_scale():
+    from torchacc_b200.ops.optim import grad_sqnorm, scale_
+    torch.manual_seed(0)
+    gs = [torch.randn(12345, device=_dev()).bfloat16(), torch.randn(777, device=_dev())]
+    stat = grad_sqnorm(gs)
+    ref = sum((g.float() ** 2).sum() for g in gs)
+    assert abs(float(stat[0]) - float(ref)) < 1e-3 * float(ref)
+    assert float(stat[1]) == 0.0
+    gs[1][5] = float("inf")
+    assert float(grad_sqnorm(gs)[1]) == 1.0
+    t = torch.ones(1000, device=_dev())
+    scale_(t, torch.tensor([0.25], device=_dev()))
+    assert torch.allclose(t, torch.full_like(t, 0.25))

@@ -1,0 +1,117 @@
+"""Linear layers on the hand-written tcgen05 GEMM (csrc/gemm/gemm_bf16.cu).
+
+``linear(x, w, bias)`` computes ``x @ w.T + bias`` with three launches of the same kernel:
+forward (K-major/K-major), dgrad (K-major/MN-major) and wgrad (MN-major/MN-major) -- no transposed copies.
+When the weight carries a ``_tb_grad_view`` (installed by the FSDP/DP engines) the weight gradient is written
+or accumulated directly into that flat-buffer slice by the GEMM epilogue and autograd sees ``None``
+(gradient-accumulation fusion), so no extra ``grad += `` pass over the weights happens.
+
+The reference reaches cuBLAS through ``nn.Linear`` here (SURVEY 2.4a "Dense GEMMs").
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from .. import _native as nat
+
+_CLUSTER = int(os.environ.get("TORCHACC_B200_GEMM_CLUSTER", "2"))
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_major: bool = False,
+         out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, accumulate: bool = False,
+         out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """``D[M,N] (+)= A_op[M,K] @ B_op[N,K]^T (+ bias)`` on 2-D bf16 tensors (last dim contiguous).
+
+    ``a`` is ``[M,K]`` (or ``[K,M]`` when ``a_mn_major``); ``b`` is ``[N,K]`` (or ``[K,N]`` when ``b_mn_major``).
+    """
+    assert a.dim() == 2 and b.dim() == 2
+    if a_mn_major:
+        K, M = a.shape
+    else:
+        M, K = a.shape
+    if b_mn_major:
+        Kb, N = b.shape
+    else:
+        N, Kb = b.shape
+    assert K == Kb, f"reduction dims differ: {K} vs {Kb}"
+    if out is None:
+        assert not accumulate
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    if not nat.use_native(a, b):
+        A = a.t() if a_mn_major else a
+        B = b if b_mn_major else b.t()
+        r = A.float() @ B.float()
+        if bias is not None:
+            r = r + bias.float()
+        if accumulate:
+            out.add_(r.to(out.dtype))
+        else:
+            out.copy_(r.to(out.dtype))
+        return out
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16, "native GEMM is bf16 x bf16"
+    assert a.stride(1) == 1 and b.stride(1) == 1 and out.stride(1) == 1
+    assert a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0, "row pitch must be a multiple of 16 bytes (TMA)"
+    assert out.dtype in (torch.bfloat16, torch.float32)
+    if bias is not None:
+        assert bias.dtype == torch.bfloat16 and bias.is_contiguous()
+    L = nat.require()
+    nat.check(
+        L.tb_gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), nat.ptr(bias), M, N, K, a.stride(0), b.stride(0),
+                       out.stride(0), int(a_mn_major), int(b_mn_major), int(out.dtype == torch.float32),
+                       int(accumulate), _CLUSTER, nat.num_sms(), nat.stream()), "tb_gemm_bf16")
+    nat.count_launch()
+    return out
+
+
+class _LinearFn(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        if x2.stride(-1) != 1 or x2.stride(0) % 8 != 0:
+            x2 = x2.contiguous()
+        y = gemm(x2, w, bias=bias)
+        ctx.save_for_backward(x2, w)
+        ctx.has_bias = bias is not None
+        ctx.x_shape = shp
+        return y.view(*shp[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if dy2.stride(-1) != 1 or dy2.stride(0) % 8 != 0:
+            dy2 = dy2.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(dy2, w, b_mn_major=True).view(ctx.x_shape)
+        if ctx.needs_input_grad[1]:
+            view = getattr(w, "_tb_grad_view", None)
+            if view is not None:
+                acc = bool(getattr(w, "_tb_grad_ready", False))
+                gemm(dy2, x2, a_mn_major=True, b_mn_major=True, out=view, accumulate=acc)
+                w._tb_grad_ready = True
+            else:
+                dw = gemm(dy2, x2, a_mn_major=True, b_mn_major=True)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy2.float().sum(0).to(dy2.dtype)
+        return dx, dw, db
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Drop-in for ``F.linear`` (bf16 CUDA tensors go through the tcgen05 GEMM)."""
+    if x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and nat.use_native(x, w):
+        return _LinearFn.apply(x, w, bias)
+    return F.linear(x, w, bias)
+
+
+class Linear(torch.nn.Linear):
+    """``nn.Linear`` whose forward/backward run on the tcgen05 GEMM."""
+
+    def forward(self, x):
+        return linear(x, self.weight, self.bias)
