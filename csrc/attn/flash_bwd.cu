@@ -1,0 +1,484 @@
+// FlashAttention backward on tcgen05 / TMEM / TMA for sm_100a.
+//
+// One CTA per (128-key tile, kv head, batch); it loops over the q heads of the GQA group and over the query tiles
+// that can see this key tile, so dK/dV are accumulated in TMEM with no atomics.  The score tile is computed
+// TRANSPOSED (S^T = K Q^T: TMEM lanes = keys, columns = queries), which lets every later GEMM read its operands in
+// place:
+//   (a) S^T  = K  Q^T    A = K  (smem, K-major)          B = Q  (smem, K-major)      -> TMEM R0
+//   (b) dP^T = V  dO^T   A = V  (smem, K-major)          B = dO (smem, K-major)      -> TMEM R1
+//   softmax warps (thread = key row):  P^T = exp2(S^T*scale - LSE), dS^T = P^T o (dP^T - delta) * scale
+//        P^T  -> TMEM R0 (bf16, aliases S^T)      dS^T -> smem (bf16, 128B-swizzled rows)
+//   (e) dQ   = dS K      A = dS^T smem read MN-major     B = K  (smem, MN-major)     -> TMEM R1 (aliases dP^T)
+//   (c) dV  += P^T dO    A = P^T (TMEM)                  B = dO (smem, MN-major)     -> TMEM R2
+//   (d) dK  += dS^T Q    A = dS^T (smem, K-major)        B = Q  (smem, MN-major)     -> TMEM R3
+// dQ is reduced across key tiles with fp32 vector red.global.add into a scratch buffer (converted afterwards).
+// Q/dO tiles stream through a 2-stage TMA ring; K/V stay resident.  The tensor pipe executes MMAs in issue order,
+// so the TMEM/smem aliases above need no extra barriers beyond "softmax done" / "dQ read out".
+//
+// Reference parity: FA2 backward reached by reference torchacc/ops/flash_attn.py:56,152,206,252,301.
+#include <math.h>
+
+#include "../common/ptx.cuh"
+#include "../common/tensormap.h"
+#include "attn.h"
+
+namespace tb {
+
+constexpr int kTile = 128;
+constexpr int kBwdThreads = 256;
+constexpr int kQStages = 2;
+
+struct BwdArgs {
+  const float* lse;
+  const float* delta;
+  float* dq_acc;
+  __nv_bfloat16* dk;
+  __nv_bfloat16* dv;
+  const int* cu_q;
+  const int* cu_k;
+  int B, Sq, Sk, Hq, Hk;
+  long long Tq;
+  long long dk_ts, dv_ts;
+  float scale_log2, scale;
+  int causal, wl, wr;
+};
+
+template <int D>
+struct BwdSmem {
+  static constexpr int kChunks = D / 64;
+  static constexpr int kTileBytes = kTile * D * 2;
+  static constexpr int kK = 0;
+  static constexpr int kV = kK + kTileBytes;
+  static constexpr int kQ = kV + kTileBytes;
+  static constexpr int kDO = kQ + kQStages * kTileBytes;
+  static constexpr int kDS = kDO + kQStages * kTileBytes;
+  static constexpr int kStat = kDS + kTile * kTile * 2;  // lse2[128], delta[128]
+  static constexpr int kBar = kStat + 2 * kTile * 4;
+  static constexpr int kTotal = kBar + 128 + 1024;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int D>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+                 const BwdArgs args) {
+  using S = BwdSmem<D>;
+  constexpr int kChunks = S::kChunks;
+  constexpr uint32_t kIdescST = make_idesc_f16(kTile, kTile, Major::K, Major::K, true);   // (a), (b)
+  constexpr uint32_t kIdescDQ = make_idesc_f16(kTile, D, Major::MN, Major::MN, true);     // (e)
+  constexpr uint32_t kIdescDKV = make_idesc_f16(kTile, D, Major::K, Major::MN, true);     // (c), (d)
+  constexpr uint32_t R0 = 0, R1 = 128, R2 = 256, R3 = 384;
+
+  const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const uint32_t lane = lane_id();
+  const int b = blockIdx.z, hk = blockIdx.y, jt = blockIdx.x;
+  const int group = args.Hq / args.Hk;
+  const int q_start = args.cu_q ? args.cu_q[b] : b * args.Sq;
+  const int q_len = args.cu_q ? (args.cu_q[b + 1] - q_start) : args.Sq;
+  const int k_start = args.cu_k ? args.cu_k[b] : b * args.Sk;
+  const int k_len = args.cu_k ? (args.cu_k[b + 1] - k_start) : args.Sk;
+  const int n0 = jt * kTile;
+  if (n0 >= k_len) return;
+
+  // query rows that can see keys [n0, n0+127]
+  const int shift = k_len - q_len;
+  int wr_eff = args.wr;
+  if (args.causal) wr_eff = (args.wr < 0) ? 0 : min(args.wr, 0);
+  const int n_last = min(n0 + kTile, k_len) - 1;
+  const int i_lo = (wr_eff < 0) ? 0 : max(0, n0 - shift - wr_eff);
+  const int i_hi = (args.wl < 0) ? (q_len - 1) : min(q_len - 1, n_last - shift + args.wl);
+  const int it_lo = i_lo / kTile;
+  const int n_qt = (i_hi < i_lo) ? 0 : (i_hi / kTile - it_lo + 1);
+  const int n_iter = n_qt * group;
+
+  const int key = n0 + (int)(((warp_idx & 3) * 32) + lane);  // key index owned by a softmax thread
+
+  if (n_iter == 0) {  // no query sees these keys: dK = dV = 0
+    for (int r = threadIdx.x; r < min(kTile, k_len - n0); r += blockDim.x) {
+      __nv_bfloat16* pk = args.dk + (long long)(k_start + n0 + r) * args.dk_ts + (long long)hk * D;
+      __nv_bfloat16* pv = args.dv + (long long)(k_start + n0 + r) * args.dv_ts + (long long)hk * D;
+      for (int d = 0; d < D; ++d) { pk[d] = __float2bfloat16(0.f); pv[d] = __float2bfloat16(0.f); }
+    }
+    return;
+  }
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sK = base + S::kK, sV = base + S::kV, sQ = base + S::kQ, sDO = base + S::kDO, sDS = base + S::kDS;
+  float* stat = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + S::kStat);
+  const uint32_t bar = base + S::kBar;
+  const uint32_t kv_full = bar;
+  auto qdo_full = [&](int s) { return bar + 8u * (1 + s); };
+  auto qdo_empty = [&](int s) { return bar + 8u * (3 + s); };
+  const uint32_t sdp_full = bar + 8u * 5, pds_ready = bar + 8u * 6, dq_full = bar + 8u * 7, r1_free = bar + 8u * 8;
+  const uint32_t dkv_full = bar + 8u * 9, tmem_slot = bar + 8u * 10;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < kQStages; ++s) { mbar_init(qdo_full(s), 1); mbar_init(qdo_empty(s), 1); }
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_ready, 4);
+    mbar_init(dq_full, 1);
+    mbar_init(r1_free, 4);
+    mbar_init(dkv_full, 1);
+    fence_mbar_init();
+  }
+  if (warp_idx == 2) tmem_alloc<1>(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // iteration -> (q head, q tile): heads outer, tiles inner
+  auto iter_head = [&](int it) { return hk * group + it / n_qt; };
+  auto iter_m0 = [&](int it) { return (it_lo + it % n_qt) * kTile; };
+
+  if (warp_idx == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(kv_full, 2 * S::kTileBytes);
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        tma_load_3d(sK + c * 16384, &tmap_k, kv_full, c * 64, hk, k_start + n0);
+        tma_load_3d(sV + c * 16384, &tmap_v, kv_full, c * 64, hk, k_start + n0);
+      }
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kQStages;
+        mbar_wait(qdo_empty(s), ((it / kQStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(qdo_full(s), 2 * S::kTileBytes);
+        const int h = iter_head(it), row0 = q_start + iter_m0(it);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          tma_load_3d(sQ + s * S::kTileBytes + c * 16384, &tmap_q, qdo_full(s), c * 64, h, row0);
+          tma_load_3d(sDO + s * S::kTileBytes + c * 16384, &tmap_do, qdo_full(s), c * 64, h, row0);
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      mbar_wait(kv_full, 0);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kQStages;
+        const uint32_t q_s = sQ + s * S::kTileBytes, do_s = sDO + s * S::kTileBytes;
+        mbar_wait(qdo_full(s), (it / kQStages) & 1);
+        tc_fence_after();
+        // (a) S^T = K Q^T -> R0   (in-order pipe: runs after (c) of the previous iteration consumed P^T in R0)
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_ss_f16<1>(tmem_base + R0, desc_kmajor_sw128(sK + (kk / 4) * 16384, kk % 4),
+                         desc_kmajor_sw128(q_s + (kk / 4) * 16384, kk % 4), kIdescST, kk != 0);
+        // (b) dP^T = V dO^T -> R1 (needs dQ of the previous iteration read out of R1)
+        mbar_wait(r1_free, (it & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_ss_f16<1>(tmem_base + R1, desc_kmajor_sw128(sV + (kk / 4) * 16384, kk % 4),
+                         desc_kmajor_sw128(do_s + (kk / 4) * 16384, kk % 4), kIdescST, kk != 0);
+        umma_commit(sdp_full);
+        // softmax warps: P^T -> R0 (TMEM), dS^T -> smem
+        mbar_wait(pds_ready, it & 1);
+        tc_fence_after();
+        // (e) dQ = dS K -> R1
+#pragma unroll
+        for (int kk = 0; kk < kTile / 16; ++kk)
+          umma_ss_f16<1>(tmem_base + R1, desc_mnmajor_sw128(sDS, kk, 16384), desc_mnmajor_sw128(sK, kk, 16384),
+                         kIdescDQ, kk != 0);
+        umma_commit(dq_full);
+        // (c) dV += P^T dO   (A from TMEM: 16 bf16 of K = 8 columns per step)
+#pragma unroll
+        for (int kk = 0; kk < kTile / 16; ++kk)
+          umma_ts_f16(tmem_base + R2, tmem_base + R0 + kk * 8, desc_mnmajor_sw128(do_s, kk, 16384), kIdescDKV,
+                      (it | kk) != 0);
+        // (d) dK += dS^T Q
+#pragma unroll
+        for (int kk = 0; kk < kTile / 16; ++kk)
+          umma_ss_f16<1>(tmem_base + R3, desc_kmajor_sw128(sDS + (kk / 4) * 16384, kk % 4),
+                         desc_mnmajor_sw128(q_s, kk, 16384), kIdescDKV, (it | kk) != 0);
+        umma_commit(qdo_empty(s));
+      }
+      umma_commit(dkv_full);
+    }
+  } else if (warp_idx >= 4) {
+    // ================================ softmax / dS / dQ read-out / epilogue ================================
+    const uint32_t q4 = warp_idx & 3;
+    const int r = q4 * 32 + lane;  // TMEM lane: key row for S^T/dP^T/dV/dK, query row for dQ
+    const uint32_t lane_off = (q4 * 32u) << 16;
+    const float sl2 = args.scale_log2, sc = args.scale;
+    const bool key_ok = key < k_len;
+    // prefetch the statistics of the first query tile
+    float lse_next, delta_next;
+    {
+      const int h = iter_head(0), row = iter_m0(0) + r;
+      const bool ok = row < q_len;
+      const float l = ok ? args.lse[(long long)h * args.Tq + q_start + row] : INFINITY;
+      lse_next = (l == -INFINITY) ? INFINITY : l * 1.4426950408889634f;
+      delta_next = ok ? args.delta[(long long)h * args.Tq + q_start + row] : 0.f;
+    }
+    for (int it = 0; it < n_iter; ++it) {
+      const int h = iter_head(it), m0 = iter_m0(it);
+      // publish this tile's row statistics (all 128 softmax threads finished the previous tile's reads)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      stat[r] = lse_next;
+      stat[kTile + r] = delta_next;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(sdp_full, it & 1);
+      tc_fence_after();
+      // interior tile: every query row of the tile sees every key of the tile -> no per-element mask
+      bool interior = (m0 + kTile <= q_len) && (n0 + kTile <= k_len);
+      if (interior) {
+        const int pos_first = m0 + shift, pos_last = m0 + kTile - 1 + shift;
+        const int hi_first = (wr_eff < 0) ? (k_len - 1) : min(k_len - 1, pos_first + wr_eff);
+        const int lo_last = (args.wl < 0) ? 0 : max(0, pos_last - args.wl);
+        interior = (hi_first >= n0 + kTile - 1) && (lo_last <= n0);
+      }
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32], dpv[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_off + R0 + c * 32, sv);
+        tmem_ld_32x32b_x32(tmem_base + lane_off + R1 + c * 32, dpv);
+        tmem_ld_wait();
+        uint32_t pk[16], dsk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float pv[2], dv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = c * 32 + 2 * i + e;   // query row inside the tile
+            const int qrow = m0 + col;
+            int lo, hi;
+            {
+              const int pos = qrow + shift;
+              hi = (wr_eff < 0) ? (k_len - 1) : min(k_len - 1, pos + wr_eff);
+              lo = (args.wl < 0) ? 0 : max(0, pos - args.wl);
+            }
+            const bool ok = interior || (key_ok && qrow < q_len && key >= lo && key <= hi);
+            const float p = ok ? fast_exp2(fmaf(__uint_as_float(sv[2 * i + e]), sl2, -stat[col])) : 0.f;
+            pv[e] = p;
+            dv[e] = p * (__uint_as_float(dpv[2 * i + e]) - stat[kTile + col]) * sc;
+          }
+          pk[i] = pack_bf16x2(pv[0], pv[1]);
+          dsk[i] = pack_bf16x2(dv[0], dv[1]);
+        }
+        // P^T chunk -> TMEM R0 columns [16c, 16c+16) (S^T columns < 32c+32 of this lane were already read)
+        tmem_st_32x32b_x16(tmem_base + lane_off + R0 + c * 16, pk);
+        // dS^T chunk -> smem row r (keys), 64 bytes = 4 x 16B units, 128B-swizzled
+        const uint32_t row_base = sDS + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t unit = (uint32_t)((c & 1) * 4 + u) ^ (uint32_t)(r & 7);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_base + unit * 16), "r"(dsk[4 * u]),
+                       "r"(dsk[4 * u + 1]), "r"(dsk[4 * u + 2]), "r"(dsk[4 * u + 3])
+                       : "memory");
+        }
+      }
+      tmem_st_wait();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_ready);
+      // prefetch the next tile's statistics while the tensor core works
+      if (it + 1 < n_iter) {
+        const int h2 = iter_head(it + 1), row = iter_m0(it + 1) + r;
+        const bool ok = row < q_len;
+        const float l = ok ? args.lse[(long long)h2 * args.Tq + q_start + row] : INFINITY;
+        lse_next = (l == -INFINITY) ? INFINITY : l * 1.4426950408889634f;
+        delta_next = ok ? args.delta[(long long)h2 * args.Tq + q_start + row] : 0.f;
+      }
+      // dQ tile: lane r = query row m0 + r
+      mbar_wait(dq_full, it & 1);
+      tc_fence_after();
+      const bool qok = (m0 + r) < q_len;
+      float* dqp = args.dq_acc + ((long long)(q_start + m0 + r) * args.Hq + h) * D;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_off + R1 + c * 32, v);
+        tmem_ld_wait();
+        if (qok) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            red_add_v4(dqp + c * 32 + u * 4, __uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]),
+                       __uint_as_float(v[4 * u + 2]), __uint_as_float(v[4 * u + 3]));
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(r1_free);
+    }
+    // ---- epilogue: dV (R2), dK (R3) -> bf16 ----
+    mbar_wait(dkv_full, 0);
+    tc_fence_after();
+    __nv_bfloat16* pdv = args.dv + (long long)(k_start + key) * args.dv_ts + (long long)hk * D;
+    __nv_bfloat16* pdk = args.dk + (long long)(k_start + key) * args.dk_ts + (long long)hk * D;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      __nv_bfloat16* dst = which == 0 ? pdv : pdk;
+      const uint32_t reg = which == 0 ? R2 : R3;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_off + reg + c * 32, v);
+        tmem_ld_wait();
+        if (key_ok) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(v[8 * u + 0]), __uint_as_float(v[8 * u + 1]));
+            w.y = pack_bf16x2(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3]));
+            w.z = pack_bf16x2(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5]));
+            w.w = pack_bf16x2(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7]));
+            *reinterpret_cast<uint4*>(dst + c * 32 + u * 8) = w;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+// delta[h, t] = sum_d dO[t,h,d] * O[t,h,d];  dq_acc[t,h,:] = 0.   One warp per (token, head).
+template <int D>
+__global__ void __launch_bounds__(256)
+bwd_preprocess_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                      float* __restrict__ delta, float* __restrict__ dq_acc, long long Tq, int Hq, long long do_ts) {
+  const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= Tq * Hq) return;
+  const long long t = w / Hq;
+  const int h = (int)(w % Hq);
+  constexpr int kPer = D / 32;  // 4 (D=128) or 2 (D=64) elements per lane
+  const __nv_bfloat16* op = o + (t * Hq + h) * D + lane * kPer;
+  const __nv_bfloat16* dp = dout + t * do_ts + (long long)h * D + lane * kPer;
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < kPer; i += 2) {
+    float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(op + i));
+    float2 g = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dp + i));
+    acc += a.x * g.x + a.y * g.y;
+  }
+  acc = warp_reduce_sum(acc);
+  if (lane == 0) delta[(long long)h * Tq + t] = acc;
+  float* q = dq_acc + (t * Hq + h) * D + lane * kPer;
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) q[i] = 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+bwd_convert_dq_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dq, long long Tq, int HD,
+                      long long dq_ts) {
+  const long long n = Tq * (HD / 4);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long t = i / (HD / 4);
+    const int c = (int)(i % (HD / 4)) * 4;
+    float4 v = *reinterpret_cast<const float4*>(dq_acc + t * HD + c);
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(dq + t * dq_ts + c) = o;
+  }
+}
+
+static CUtensorMap make_map_thd_b(const void* base, long long tokens, int heads, int D, long long ts) {
+  uint64_t dims[3] = {(uint64_t)D, (uint64_t)heads, (uint64_t)tokens};
+  uint64_t strides[2] = {(uint64_t)D * 2, (uint64_t)ts * 2};
+  uint32_t box[3] = {64, 1, 128};
+  return make_tensor_map(base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+template <int D>
+static cudaError_t launch_bwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+                              const CUtensorMap& mdo, const BwdArgs& a, int num_k_tiles, cudaStream_t stream) {
+  using S = BwdSmem<D>;
+  auto kern = flash_bwd_kernel<D>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid(num_k_tiles, a.Hk, a.B);
+  kern<<<grid, kBwdThreads, S::kTotal, stream>>>(mq, mk, mv, mdo, a);
+  return cudaGetLastError();
+}
+
+cudaError_t flash_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                           const float* lse, void* dq, void* dk, void* dv, float* dq_acc, float* delta,
+                           const int* cu_q, const int* cu_k, int B, int Sq, int Sk, int Hq, int Hk, int D,
+                           long long q_ts, long long k_ts, long long v_ts, long long do_ts, float scale, bool causal,
+                           int wl, int wr, long long Tq, long long Tk, long long dq_ts, long long dk_ts,
+                           long long dv_ts, int num_sms, cudaStream_t stream) {
+  if (B == 0 || Tq == 0 || Tk == 0) return cudaSuccess;
+  if (D != 64 && D != 128) return cudaErrorInvalidValue;
+  if (Hq % Hk != 0) return cudaErrorInvalidValue;
+  // 1) delta = rowsum(dO o O), dq_acc = 0
+  {
+    const long long warps = Tq * Hq;
+    const long long blocks = (warps * 32 + 255) / 256;
+    if (D == 128)
+      bwd_preprocess_kernel<128><<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)o,
+                                                                        (const __nv_bfloat16*)dout, delta, dq_acc, Tq,
+                                                                        Hq, do_ts);
+    else
+      bwd_preprocess_kernel<64><<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)o,
+                                                                       (const __nv_bfloat16*)dout, delta, dq_acc, Tq,
+                                                                       Hq, do_ts);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  // 2) main kernel
+  CUtensorMap mq, mk, mv, mdo;
+  try {
+    mq = make_map_thd_b(q, Tq, Hq, D, q_ts);
+    mk = make_map_thd_b(k, Tk, Hk, D, k_ts);
+    mv = make_map_thd_b(v, Tk, Hk, D, v_ts);
+    mdo = make_map_thd_b(dout, Tq, Hq, D, do_ts);
+  } catch (const std::exception& e) {
+    fprintf(stderr, "%s\n", e.what());
+    return cudaErrorInvalidValue;
+  }
+  BwdArgs a;
+  a.lse = lse; a.delta = delta; a.dq_acc = dq_acc;
+  a.dk = (__nv_bfloat16*)dk; a.dv = (__nv_bfloat16*)dv;
+  a.cu_q = cu_q; a.cu_k = cu_k;
+  a.B = B; a.Sq = Sq; a.Sk = Sk; a.Hq = Hq; a.Hk = Hk;
+  a.Tq = Tq;
+  a.dk_ts = dk_ts; a.dv_ts = dv_ts;
+  a.scale = scale;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  a.causal = causal ? 1 : 0;
+  a.wl = wl; a.wr = wr;
+  const int max_k = cu_k ? (int)Tk : Sk;
+  const int num_k_tiles = (max_k + kTile - 1) / kTile;
+  cudaError_t e = (D == 128) ? launch_bwd<128>(mq, mk, mv, mdo, a, num_k_tiles, stream)
+                             : launch_bwd<64>(mq, mk, mv, mdo, a, num_k_tiles, stream);
+  if (e != cudaSuccess) return e;
+  // 3) dq = bf16(dq_acc)
+  {
+    const long long n = Tq * (long long)(Hq * D / 4);
+    long long blocks = (n + 255) / 256;
+    if (blocks > (long long)num_sms * 16) blocks = (long long)num_sms * 16;
+    bwd_convert_dq_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dq_acc, (__nv_bfloat16*)dq, Tq, Hq * D, dq_ts);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+}  // namespace tb

@@ -1,0 +1,412 @@
+// FlashAttention forward on tcgen05 / TMEM / TMA for sm_100a.
+//
+// One CTA per (128-row query tile, q head, batch/sequence).  Warp roles:
+//   warp 0    : TMA producer  -- Q once, then a 2-stage ring of K and V tiles (3-D tensor maps over
+//               [tokens, heads, D], SWIZZLE_128B boxes of 64 x 1 x 128, so strided q/k/v views of a fused QKV
+//               activation are read in place)
+//   warp 1    : MMA issuer    -- S = Q K^T (UMMA 128x128xD, K-major/K-major) into a double-buffered TMEM S tile,
+//               O += P V (UMMA 128xDx128, P K-major from smem, V MN-major) into a TMEM O accumulator
+//   warp 2    : TMEM allocator
+//   warps 4-7 : softmax       -- thread i owns query row i (TMEM lane i): tcgen05.ld the S row, scale/mask, online
+//               max/sum in fp32 with exp2, write P as bf16 into 128B-swizzled smem, lazily rescale O in TMEM only
+//               when the running max moved by more than 2^8 (exact: P and the row sum use the same stale max)
+// S(j+1) is issued before P V(j), so the tensor pipe computes the next score tile while the softmax warps work.
+// Masking: causal (bottom-right aligned), sliding window (left, right), per-sequence lengths (cu_seqlens) and the
+// ragged tail; GQA by mapping q head h to kv head h / (Hq / Hk).
+//
+// Reference parity: torch_xla custom calls / flash-attn FA2 kernels used by reference torchacc/ops/flash_attn.py
+// (mma.sync, sm80-class); SURVEY 2.4a rows "FA2 forward (fixed)", "FA2 varlen".
+#include <math.h>
+
+#include "../common/ptx.cuh"
+#include "../common/tensormap.h"
+#include "attn.h"
+
+namespace tb {
+
+constexpr int kBM = 128;  // query rows per CTA
+constexpr int kBN = 128;  // keys per tile
+constexpr int kKVStages = 2;
+constexpr int kFwdThreads = 256;
+constexpr float kRescaleThreshold = 8.0f;  // log2 domain
+
+struct FwdArgs {
+  __nv_bfloat16* o;
+  float* lse;
+  const int* cu_q;
+  const int* cu_k;
+  int B, Sq, Sk, Hq, Hk;
+  long long o_ts;
+  long long Tq;
+  float scale_log2;
+  int causal, wl, wr;
+  int num_q_tiles;
+};
+
+template <int D>
+struct FwdSmem {
+  static constexpr int kChunks = D / 64;
+  static constexpr int kQBytes = kBM * D * 2;
+  static constexpr int kKBytes = kBN * D * 2;
+  static constexpr int kPBytes = kBM * kBN * 2;
+  static constexpr int kQ = 0;
+  static constexpr int kK = kQ + kQBytes;
+  static constexpr int kV = kK + kKVStages * kKBytes;
+  static constexpr int kP = kV + kKVStages * kKBytes;
+  static constexpr int kBar = kP + kPBytes;
+  static constexpr int kTotal = kBar + 256 + 1024;
+};
+
+// visible key range [lo, hi] for query row `row` (0-based inside its sequence)
+__device__ __forceinline__ void key_bounds(int row, int q_len, int k_len, int causal, int wl, int wr, int& lo, int& hi) {
+  const int pos = row + (k_len - q_len);
+  int r = wr;
+  if (causal) r = (wr < 0) ? 0 : min(wr, 0);
+  hi = (r < 0) ? (k_len - 1) : min(k_len - 1, pos + r);
+  lo = (wl < 0) ? 0 : max(0, pos - wl);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                 const __grid_constant__ CUtensorMap tmap_v, const FwdArgs args) {
+  using S = FwdSmem<D>;
+  constexpr int kChunks = S::kChunks;
+  constexpr uint32_t kIdescS = make_idesc_f16(kBM, kBN, Major::K, Major::K, true);
+  constexpr uint32_t kIdescO = make_idesc_f16(kBM, D, Major::K, Major::MN, true);
+  constexpr uint32_t kTmemS0 = 0, kTmemO = 2 * kBN;
+
+  const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const uint32_t lane = lane_id();
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int hk = h / (args.Hq / args.Hk);
+  const int tile = args.num_q_tiles - 1 - (int)blockIdx.x;  // heavy (late) causal tiles first
+  const int q_start = args.cu_q ? args.cu_q[b] : b * args.Sq;
+  const int q_len = args.cu_q ? (args.cu_q[b + 1] - q_start) : args.Sq;
+  const int k_start = args.cu_k ? args.cu_k[b] : b * args.Sk;
+  const int k_len = args.cu_k ? (args.cu_k[b + 1] - k_start) : args.Sk;
+  const int m0 = tile * kBM;
+  if (m0 >= q_len) return;
+
+  // KV tile range touched by this query tile
+  int lo_first, hi_first, lo_last, hi_last;
+  const int last_row = min(m0 + kBM, q_len) - 1;
+  key_bounds(m0, q_len, k_len, args.causal, args.wl, args.wr, lo_first, hi_first);
+  key_bounds(last_row, q_len, k_len, args.causal, args.wl, args.wr, lo_last, hi_last);
+  const int kmin = lo_first, kmax = hi_last;
+  const int j_lo = kmin / kBN;
+  const int j_hi = (kmax < 0 || kmax < kmin) ? j_lo : (kmax / kBN + 1);
+  const int n_tiles = j_hi - j_lo;
+
+  if (n_tiles <= 0) {  // nothing visible: O = 0, LSE = -inf
+    for (int r = threadIdx.x; r < min(kBM, q_len - m0); r += blockDim.x) {
+      __nv_bfloat16* op = args.o + (long long)(q_start + m0 + r) * args.o_ts + (long long)h * D;
+      for (int d = 0; d < D; ++d) op[d] = __float2bfloat16(0.f);
+      args.lse[(long long)h * args.Tq + q_start + m0 + r] = -INFINITY;
+    }
+    return;
+  }
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base + S::kQ, sK = base + S::kK, sV = base + S::kV, sP = base + S::kP;
+  const uint32_t bar = base + S::kBar;
+  const uint32_t q_full = bar;
+  auto k_full = [&](int s) { return bar + 8u * (1 + s); };
+  auto v_full = [&](int s) { return bar + 8u * (1 + kKVStages + s); };
+  auto kv_empty = [&](int s) { return bar + 8u * (1 + 2 * kKVStages + s); };
+  auto s_full = [&](int i) { return bar + 8u * (1 + 3 * kKVStages + i); };
+  auto s_free = [&](int i) { return bar + 8u * (3 + 3 * kKVStages + i); };
+  const uint32_t p_ready = bar + 8u * (5 + 3 * kKVStages);
+  const uint32_t o_done = bar + 8u * (6 + 3 * kKVStages);
+  const uint32_t tmem_slot = bar + 8u * (7 + 3 * kKVStages);
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kKVStages; ++s) {
+      mbar_init(k_full(s), 1);
+      mbar_init(v_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_full(i), 1);
+      mbar_init(s_free(i), 4);
+    }
+    mbar_init(p_ready, 4);
+    mbar_init(o_done, 1);
+    fence_mbar_init();
+  }
+  if (warp_idx == 2) tmem_alloc<1>(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp_idx == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, S::kQBytes);
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) tma_load_3d(sQ + c * 16384, &tmap_q, q_full, c * 64, h, q_start + m0);
+      for (int t = 0; t < n_tiles; ++t) {
+        const int s = t % kKVStages;
+        const uint32_t ph = (t / kKVStages) & 1;
+        mbar_wait(kv_empty(s), ph ^ 1);
+        const int row0 = k_start + (j_lo + t) * kBN;
+        mbar_arrive_expect_tx(k_full(s), S::kKBytes);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c)
+          tma_load_3d(sK + s * S::kKBytes + c * 16384, &tmap_k, k_full(s), c * 64, hk, row0);
+        mbar_arrive_expect_tx(v_full(s), S::kKBytes);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c)
+          tma_load_3d(sV + s * S::kKBytes + c * 16384, &tmap_v, v_full(s), c * 64, hk, row0);
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      auto issue_s = [&](int t) {
+        const int s = t % kKVStages;
+        const uint32_t kb = sK + s * S::kKBytes;
+        const uint32_t dst = tmem_base + kTmemS0 + (t & 1) * kBN;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint64_t da = desc_kmajor_sw128(sQ + (kk / 4) * 16384, kk % 4);
+          const uint64_t db = desc_kmajor_sw128(kb + (kk / 4) * 16384, kk % 4);
+          umma_ss_f16<1>(dst, da, db, kIdescS, kk != 0);
+        }
+        umma_commit(s_full(t & 1));
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(k_full(0), 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int t = 0; t < n_tiles; ++t) {
+        if (t + 1 < n_tiles) {
+          const int s1 = (t + 1) % kKVStages;
+          mbar_wait(k_full(s1), ((t + 1) / kKVStages) & 1);
+          mbar_wait(s_free((t + 1) & 1), (((t + 1) >> 1) & 1) ^ 1);
+          tc_fence_after();
+          issue_s(t + 1);
+        }
+        const int s = t % kKVStages;
+        mbar_wait(v_full(s), (t / kKVStages) & 1);
+        mbar_wait(p_ready, t & 1);
+        tc_fence_after();
+        const uint32_t vb = sV + s * S::kKBytes;
+#pragma unroll
+        for (int kk = 0; kk < kBN / 16; ++kk) {
+          const uint64_t da = desc_kmajor_sw128(sP + (kk / 4) * 16384, kk % 4);
+          const uint64_t db = desc_mnmajor_sw128(vb, kk, 16384);
+          umma_ss_f16<1>(tmem_base + kTmemO, da, db, kIdescO, (t | kk) != 0);
+        }
+        umma_commit(kv_empty(s));
+        umma_commit(o_done);
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ================================ softmax + epilogue ================================
+    const uint32_t q4 = warp_idx & 3;
+    const int r = q4 * 32 + lane;        // row inside the tile == TMEM lane
+    const int row = m0 + r;              // row inside the sequence
+    int lo, hi;
+    key_bounds(min(row, q_len - 1), q_len, k_len, args.causal, args.wl, args.wr, lo, hi);
+    const uint32_t lane_off = (q4 * 32u) << 16;
+    float m_used = -INFINITY, l_run = 0.f;
+    const float sl2 = args.scale_log2;
+
+    for (int t = 0; t < n_tiles; ++t) {
+      const int n0 = (j_lo + t) * kBN;
+      mbar_wait(s_full(t & 1), (t >> 1) & 1);
+      tc_fence_after();
+      uint32_t sv[4][32];
+      const uint32_t s_addr = tmem_base + lane_off + kTmemS0 + (t & 1) * kBN;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(s_addr + c * 32, sv[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free(t & 1));  // S buffer may be overwritten by S(t+2)
+
+      const bool full_tile = (n0 >= lo) && (n0 + kBN - 1 <= hi);
+      const bool warp_full = __all_sync(0xffffffffu, full_tile);
+      float mx = -INFINITY;
+      if (warp_full) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[c][i]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int kidx = n0 + c * 32 + i;
+            const float v = (kidx >= lo && kidx <= hi) ? __uint_as_float(sv[c][i]) : -INFINITY;
+            sv[c][i] = __float_as_uint(v);
+            mx = fmaxf(mx, v);
+          }
+      }
+      const float m_new = fmaxf(m_used, mx * sl2);
+      // lazy rescale: only move the reference max when it grew by more than the threshold
+      float alpha = 1.f;
+      bool rescale = false;
+      if (m_new > m_used + kRescaleThreshold || m_used == -INFINITY) {
+        if (m_new != -INFINITY) {
+          alpha = (m_used == -INFINITY) ? 0.f : fast_exp2(m_used - m_new);
+          rescale = (m_used != -INFINITY);
+          m_used = m_new;
+        }
+      }
+      const float mref = (m_used == -INFINITY) ? 0.f : m_used;
+      float psum = 0.f;
+      uint32_t pk[4][16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[c][2 * i]), sl2, -mref));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[c][2 * i + 1]), sl2, -mref));
+          psum += p0 + p1;
+          pk[c][i] = pack_bf16x2(p0, p1);
+        }
+      l_run = l_run * alpha + psum;
+
+      // P buffer and O accumulator are free once P V(t-1) retired
+      if (t > 0) {
+        mbar_wait(o_done, (t - 1) & 1);
+        tc_fence_after();
+      }
+      // P -> smem, K-major SWIZZLE_128B: row r, 16-byte unit u lives at unit (u ^ (r & 7))
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t chunk_base = sP + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t unit = (uint32_t)((c & 1) * 4 + u) ^ (uint32_t)(r & 7);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(chunk_base + unit * 16), "r"(pk[c][4 * u]),
+                       "r"(pk[c][4 * u + 1]), "r"(pk[c][4 * u + 2]), "r"(pk[c][4 * u + 3])
+                       : "memory");
+        }
+      }
+      if (t > 0 && __any_sync(0xffffffffu, rescale)) {
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) {
+          uint32_t ov[32];
+          tmem_ld_32x32b_x32(tmem_base + lane_off + kTmemO + c * 32, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+          tmem_st_32x32b_x32(tmem_base + lane_off + kTmemO + c * 32, ov);
+        }
+        tmem_st_wait();
+      }
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+    }
+
+    // ---- epilogue: O / l -> bf16, LSE ----
+    mbar_wait(o_done, (n_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv_l = (l_run > 0.f) ? (1.f / l_run) : 0.f;
+    const bool valid = row < q_len;
+    __nv_bfloat16* op = args.o + (long long)(q_start + row) * args.o_ts + (long long)h * D;
+#pragma unroll
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t ov[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_off + kTmemO + c * 32, ov);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(ov[8 * u + 0]) * inv_l, __uint_as_float(ov[8 * u + 1]) * inv_l);
+          w.y = pack_bf16x2(__uint_as_float(ov[8 * u + 2]) * inv_l, __uint_as_float(ov[8 * u + 3]) * inv_l);
+          w.z = pack_bf16x2(__uint_as_float(ov[8 * u + 4]) * inv_l, __uint_as_float(ov[8 * u + 5]) * inv_l);
+          w.w = pack_bf16x2(__uint_as_float(ov[8 * u + 6]) * inv_l, __uint_as_float(ov[8 * u + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(op + c * 32 + u * 8) = w;
+        }
+      }
+      __syncwarp();
+    }
+    if (valid)
+      args.lse[(long long)h * args.Tq + q_start + row] =
+          (l_run > 0.f) ? (m_used + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+// 3-D tensor map over a token-major [tokens, heads, D] bf16 tensor with token stride `ts` elements.
+static CUtensorMap make_map_thd(const void* base, long long tokens, int heads, int D, long long ts) {
+  uint64_t dims[3] = {(uint64_t)D, (uint64_t)heads, (uint64_t)tokens};
+  uint64_t strides[2] = {(uint64_t)D * 2, (uint64_t)ts * 2};
+  uint32_t box[3] = {64, 1, 128};
+  return make_tensor_map(base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+template <int D>
+static cudaError_t launch_fwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const FwdArgs& a,
+                              int max_q_len, cudaStream_t stream) {
+  using S = FwdSmem<D>;
+  auto kern = flash_fwd_kernel<D>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid(a.num_q_tiles, a.Hq, a.B);
+  kern<<<grid, kFwdThreads, S::kTotal, stream>>>(mq, mk, mv, a);
+  return cudaGetLastError();
+}
+
+cudaError_t flash_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const int* cu_q,
+                           const int* cu_k, int B, int Sq, int Sk, int Hq, int Hk, int D, long long q_ts,
+                           long long k_ts, long long v_ts, long long o_ts, float scale, bool causal, int wl, int wr,
+                           long long Tq, long long Tk, int max_q_len, cudaStream_t stream) {
+  if (B == 0 || Tq == 0) return cudaSuccess;
+  if (D != 64 && D != 128) return cudaErrorInvalidValue;
+  if (Hq % Hk != 0) return cudaErrorInvalidValue;
+  CUtensorMap mq, mk, mv;
+  try {
+    mq = make_map_thd(q, Tq, Hq, D, q_ts);
+    mk = make_map_thd(k, Tk, Hk, D, k_ts);
+    mv = make_map_thd(v, Tk, Hk, D, v_ts);
+  } catch (const std::exception& e) {
+    fprintf(stderr, "%s\n", e.what());
+    return cudaErrorInvalidValue;
+  }
+  FwdArgs a;
+  a.o = (__nv_bfloat16*)o;
+  a.lse = lse;
+  a.cu_q = cu_q;
+  a.cu_k = cu_k;
+  a.B = B; a.Sq = Sq; a.Sk = Sk; a.Hq = Hq; a.Hk = Hk;
+  a.o_ts = o_ts;
+  a.Tq = Tq;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  a.causal = causal ? 1 : 0;
+  a.wl = wl; a.wr = wr;
+  const int mq_len = cu_q ? (max_q_len > 0 ? max_q_len : (int)Tq) : Sq;
+  a.num_q_tiles = (mq_len + kBM - 1) / kBM;
+  if (D == 128) return launch_fwd<128>(mq, mk, mv, a, mq_len, stream);
+  return launch_fwd<64>(mq, mk, mv, a, mq_len, stream);
+}
+
+}  // namespace tb

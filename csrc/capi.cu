@@ -86,3 +86,60 @@ TB_API int tb_sqnorm_accumulate(uint64_t g, int is_bf16, long long n, uint64_t o
 TB_API int tb_scale_inplace(uint64_t g, int is_bf16, long long n, uint64_t scale, int num_sms, uint64_t stream) {
   return (int)tb::scale_inplace(P<void>(g), is_bf16 != 0, n, P<float>(scale), num_sms, S(stream));
 }
+
+// ---- attention ----------------------------------------------------------------------------------------
+TB_API int tb_flash_attn_fwd(uint64_t q, uint64_t k, uint64_t v, uint64_t o, uint64_t lse, uint64_t cu_q,
+                             uint64_t cu_k, int B, int Sq, int Sk, int Hq, int Hk, int D, long long q_ts,
+                             long long k_ts, long long v_ts, long long o_ts, float scale, int causal, int wl, int wr,
+                             long long Tq, long long Tk, int max_q_len, int num_sms, uint64_t stream) {
+  (void)num_sms;
+  return (int)tb::flash_attn_fwd(P<void>(q), P<void>(k), P<void>(v), P<void>(o), P<float>(lse), P<int>(cu_q),
+                                 P<int>(cu_k), B, Sq, Sk, Hq, Hk, D, q_ts, k_ts, v_ts, o_ts, scale, causal != 0, wl,
+                                 wr, Tq, Tk, max_q_len, S(stream));
+}
+TB_API int tb_flash_attn_bwd(uint64_t q, uint64_t k, uint64_t v, uint64_t o, uint64_t dout, uint64_t lse, uint64_t dq,
+                             uint64_t dk, uint64_t dv, uint64_t dq_acc, uint64_t delta, uint64_t cu_q, uint64_t cu_k,
+                             int B, int Sq, int Sk, int Hq, int Hk, int D, long long q_ts, long long k_ts,
+                             long long v_ts, long long do_ts, float scale, int causal, int wl, int wr, long long Tq,
+                             long long Tk, long long dq_ts, long long dk_ts, long long dv_ts, int num_sms,
+                             uint64_t stream) {
+  return (int)tb::flash_attn_bwd(P<void>(q), P<void>(k), P<void>(v), P<void>(o), P<void>(dout), P<float>(lse),
+                                 P<void>(dq), P<void>(dk), P<void>(dv), P<float>(dq_acc), P<float>(delta),
+                                 P<int>(cu_q), P<int>(cu_k), B, Sq, Sk, Hq, Hk, D, q_ts, k_ts, v_ts, do_ts, scale,
+                                 causal != 0, wl, wr, Tq, Tk, dq_ts, dk_ts, dv_ts, num_sms, S(stream));
+}
+
+// ---- symmetric-memory communication ------------------------------------------------------------------------
+TB_API int tb_symm_alloc(long long bytes, uint64_t* out_ptr) {
+  void* p = nullptr;
+  cudaError_t e = tb::symm_alloc((size_t)bytes, &p);
+  *out_ptr = reinterpret_cast<uint64_t>(p);
+  return (int)e;
+}
+TB_API int tb_symm_free(uint64_t ptr) { return (int)tb::symm_free(P<void>(ptr)); }
+TB_API int tb_symm_get_handle(uint64_t ptr, void* handle64) { return (int)tb::symm_get_handle(P<void>(ptr), handle64); }
+TB_API int tb_symm_open_handle(const void* handle64, uint64_t* out_ptr) {
+  void* p = nullptr;
+  cudaError_t e = tb::symm_open_handle(handle64, &p);
+  *out_ptr = reinterpret_cast<uint64_t>(p);
+  return (int)e;
+}
+TB_API int tb_symm_close_handle(uint64_t ptr) { return (int)tb::symm_close_handle(P<void>(ptr)); }
+TB_API int tb_symm_all_gather(const uint64_t* peers, const uint64_t* pads, long long src_off, uint64_t out,
+                              long long bytes, int rank, int world, int channel, uint32_t epoch, uint64_t counter,
+                              int num_sms, uint64_t stream) {
+  return (int)tb::symm_all_gather(peers, pads, (size_t)src_off, P<void>(out), (size_t)bytes, rank, world, channel, epoch,
+                                  P<uint32_t>(counter), num_sms, S(stream));
+}
+TB_API int tb_symm_reduce_scatter(const uint64_t* peers, const uint64_t* pads, long long src_off, uint64_t out,
+                                  long long n, int in_bf16, int out_fp32, float scale, int rank, int world, int channel,
+                                  uint32_t epoch, uint64_t counter, int num_sms, uint64_t stream) {
+  return (int)tb::symm_reduce_scatter(peers, pads, (size_t)src_off, P<void>(out), (size_t)n, in_bf16 != 0, out_fp32 != 0,
+                                      scale, rank, world, channel, epoch, P<uint32_t>(counter), num_sms, S(stream));
+}
+TB_API int tb_symm_all_to_all(const uint64_t* peers, const uint64_t* pads, long long src_off, uint64_t out,
+                              long long chunk_bytes, int rank, int world, int channel, uint32_t epoch, uint64_t counter,
+                              int num_sms, uint64_t stream) {
+  return (int)tb::symm_all_to_all(peers, pads, (size_t)src_off, P<void>(out), (size_t)chunk_bytes, rank, world, channel,
+                                  epoch, P<uint32_t>(counter), num_sms, S(stream));
+}

@@ -1,0 +1,275 @@
+// Symmetric-memory communication runtime for one NVSwitch domain (<= 8 GPUs per process group).
+//
+// Every rank allocates its communication buffers with cudaMalloc, exports them as CUDA IPC handles (exchanged through
+// torch.distributed by the Python side) and maps every peer's buffer into its own address space.  Collectives are
+// then plain CUDA kernels that read peer memory over NVLink with 16-byte loads ("pull"), synchronised by
+// epoch-numbered flags in a small symmetric signal pad -- no NCCL on these paths:
+//
+//   all_gather      out[r*n:(r+1)*n] = peer_r.shard                        (FSDP parameter gather, TP activation gather)
+//   reduce_scatter  out = scale * sum_r peer_r.buf[rank*n:(rank+1)*n]      (bf16 on the wire, fp32 accumulate/output)
+//   all_reduce      in place, one-shot (every rank reduces everything) or two-shot (reduce-scatter + all-gather)
+//   all_to_all      out[r*c:(r+1)*c] = peer_r.buf[rank*c:(rank+1)*c]       (Ulysses head/sequence exchange)
+//
+// Protocol per call (epoch e, channel ch):  entry barrier  (everybody's input is in place)  ->  pull  ->
+// exit barrier (everybody finished reading my buffer, so it may be overwritten).  The barriers are device side:
+// block 0 publishes `e` into slot [ch][my_rank] of every peer's pad (st.release.sys) and all blocks spin on their own
+// pad (ld.acquire.sys) -- the spin is on LOCAL memory.
+//
+// Replaces: NCCL all-gather / reduce-scatter / all-reduce / all-to-all calls the reference makes through torch FSDP,
+// DDP and torch.distributed.
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../common/ptx.cuh"
+#include "comm.h"
+
+namespace tb {
+
+constexpr int kMaxWorld = 8;
+constexpr int kPadChannels = 64;
+constexpr int kPadSlots = 16;  // per channel: [0,8) entry flags, [8,16) exit flags
+
+struct Peers {
+  void* ptr[kMaxWorld];
+};
+struct Pads {
+  uint32_t* ptr[kMaxWorld];
+};
+
+TB_DEVICE void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+TB_DEVICE uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+TB_DEVICE uint4 ld_peer_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+
+// Entry barrier: all ranks have launched this collective and their inputs are written.
+TB_DEVICE void barrier_enter(const Pads& pads, int rank, int world, int ch, uint32_t epoch) {
+  if (blockIdx.x == 0 && threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(pads.ptr[threadIdx.x] + ch * kPadSlots + rank, epoch);
+  }
+  if (threadIdx.x < world) {
+    const uint32_t* mine = pads.ptr[rank] + ch * kPadSlots + threadIdx.x;
+    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+    }
+  }
+  __syncthreads();
+}
+
+// Exit barrier: every block of THIS rank is done reading, then tell the peers; block 0 stays until all peers are done.
+TB_DEVICE void barrier_exit(const Pads& pads, int rank, int world, int ch, uint32_t epoch, uint32_t* block_counter) {
+  __syncthreads();
+  __shared__ uint32_t s_last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t prev = atomicAdd(block_counter, 1u);
+    s_last = (prev == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) *block_counter = 0;  // re-arm for the next call (stream ordered)
+  if (threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(pads.ptr[threadIdx.x] + ch * kPadSlots + 8 + rank, epoch);
+    const uint32_t* mine = pads.ptr[rank] + ch * kPadSlots + 8 + threadIdx.x;
+    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+    }
+  }
+  __syncthreads();
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// all-gather (bytes): out + r*bytes <- peer[r] (+ src_off)
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+all_gather_kernel(Peers src, Pads pads, uint8_t* __restrict__ out, size_t bytes, int rank, int world, int ch,
+                  uint32_t epoch, uint32_t* block_counter) {
+  barrier_enter(pads, rank, world, ch, epoch);
+  const size_t nvec = bytes >> 4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int step = 0; step < world; ++step) {
+    const int r = (rank + step) % world;  // start with the local shard, then walk the ring so peers are hit evenly
+    const uint4* s = reinterpret_cast<const uint4*>(src.ptr[r]);
+    uint4* d = reinterpret_cast<uint4*>(out + (size_t)r * bytes);
+    if (r == rank && (const void*)s == (const void*)d) continue;  // shard already lives inside the output buffer
+    size_t i = tid;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+      uint4 a = ld_peer_v4(s + i), b = ld_peer_v4(s + i + stride), c = ld_peer_v4(s + i + 2 * stride),
+            e = ld_peer_v4(s + i + 3 * stride);
+      d[i] = a; d[i + stride] = b; d[i + 2 * stride] = c; d[i + 3 * stride] = e;
+    }
+    for (; i < nvec; i += stride) d[i] = ld_peer_v4(s + i);
+  }
+  barrier_exit(pads, rank, world, ch, epoch, block_counter);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// reduce-scatter: out[i] = scale * sum_r peer_r[rank*n + i], fp32 accumulation.  In: bf16 or fp32.  Out: fp32/bf16.
+// ----------------------------------------------------------------------------------------------------------
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(512)
+reduce_scatter_kernel(Peers src, Pads pads, OutT* __restrict__ out, size_t n, float scale, int rank, int world, int ch,
+                      uint32_t epoch, uint32_t* block_counter) {
+  barrier_enter(pads, rank, world, ch, epoch);
+  constexpr int kPer = 16 / sizeof(InT);  // elements per 16-byte load: 8 (bf16) or 4 (fp32)
+  const size_t nvec = n / kPer;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    float acc[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) acc[j] = 0.f;
+    uint4 v[kMaxWorld];
+#pragma unroll
+    for (int step = 0; step < kMaxWorld; ++step) {
+      if (step < world) {
+        const int r = (rank + step) % world;
+        v[step] = ld_peer_v4(reinterpret_cast<const uint4*>(reinterpret_cast<const InT*>(src.ptr[r]) + (size_t)rank * n) + i);
+      }
+    }
+#pragma unroll
+    for (int step = 0; step < kMaxWorld; ++step) {
+      if (step < world) {
+        if constexpr (sizeof(InT) == 2) {
+          float2 a = unpack_bf16x2(v[step].x), b = unpack_bf16x2(v[step].y), c = unpack_bf16x2(v[step].z),
+                 d = unpack_bf16x2(v[step].w);
+          acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+          acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+        } else {
+          acc[0] += __uint_as_float(v[step].x); acc[1] += __uint_as_float(v[step].y);
+          acc[2] += __uint_as_float(v[step].z); acc[3] += __uint_as_float(v[step].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) acc[j] *= scale;
+    if constexpr (sizeof(OutT) == 4) {
+      float4* o = reinterpret_cast<float4*>(out + i * kPer);
+      o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      if constexpr (kPer == 8) o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else {
+      if constexpr (kPer == 8) {
+        uint4 o;
+        o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+        o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+        *reinterpret_cast<uint4*>(out + i * 8) = o;
+      } else {
+        uint2 o;
+        o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+        *reinterpret_cast<uint2*>(out + i * 4) = o;
+      }
+    }
+  }
+  barrier_exit(pads, rank, world, ch, epoch, block_counter);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// all-to-all (bytes): out + r*chunk <- peer[r] + rank*chunk
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+all_to_all_kernel(Peers src, Pads pads, uint8_t* __restrict__ out, size_t chunk_bytes, int rank, int world, int ch,
+                  uint32_t epoch, uint32_t* block_counter) {
+  barrier_enter(pads, rank, world, ch, epoch);
+  const size_t nvec = chunk_bytes >> 4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (int step = 0; step < world; ++step) {
+    const int r = (rank + step) % world;
+    const uint4* s = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(src.ptr[r]) + (size_t)rank * chunk_bytes);
+    uint4* d = reinterpret_cast<uint4*>(out + (size_t)r * chunk_bytes);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) d[i] = ld_peer_v4(s + i);
+  }
+  barrier_exit(pads, rank, world, ch, epoch, block_counter);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// host API
+// ----------------------------------------------------------------------------------------------------------
+static int grid_for(size_t bytes, int num_sms) {
+  size_t blocks = (bytes / 16 + 511) / 512;
+  const int cap = num_sms < 64 ? num_sms : 64;  // ~64 CTAs of 512 threads saturate NVLink; leave SMs for compute
+  if (blocks > (size_t)cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+static void fill(Peers& p, Pads& q, const uint64_t* peer_ptrs, const uint64_t* pad_ptrs, int world, size_t off_bytes) {
+  for (int i = 0; i < kMaxWorld; ++i) {
+    p.ptr[i] = i < world ? reinterpret_cast<void*>(peer_ptrs[i] + off_bytes) : nullptr;
+    q.ptr[i] = i < world ? reinterpret_cast<uint32_t*>(pad_ptrs[i]) : nullptr;
+  }
+}
+
+cudaError_t symm_all_gather(const uint64_t* peer_ptrs, const uint64_t* pad_ptrs, size_t src_off_bytes, void* out,
+                            size_t bytes, int rank, int world, int channel, uint32_t epoch, uint32_t* block_counter,
+                            int num_sms, cudaStream_t stream) {
+  if (world > kMaxWorld || bytes % 16 != 0 || channel >= kPadChannels) return cudaErrorInvalidValue;
+  Peers p; Pads q;
+  fill(p, q, peer_ptrs, pad_ptrs, world, src_off_bytes);
+  all_gather_kernel<<<grid_for(bytes * world, num_sms), 512, 0, stream>>>(p, q, (uint8_t*)out, bytes, rank, world,
+                                                                          channel, epoch, block_counter);
+  return cudaGetLastError();
+}
+
+cudaError_t symm_reduce_scatter(const uint64_t* peer_ptrs, const uint64_t* pad_ptrs, size_t src_off_bytes, void* out,
+                                size_t n, bool in_bf16, bool out_fp32, float scale, int rank, int world, int channel,
+                                uint32_t epoch, uint32_t* block_counter, int num_sms, cudaStream_t stream) {
+  if (world > kMaxWorld || channel >= kPadChannels) return cudaErrorInvalidValue;
+  if (n % (in_bf16 ? 8 : 4) != 0) return cudaErrorInvalidValue;
+  Peers p; Pads q;
+  fill(p, q, peer_ptrs, pad_ptrs, world, src_off_bytes);
+  const int grid = grid_for(n * (in_bf16 ? 2 : 4) * world, num_sms);
+#define TB_RS(IN, OUT)                                                                                          \
+  reduce_scatter_kernel<IN, OUT><<<grid, 512, 0, stream>>>(p, q, (OUT*)out, n, scale, rank, world, channel, epoch, \
+                                                            block_counter)
+  if (in_bf16 && out_fp32) TB_RS(__nv_bfloat16, float);
+  else if (in_bf16) TB_RS(__nv_bfloat16, __nv_bfloat16);
+  else if (out_fp32) TB_RS(float, float);
+  else TB_RS(float, __nv_bfloat16);
+#undef TB_RS
+  return cudaGetLastError();
+}
+
+cudaError_t symm_all_to_all(const uint64_t* peer_ptrs, const uint64_t* pad_ptrs, size_t src_off_bytes, void* out,
+                            size_t chunk_bytes, int rank, int world, int channel, uint32_t epoch,
+                            uint32_t* block_counter, int num_sms, cudaStream_t stream) {
+  if (world > kMaxWorld || chunk_bytes % 16 != 0 || channel >= kPadChannels) return cudaErrorInvalidValue;
+  Peers p; Pads q;
+  fill(p, q, peer_ptrs, pad_ptrs, world, src_off_bytes);
+  all_to_all_kernel<<<grid_for(chunk_bytes * world, num_sms), 512, 0, stream>>>(p, q, (uint8_t*)out, chunk_bytes, rank,
+                                                                                world, channel, epoch, block_counter);
+  return cudaGetLastError();
+}
+
+// ---- IPC plumbing -----------------------------------------------------------------------------------------
+cudaError_t symm_alloc(size_t bytes, void** ptr) {
+  cudaError_t e = cudaMalloc(ptr, bytes);
+  if (e != cudaSuccess) return e;
+  return cudaMemset(*ptr, 0, bytes);
+}
+cudaError_t symm_free(void* ptr) { return cudaFree(ptr); }
+cudaError_t symm_get_handle(void* ptr, void* handle64) {
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+  if (e != cudaSuccess) return e;
+  memcpy(handle64, &h, sizeof(h));
+  return cudaSuccess;
+}
+cudaError_t symm_open_handle(const void* handle64, void** ptr) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  return cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+}
+cudaError_t symm_close_handle(void* ptr) { return cudaIpcCloseMemHandle(ptr); }
+
+}  // namespace tb

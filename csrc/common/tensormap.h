@@ -43,6 +43,13 @@ inline CUtensorMap make_tensor_map(const void* base, CUtensorMapDataType dtype, 
   }
   CUresult r = get_encode_tiled()(&m, dtype, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {
+    // Driver entry points need a current context on THIS thread; autograd's backward threads may not have touched
+    // the runtime yet.  cudaFree(0) binds the device's primary context, then retry.
+    cudaFree(0);
+    r = get_encode_tiled()(&m, dtype, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS)
     throw std::runtime_error("torchacc_b200: cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   return m;

@@ -1,0 +1,109 @@
+"""tcgen05 flash-attention kernels vs the explicit fp32 reference (causal / GQA / window / varlen / packed),
+including the cases the reference's own suite skips (causal, local, varlen-causal)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _rand(B, S, H, D, seed):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return (torch.randn(B, S, H, D, device=DEV, generator=g) * 0.8).bfloat16()
+
+
+def _check(a, b, name, rtol=3e-2, atol=3e-2):
+    a, b = a.float(), b.float()
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    bad = int((err > tol).sum())
+    assert bad == 0, f"{name}: {bad}/{a.numel()} off, max err {float(err.max()):.4g} (ref max {float(b.abs().max()):.3g})"
+
+
+CASES = [
+    # B, Sq, Sk, Hq, Hk, D, causal, window
+    (2, 256, 256, 4, 4, 128, False, (-1, -1)),
+    (2, 256, 256, 4, 4, 128, True, (-1, -1)),
+    (1, 512, 512, 8, 2, 128, True, (-1, -1)),
+    (2, 200, 200, 4, 2, 128, True, (-1, -1)),       # ragged tail
+    (1, 130, 390, 4, 4, 128, True, (-1, -1)),       # Sq != Sk, bottom-right aligned causal
+    (1, 384, 384, 4, 1, 64, True, (-1, -1)),        # head_dim 64, MQA
+    (2, 320, 320, 4, 4, 64, False, (-1, -1)),
+    (1, 640, 640, 4, 2, 128, True, (100, 0)),       # sliding window
+    (1, 512, 512, 2, 2, 128, False, (64, 32)),      # local, non-causal
+    (1, 1024, 1024, 8, 8, 128, True, (-1, -1)),
+]
+
+
+@pytest.mark.parametrize("B,Sq,Sk,Hq,Hk,D,causal,window", CASES)
+def test_flash_attn_fwd_bwd(B, Sq, Sk, Hq, Hk, D, causal, window):
+    from torchacc_b200.ops import attention as A
+    from torchacc_b200 import _native as nat
+    A.set_attention_backend("native")
+    q, k, v = _rand(B, Sq, Hq, D, 1), _rand(B, Sk, Hk, D, 2), _rand(B, Sk, Hk, D, 3)
+    q.requires_grad_(); k.requires_grad_(); v.requires_grad_()
+    n0 = nat.LAUNCHES
+    out, lse, _ = A.flash_attn_func(q, k, v, causal=causal, window_size=window, return_attn_probs=True)
+    assert nat.LAUNCHES > n0, "native attention kernel was not launched"
+    do = _rand(B, Sq, Hq, D, 4)
+    out.backward(do)
+    qf, kf, vf = (t.detach().float().requires_grad_() for t in (q, k, v))
+    ref, lse_ref = A.attention_reference(qf, kf, vf, None, causal, window)
+    ref.backward(do.float())
+    _check(out, ref, "out")
+    fin = torch.isfinite(lse_ref)
+    _check(lse[fin], lse_ref[fin], "lse", 1e-2, 1e-2)
+    _check(v.grad, vf.grad, "dv")
+    _check(k.grad, kf.grad, "dk")
+    _check(q.grad, qf.grad, "dq")
+    A.set_attention_backend("auto")
+
+
+def test_varlen_mask_and_position_ids():
+    from torchacc_b200.ops import attention as A
+    A.set_attention_backend("native")
+    B, S, H, Hk, D = 3, 256, 4, 2, 128
+    q, k, v = _rand(B, S, H, D, 5), _rand(B, S, Hk, D, 6), _rand(B, S, Hk, D, 7)
+    lens = torch.tensor([256, 100, 177], device=DEV)
+    mask = (torch.arange(S, device=DEV)[None, :] < lens[:, None]).int()
+    for causal in (False, True):
+        out = A.flash_attn_varlen_func(q, k, v, mask, causal=causal)
+        ref, _ = A.attention_reference_masked(q, k, v, mask.bool(), 1 / math.sqrt(D), causal, (-1, -1))
+        _check(out, ref, f"varlen causal={causal}")
+    # packed sequences by position ids (batch of 1)
+    seqs = [100, 156, 128]
+    total = sum(seqs)
+    pos = torch.cat([torch.arange(n, device=DEV) for n in seqs])[None]
+    q1, k1, v1 = _rand(1, total, H, D, 8), _rand(1, total, Hk, D, 9), _rand(1, total, Hk, D, 10)
+    out = A.flash_attn_varlen_position_ids_func(q1, k1, v1, pos, causal=True)
+    off = 0
+    for n in seqs:
+        ref, _ = A.attention_reference(q1[:, off:off + n], k1[:, off:off + n], v1[:, off:off + n], None, True)
+        _check(out[:, off:off + n], ref, f"packed seq at {off}")
+        off += n
+    A.set_attention_backend("auto")
+
+
+def test_qkvpacked_tokens_fwd_bwd():
+    """The native-model fast path: fused QKV activation in, one dqkv tensor out."""
+    from torchacc_b200.ops import attention as A
+    A.set_attention_backend("native")
+    B, S, hq, hk, D = 2, 384, 8, 2, 128
+    T = B * S
+    g = torch.Generator(device=DEV).manual_seed(0)
+    qkv = (torch.randn(T, (hq + 2 * hk) * D, device=DEV, generator=g) * 0.7).bfloat16().requires_grad_()
+    out = A.flash_attn_qkvpacked_tokens(qkv, hq, hk, D, B, S, causal=True)
+    do = (torch.randn(T, hq * D, device=DEV, generator=g)).bfloat16()
+    out.backward(do)
+    x = qkv.detach().float().requires_grad_()
+    q = x[:, :hq * D].reshape(B, S, hq, D)
+    k = x[:, hq * D:(hq + hk) * D].reshape(B, S, hk, D)
+    v = x[:, (hq + hk) * D:].reshape(B, S, hk, D)
+    ref, _ = A.attention_reference(q, k, v, None, True)
+    ref.reshape(T, hq * D).backward(do.float())
+    _check(out, ref.reshape(T, hq * D), "out")
+    _check(qkv.grad, x.grad, "dqkv")
+    A.set_attention_backend("auto")

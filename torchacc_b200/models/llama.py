@@ -99,6 +99,7 @@ class ParallelContext:
     """What a layer needs to know about the surrounding parallelism (filled by the TP / CP wrappers)."""
 
     def __init__(self):
+        self.tp = None               # parallel.tp.TPContext when tensor parallel
         self.tp_group = None
         self.tp_size = 1
         self.sequence_parallel = False
@@ -121,10 +122,14 @@ class LlamaAttention(nn.Module):
 
     def forward(self, x, rope, batch, seq_len, position_ids=None, cu_seqlens=None, pctx: Optional[ParallelContext] = None):
         cos, sin = rope
-        qkv = linear(x, self.qkv_proj.weight, self.qkv_proj.bias)           # [T, (Hq+2Hk) D]
+        tp = pctx.tp if pctx is not None else None
         hq, hk = self.num_heads, self.num_kv_heads
-        if pctx is not None and pctx.tp_size > 1:
-            hq, hk = hq // pctx.tp_size, max(hk // pctx.tp_size, 1)
+        if tp is not None:
+            from ..parallel.tp import column_parallel_linear, row_parallel_linear
+            qkv = column_parallel_linear(x, self.qkv_proj.weight, self.qkv_proj.bias, tp)   # all-gather -> GEMM
+            hq, hk = hq // tp.size, hk // tp.size
+        else:
+            qkv = linear(x, self.qkv_proj.weight, self.qkv_proj.bias)       # [T, (Hq+2Hk) D]
         window = (-1, -1)
         if self.cfg.sliding_window:
             window = (self.cfg.sliding_window - 1, 0)
@@ -136,6 +141,8 @@ class LlamaAttention(nn.Module):
             qkv = rope_qkv_(qkv, hq, hk, self.head_dim, cos, sin, position_ids, seq_len)
             o = attn_ops.flash_attn_qkvpacked_tokens(qkv, hq, hk, self.head_dim, batch, seq_len, causal=True,
                                                      window_size=window, cu_seqlens=cu_seqlens)
+        if tp is not None:
+            return row_parallel_linear(o, self.o_proj.weight, tp)           # GEMM -> reduce-scatter
         return linear(o, self.o_proj.weight, None)
 
 
@@ -147,7 +154,12 @@ class LlamaMLP(nn.Module):
         self.gate_up_proj = nn.Linear(cfg.hidden_size, 2 * cfg.intermediate_size, bias=False, **kw)
         self.down_proj = nn.Linear(cfg.intermediate_size, cfg.hidden_size, bias=False, **kw)
 
-    def forward(self, x):
+    def forward(self, x, pctx=None):
+        tp = pctx.tp if pctx is not None else None
+        if tp is not None:
+            from ..parallel.tp import column_parallel_linear, row_parallel_linear
+            return row_parallel_linear(swiglu(column_parallel_linear(x, self.gate_up_proj.weight, None, tp)),
+                                       self.down_proj.weight, tp)
         return linear(swiglu(linear(x, self.gate_up_proj.weight)), self.down_proj.weight)
 
 
@@ -164,10 +176,14 @@ class LlamaDecoderLayer(nn.Module):
         self.mlp = LlamaMLP(cfg, **kw)
 
     def forward(self, h, rope, batch, seq_len, position_ids=None, cu_seqlens=None, pctx=None):
-        y, _ = rmsnorm(h, self.input_layernorm.weight, self.input_layernorm.eps)
+        w1, w2 = self.input_layernorm.weight, self.post_attention_layernorm.weight
+        if pctx is not None and pctx.tp is not None:
+            from ..parallel.tp import tp_replicated
+            w1, w2 = tp_replicated(w1, pctx.tp), tp_replicated(w2, pctx.tp)
+        y, _ = rmsnorm(h, w1, self.input_layernorm.eps)
         a = self.self_attn(y, rope, batch, seq_len, position_ids, cu_seqlens, pctx)
-        y2, h2 = rmsnorm(a, self.post_attention_layernorm.weight, self.post_attention_layernorm.eps, residual=h)
-        m = self.mlp(y2)
+        y2, h2 = rmsnorm(a, w2, self.post_attention_layernorm.eps, residual=h)
+        m = self.mlp(y2, pctx)
         return h2 + m
 
 
@@ -210,9 +226,15 @@ class LlamaModel(nn.Module):
         if S > rope[0].shape[0]:
             raise ValueError(f"sequence length {S} exceeds max_position_embeddings {rope[0].shape[0]}")
         pos = position_ids.reshape(-1).to(torch.int32) if position_ids is not None else None
+        tp = self.pctx.tp
+        wn = self.norm.weight
+        if tp is not None and tp.sequence_parallel:
+            from ..parallel.tp import scatter_tokens, tp_replicated
+            h = scatter_tokens(h, tp)                       # residual stream is token-sharded between the linears
+            wn = tp_replicated(wn, tp)
         for layer in self.layers:
             h = layer(h, rope, B, S, pos, cu_seqlens, self.pctx)
-        y, _ = rmsnorm(h, self.norm.weight, self.norm.eps)
+        y, _ = rmsnorm(h, wn, self.norm.eps)
         return y
 
 
@@ -269,11 +291,26 @@ class LlamaForCausalLM(nn.Module):
                     lab = lab.masked_fill(nxt_is_start, -100)
             else:
                 lab = labels
-            out["loss"] = fused_linear_cross_entropy(hidden, self.lm_head.weight, lab.reshape(-1),
-                                                     chunk_tokens=self.config.loss_chunk_tokens,
-                                                     n_valid_total=n_valid_total)
+            tp = self.model.pctx.tp
+            if tp is not None:
+                from ..parallel.tp import gather_tokens, vocab_parallel_cross_entropy
+                hid = gather_tokens(hidden, tp) if tp.sequence_parallel else hidden
+                out["loss"] = vocab_parallel_cross_entropy(hid, self.lm_head.weight, lab.reshape(-1), tp)
+            else:
+                out["loss"] = fused_linear_cross_entropy(hidden, self.lm_head.weight, lab.reshape(-1),
+                                                         chunk_tokens=self.config.loss_chunk_tokens,
+                                                         n_valid_total=n_valid_total)
         if return_logits or (labels is None and return_logits is None):
-            out["logits"] = linear(hidden, self.lm_head.weight).view(B, S, -1)
+            tp = self.model.pctx.tp
+            if tp is not None:
+                from ..parallel.tp import gather_tokens
+                hid = gather_tokens(hidden, tp) if tp.sequence_parallel else hidden
+                local = linear(hid, self.lm_head.weight)                      # [T, V/tp]
+                parts = [torch.empty_like(local) for _ in range(tp.size)]
+                torch.distributed.all_gather(parts, local.contiguous(), group=tp.group)
+                out["logits"] = torch.cat(parts, -1).view(B, S, -1)
+            else:
+                out["logits"] = linear(hidden, self.lm_head.weight).view(B, S, -1)
         return out
 
     # ---- HF interop -------------------------------------------------------------------------------------

@@ -85,12 +85,13 @@ class _FusedLinearCEFn(torch.autograd.Function):
         dh = torch.empty_like(h2) if want_grad else None
         need_w = weight.requires_grad and want_grad
         view = getattr(weight, "_tb_grad_view", None)
-        if need_w and view is None:
-            dw = torch.zeros_like(weight)
-            acc0 = True
-        elif need_w:
-            dw = view
-            acc0 = bool(getattr(weight, "_tb_grad_ready", False))
+        # The weight gradient is produced HERE (forward) for d(loss) = 1; backward rescales it by the incoming
+        # gradient.  Writing straight into the engine's flat gradient slice is only possible when that slice holds
+        # nothing yet (otherwise our contribution could not be rescaled separately).
+        direct = need_w and view is not None and not bool(getattr(weight, "_tb_grad_ready", False))
+        if need_w:
+            dw = view if direct else torch.zeros_like(weight)
+            acc0 = not direct
         else:
             dw, acc0 = None, False
         total = torch.zeros((), dtype=torch.float32, device=h2.device)
@@ -109,21 +110,29 @@ class _FusedLinearCEFn(torch.autograd.Function):
                 gemm(lg, h2[s:e], a_mn_major=True, b_mn_major=True, out=dw,
                      accumulate=(acc0 or not first))                        # dW += dlogits^T @ h
             first = False
-        if need_w and view is not None:
+        if direct:
             weight._tb_grad_ready = True
-        ctx.save_for_backward(dh, dw if (need_w and view is None) else None)
+        ctx.save_for_backward(dh, dw if need_w else None)
         ctx.shape = hidden.shape
-        ctx.need_w = need_w and view is None
+        ctx.mode = "direct" if direct else ("view" if (need_w and view is not None) else ("own" if need_w else "none"))
+        ctx.view = view if need_w else None
+        ctx.weight = weight if (need_w and view is not None) else None
         return total * scale[0]
 
     @staticmethod
     def backward(ctx, dloss):
         dh, dw = ctx.saved_tensors
-        # gradients were computed for d(loss)=1; the loss is normally the root so dloss == 1
+        # gradients were computed for d(loss) = 1: apply the incoming scale (1/num_micro_batches, loss scaling ...)
         dh = dh * dloss.to(dh.dtype)
-        if ctx.need_w:
-            dw = dw * dloss.to(dw.dtype)
-        return dh.view(ctx.shape), (dw if ctx.need_w else None), None, None, None, None
+        out_dw = None
+        if ctx.mode == "direct":
+            ctx.view.mul_(dloss.to(ctx.view.dtype))
+        elif ctx.mode == "view":
+            ctx.view.add_(dw * dloss.to(dw.dtype))
+            ctx.weight._tb_grad_ready = True
+        elif ctx.mode == "own":
+            out_dw = dw * dloss.to(dw.dtype)
+        return dh.view(ctx.shape), out_dw, None, None, None, None
 
 
 def fused_linear_cross_entropy(hidden: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor,

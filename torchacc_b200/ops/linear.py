@@ -75,11 +75,14 @@ class _LinearFn(torch.autograd.Function):
         x2 = x.reshape(-1, shp[-1])
         if x2.stride(-1) != 1 or x2.stride(0) % 8 != 0:
             x2 = x2.contiguous()
-        y = gemm(x2, w, bias=bias)
+        # allocate with the final shape: returning a view made inside a custom Function would forbid later
+        # in-place ops on the result (RoPE rotates the QKV activation in place)
+        y = torch.empty((*shp[:-1], w.shape[0]), dtype=x.dtype, device=x.device)
+        gemm(x2, w, bias=bias, out=y.view(-1, w.shape[0]))
         ctx.save_for_backward(x2, w)
         ctx.has_bias = bias is not None
         ctx.x_shape = shp
-        return y.view(*shp[:-1], w.shape[0])
+        return y
 
     @staticmethod
     def backward(ctx, dy):
@@ -89,7 +92,8 @@ class _LinearFn(torch.autograd.Function):
             dy2 = dy2.contiguous()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = gemm(dy2, w, b_mn_major=True).view(ctx.x_shape)
+            dx = torch.empty(ctx.x_shape, dtype=dy2.dtype, device=dy2.device)
+            gemm(dy2, w, b_mn_major=True, out=dx.view(-1, ctx.x_shape[-1]))
         if ctx.needs_input_grad[1]:
             view = getattr(w, "_tb_grad_view", None)
             if view is not None:

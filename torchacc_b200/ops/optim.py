@@ -68,6 +68,14 @@ class FusedAdamW(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self.grad_scale: Optional[torch.Tensor] = None
         self.found_inf: Optional[torch.Tensor] = None
+        # flat shards of a sharding engine: switch the engine to bf16/fp32 `_tb_grad` hand-off (no fp32 .grad copies)
+        engines = set()
+        for group in self.param_groups:
+            for p in group["params"]:
+                unit = getattr(p, "_tb_unit", None)
+                if unit is not None and id(unit.engine) not in engines:
+                    engines.add(id(unit.engine))
+                    unit.engine.use_fused_optimizer(self)
 
     @torch.no_grad()
     def step(self, closure=None):

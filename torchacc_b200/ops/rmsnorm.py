@@ -28,8 +28,8 @@ class _RMSNormFn(torch.autograd.Function):
         x2 = x.contiguous().view(-1, H)
         r2 = residual.contiguous().view(-1, H) if residual is not None else None
         rows = x2.shape[0]
-        y = torch.empty_like(x2)
-        h = torch.empty_like(x2) if r2 is not None else x2
+        y = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+        h = torch.empty(x.shape, dtype=x.dtype, device=x.device) if r2 is not None else x2
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
         L = nat.require()
         nat.check(
@@ -37,12 +37,12 @@ class _RMSNormFn(torch.autograd.Function):
                              h.data_ptr() if r2 is not None else 0, rstd.data_ptr(), rows, H, eps, nat.num_sms(),
                              nat.stream()), "tb_rmsnorm_fwd")
         nat.count_launch()
-        ctx.save_for_backward(h, w, rstd)
+        ctx.save_for_backward(h.view(-1, H) if r2 is not None else h, w, rstd)
         ctx.has_res = r2 is not None
         ctx.shape = x.shape
         if r2 is not None:
-            return y.view(x.shape), h.view(x.shape)
-        return y.view(x.shape), None
+            return y, h
+        return y, None
 
     @staticmethod
     def backward(ctx, dy, dh):
@@ -51,14 +51,13 @@ class _RMSNormFn(torch.autograd.Function):
         rows = h.shape[0]
         dy2 = dy.contiguous().view(-1, H)
         dres = dh.contiguous().view(-1, H) if (dh is not None and ctx.has_res) else None
-        dx = torch.empty_like(h)
+        dx = torch.empty(ctx.shape, dtype=h.dtype, device=h.device)
         dw = torch.zeros(H, dtype=torch.float32, device=h.device)
         L = nat.require()
         nat.check(
             L.tb_rmsnorm_bwd(dy2.data_ptr(), h.data_ptr(), w.data_ptr(), rstd.data_ptr(), nat.ptr(dres),
                              dx.data_ptr(), dw.data_ptr(), rows, H, nat.num_sms(), nat.stream()), "tb_rmsnorm_bwd")
         nat.count_launch()
-        dx = dx.view(ctx.shape)
         return dx, dw.to(w.dtype), (dx if ctx.has_res else None), None
 
 

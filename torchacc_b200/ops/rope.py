@@ -78,8 +78,8 @@ class _RopeFn(torch.autograd.Function):
             cos, sin, positions = ctx.saved_tensors
         else:
             (cos, sin), positions = ctx.saved_tensors, None
-        dq = dq.contiguous()
-        dk = dk.contiguous()
+        dq = dq.clone(memory_format=torch.contiguous_format)
+        dk = dk.clone(memory_format=torch.contiguous_format)
         _apply_inplace(dq, cos, sin, positions, ctx.seq_len, True)
         _apply_inplace(dk, cos, sin, positions, ctx.seq_len, True)
         return dq, dk, None, None, None, None
@@ -125,8 +125,8 @@ class _RopeQKVFn(torch.autograd.Function):
             cos, sin, positions = ctx.saved_tensors
         else:
             (cos, sin), positions = ctx.saved_tensors, None
-        if not dqkv.is_contiguous():
-            dqkv = dqkv.contiguous()
+        # the incoming gradient belongs to autograd (it may be shared / inspected by the caller): rotate a copy
+        dqkv = dqkv.clone(memory_format=torch.contiguous_format)
         T = dqkv.shape[0]
         dq = dqkv.as_strided((T, hq, d), (dqkv.stride(0), d, 1), dqkv.storage_offset())
         dk = dqkv.as_strided((T, hk, d), (dqkv.stride(0), d, 1), dqkv.storage_offset() + hq * d)

@@ -25,14 +25,14 @@ class _SwiGLUFn(torch.autograd.Function):
         Fdim = g.shape[-1]
         g2, u2 = _rows(g), _rows(u)
         T = g2.shape[0]
-        h = torch.empty((T, Fdim), dtype=g.dtype, device=g.device)
+        h = torch.empty((*g.shape[:-1], Fdim), dtype=g.dtype, device=g.device)
         L = nat.require()
         nat.check(L.tb_swiglu_fwd(g2.data_ptr(), u2.data_ptr(), h.data_ptr(), T, Fdim, g2.stride(0), u2.stride(0),
                                   nat.num_sms(), nat.stream()), "tb_swiglu_fwd")
         nat.count_launch()
         ctx.save_for_backward(g2, u2)
         ctx.shape = g.shape
-        return h.view(*g.shape[:-1], Fdim)
+        return h
 
     @staticmethod
     def backward(ctx, dh):
@@ -64,28 +64,29 @@ class _SwiGLUFusedFn(torch.autograd.Function):
         Fdim = gu.shape[-1] // 2
         gu2 = _rows(gu)
         T = gu2.shape[0]
-        h = torch.empty((T, Fdim), dtype=gu.dtype, device=gu.device)
+        h = torch.empty((*gu.shape[:-1], Fdim), dtype=gu.dtype, device=gu.device)
         L = nat.require()
         nat.check(L.tb_swiglu_fwd(gu2.data_ptr(), gu2.data_ptr() + 2 * Fdim, h.data_ptr(), T, Fdim, gu2.stride(0),
                                   gu2.stride(0), nat.num_sms(), nat.stream()), "tb_swiglu_fwd")
         nat.count_launch()
         ctx.save_for_backward(gu2)
         ctx.shape = gu.shape
-        return h.view(*gu.shape[:-1], Fdim)
+        return h
 
     @staticmethod
     def backward(ctx, dh):
         (gu2,) = ctx.saved_tensors
         T, Fdim = gu2.shape[0], gu2.shape[1] // 2
         dh2 = dh.contiguous().view(T, Fdim)
-        dgu = torch.empty((T, 2 * Fdim), dtype=gu2.dtype, device=gu2.device)
+        dgu = torch.empty(ctx.shape, dtype=gu2.dtype, device=gu2.device)
+        ld = 2 * Fdim
         L = nat.require()
         nat.check(
             L.tb_swiglu_bwd(dh2.data_ptr(), gu2.data_ptr(), gu2.data_ptr() + 2 * Fdim, dgu.data_ptr(),
-                            dgu.data_ptr() + 2 * Fdim, T, Fdim, gu2.stride(0), gu2.stride(0), dgu.stride(0),
-                            dgu.stride(0), nat.num_sms(), nat.stream()), "tb_swiglu_bwd")
+                            dgu.data_ptr() + 2 * Fdim, T, Fdim, gu2.stride(0), gu2.stride(0), ld, ld, nat.num_sms(),
+                            nat.stream()), "tb_swiglu_bwd")
         nat.count_launch()
-        return dgu.view(ctx.shape)
+        return dgu
 
 
 def swiglu(gu: torch.Tensor) -> torch.Tensor:

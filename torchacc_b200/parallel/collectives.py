@@ -36,6 +36,14 @@ class Collectives:
     def all_reduce(self, t: torch.Tensor, scale: float = 1.0) -> None:
         raise NotImplementedError
 
+    def all_to_all(self, inp: torch.Tensor, out: torch.Tensor) -> None:
+        """Equal-chunk all-to-all on flat contiguous tensors."""
+        dist.all_to_all_single(out, inp, group=self.group)
+
+    def alloc(self, numel: int, dtype: torch.dtype, device=None) -> torch.Tensor:
+        """Buffer that will be the *source* of a collective (symmetric memory for the peer-memory back-end)."""
+        return torch.zeros(numel, dtype=dtype, device=device)
+
 
 class LocalCollectives(Collectives):
     """world == 1."""
@@ -54,6 +62,9 @@ class LocalCollectives(Collectives):
     def all_reduce(self, t, scale=1.0):
         if scale != 1.0:
             t.mul_(scale)
+
+    def all_to_all(self, inp, out):
+        out.copy_(inp)
 
 
 class NcclCollectives(Collectives):
@@ -81,6 +92,27 @@ class NcclCollectives(Collectives):
 
 class GlooCollectives(Collectives):
     name = "gloo"
+
+    def all_to_all(self, inp, out):
+        ins = list(inp.reshape(self.world, -1).unbind(0))
+        outs = [torch.empty_like(c) for c in ins]
+        if inp.dtype == torch.bfloat16:
+            ins = [c.view(torch.int16).contiguous() for c in ins]
+            outs = [c.view(torch.int16) for c in outs]
+        work = []
+        # gloo has no all_to_all: pairwise exchange
+        for r in range(self.world):
+            if r == self.rank:
+                outs[r].copy_(ins[r])
+        for shift in range(1, self.world):
+            dst, src = (self.rank + shift) % self.world, (self.rank - shift) % self.world
+            g_dst = dist.get_global_rank(self.group, dst) if self.group is not None else dst
+            g_src = dist.get_global_rank(self.group, src) if self.group is not None else src
+            sw = dist.isend(ins[dst].contiguous(), g_dst, group=self.group)
+            dist.recv(outs[src], g_src, group=self.group)
+            sw.wait()
+        flat = torch.cat([o.reshape(-1) for o in outs])
+        out.reshape(-1).view(flat.dtype).copy_(flat)
 
     def all_gather(self, shard, full):
         if full.dtype == torch.bfloat16:  # gloo has no bf16 kernels on every build: move as int16 bit patterns

@@ -49,8 +49,9 @@ class _ParamInfo:
 class _BufferPool:
     """Rotating pool of equally sized device buffers keyed by (numel, dtype)."""
 
-    def __init__(self, device, depth: int = 2):
+    def __init__(self, device, depth: int = 2, allocator=None):
         self.device, self.depth = device, depth
+        self.allocator = allocator
         self._bufs: Dict[tuple, List[torch.Tensor]] = {}
         self._events: Dict[int, Optional[torch.cuda.Event]] = {}
         self._next: Dict[tuple, int] = {}
@@ -60,7 +61,8 @@ class _BufferPool:
         lst = self._bufs.setdefault(key, [])
         i = self._next.get(key, 0)
         if len(lst) < self.depth:
-            buf = torch.zeros(numel, dtype=dtype, device=self.device)
+            buf = (self.allocator(numel, dtype) if self.allocator is not None
+                   else torch.zeros(numel, dtype=dtype, device=self.device))
             lst.append(buf)
             self._next[key] = len(lst) % self.depth
             return buf
@@ -153,7 +155,10 @@ class FlatParamUnit:
         if lp_dtype == torch.float32:
             self.lp_shard = self.flat_param.data                        # fp32 training: no separate copy
         else:
-            self.lp_shard = shard.to(lp_dtype)
+            # the bf16 shard is what peers pull during the all-gather: allocate it where they can reach it
+            self.lp_shard = eng.shard_coll.alloc(self.shard_numel, lp_dtype, dev) if hasattr(eng.shard_coll, "domain") \
+                else torch.empty(self.shard_numel, dtype=lp_dtype, device=dev)
+            self.lp_shard.copy_(shard)
             self.flat_param._tb_lp_shard = self.lp_shard
         self.lp_version = self.flat_param._version
         if world == 1:
@@ -455,7 +460,8 @@ class ShardingEngine:
         self.grad_shard_dtype = torch.float32 if reduce_dtype == "fp32" else self.grad_wire_dtype
         self.units: List[FlatParamUnit] = []
         self.lp_pool = _BufferPool(device, depth=2 + prefetch)
-        self.grad_pool = _BufferPool(device, depth=2)
+        symm_grad = hasattr(self.shard_coll, "domain")
+        self.grad_pool = _BufferPool(device, depth=2, allocator=(self.shard_coll.alloc if symm_grad else None))
         self._empty = torch.empty(0, dtype=compute_dtype, device=device)
         cuda = device.type == "cuda"
         self.gather_stream = torch.cuda.Stream(device) if (cuda and self.shard_world > 1) else None
