@@ -11,7 +11,9 @@
 //   (e) dQ   = dS K      A = dS^T smem read MN-major     B = K  (smem, MN-major)     -> TMEM R1 (aliases dP^T)
 //   (c) dV  += P^T dO    A = P^T (TMEM)                  B = dO (smem, MN-major)     -> TMEM R2
 //   (d) dK  += dS^T Q    A = dS^T (smem, K-major)        B = Q  (smem, MN-major)     -> TMEM R3
-// dQ is reduced across key tiles with fp32 vector red.global.add into a scratch buffer (converted afterwards).
+// dQ is reduced across key tiles with TMA bulk reduce-add (cp.reduce.async.bulk.tensor .add.f32) from a swizzled smem
+// staging tile that reuses the dS^T buffer -- per-lane red.global atomics cap at ~1 lane/clk/SM and were 80% of the
+// first version's run time.
 // Q/dO tiles stream through a 2-stage TMA ring; K/V stay resident.  The tensor pipe executes MMAs in issue order,
 // so the TMEM/smem aliases above need no extra barriers beyond "softmax done" / "dQ read out".
 //
@@ -25,7 +27,7 @@
 namespace tb {
 
 constexpr int kTile = 128;
-constexpr int kBwdThreads = 256;
+constexpr int kBwdThreads = 384;  // 4 control warps + 2 softmax warpgroups (each owns 64 of the 128 query columns)
 constexpr int kQStages = 2;
 
 struct BwdArgs {
@@ -65,7 +67,7 @@ template <int D>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
-                 const BwdArgs args) {
+                 const __grid_constant__ CUtensorMap tmap_dq, const BwdArgs args) {
   using S = BwdSmem<D>;
   constexpr int kChunks = S::kChunks;
   constexpr uint32_t kIdescST = make_idesc_f16(kTile, kTile, Major::K, Major::K, true);   // (a), (b)
@@ -119,14 +121,15 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
+    tma_prefetch_desc(&tmap_dq);
   }
   if (warp_idx == 1 && lane == 0) {
     mbar_init(kv_full, 1);
     for (int s = 0; s < kQStages; ++s) { mbar_init(qdo_full(s), 1); mbar_init(qdo_empty(s), 1); }
     mbar_init(sdp_full, 1);
-    mbar_init(pds_ready, 4);
+    mbar_init(pds_ready, 8);
     mbar_init(dq_full, 1);
-    mbar_init(r1_free, 4);
+    mbar_init(r1_free, 8);
     mbar_init(dkv_full, 1);
     fence_mbar_init();
   }
@@ -192,44 +195,49 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int kk = 0; kk < kTile / 16; ++kk)
           umma_ss_f16<1>(tmem_base + R1, desc_mnmajor_sw128(sDS, kk, 16384), desc_mnmajor_sw128(sK, kk, 16384),
                          kIdescDQ, kk != 0);
-        umma_commit(dq_full);
-        // (c) dV += P^T dO   (A from TMEM: 16 bf16 of K = 8 columns per step)
-#pragma unroll
-        for (int kk = 0; kk < kTile / 16; ++kk)
-          umma_ts_f16(tmem_base + R2, tmem_base + R0 + kk * 8, desc_mnmajor_sw128(do_s, kk, 16384), kIdescDKV,
-                      (it | kk) != 0);
         // (d) dK += dS^T Q
 #pragma unroll
         for (int kk = 0; kk < kTile / 16; ++kk)
           umma_ss_f16<1>(tmem_base + R3, desc_kmajor_sw128(sDS + (kk / 4) * 16384, kk % 4),
                          desc_mnmajor_sw128(q_s, kk, 16384), kIdescDKV, (it | kk) != 0);
+        umma_commit(dq_full);   // dQ complete AND dS^T smem no longer read: it becomes the dQ staging tile
+        // (c) dV += P^T dO   (A from TMEM: 16 bf16 of K = 8 columns per step)
+#pragma unroll
+        for (int kk = 0; kk < kTile / 16; ++kk)
+          umma_ts_f16(tmem_base + R2, tmem_base + R0 + kk * 8, desc_mnmajor_sw128(do_s, kk, 16384), kIdescDKV,
+                      (it | kk) != 0);
         umma_commit(qdo_empty(s));
       }
       umma_commit(dkv_full);
     }
   } else if (warp_idx >= 4) {
     // ================================ softmax / dS / dQ read-out / epilogue ================================
+    // two warpgroups: grp 0 = warps 4-7 owns query columns [0,64), grp 1 = warps 8-11 owns [64,128)
     const uint32_t q4 = warp_idx & 3;
+    const int grp = (warp_idx - 4) >> 2;
     const int r = q4 * 32 + lane;  // TMEM lane: key row for S^T/dP^T/dV/dK, query row for dQ
     const uint32_t lane_off = (q4 * 32u) << 16;
     const float sl2 = args.scale_log2, sc = args.scale;
     const bool key_ok = key < k_len;
-    // prefetch the statistics of the first query tile
-    float lse_next, delta_next;
-    {
-      const int h = iter_head(0), row = iter_m0(0) + r;
+    // group 0 prefetches the row statistics of the next query tile
+    float lse_next = 0.f, delta_next = 0.f;
+    auto fetch_stats = [&](int it) {
+      const int h = iter_head(it), row = iter_m0(it) + r;
       const bool ok = row < q_len;
       const float l = ok ? args.lse[(long long)h * args.Tq + q_start + row] : INFINITY;
       lse_next = (l == -INFINITY) ? INFINITY : l * 1.4426950408889634f;
       delta_next = ok ? args.delta[(long long)h * args.Tq + q_start + row] : 0.f;
-    }
+    };
+    if (grp == 0) fetch_stats(0);
     for (int it = 0; it < n_iter; ++it) {
       const int h = iter_head(it), m0 = iter_m0(it);
-      // publish this tile's row statistics (all 128 softmax threads finished the previous tile's reads)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      stat[r] = lse_next;
-      stat[kTile + r] = delta_next;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // publish this tile's row statistics (all 256 softmax threads finished the previous tile's reads)
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (grp == 0) {
+        stat[r] = lse_next;
+        stat[kTile + r] = delta_next;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(sdp_full, it & 1);
       tc_fence_after();
       // interior tile: every query row of the tile sees every key of the tile -> no per-element mask
@@ -240,10 +248,19 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const int lo_last = (args.wl < 0) ? 0 : max(0, pos_last - args.wl);
         interior = (hi_first >= n0 + kTile - 1) && (lo_last <= n0);
       }
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t sv[32], dpv[32];
-        tmem_ld_32x32b_x32(tmem_base + lane_off + R0 + c * 32, sv);
+      // read this group's 64 S^T columns, then make sure BOTH groups are done reading before P^T (which aliases
+      // S^T columns [0,64)) is written
+      uint32_t sv[2][32];
+      tmem_ld_32x32b_x32(tmem_base + lane_off + R0 + (2 * grp) * 32, sv[0]);
+      tmem_ld_32x32b_x32(tmem_base + lane_off + R0 + (2 * grp + 1) * 32, sv[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * grp + cc;
+        uint32_t dpv[32];
         tmem_ld_32x32b_x32(tmem_base + lane_off + R1 + c * 32, dpv);
         tmem_ld_wait();
         uint32_t pk[16], dsk[16];
@@ -253,22 +270,22 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int col = c * 32 + 2 * i + e;   // query row inside the tile
-            const int qrow = m0 + col;
-            int lo, hi;
-            {
+            bool ok = true;
+            if (!interior) {
+              const int qrow = m0 + col;
               const int pos = qrow + shift;
-              hi = (wr_eff < 0) ? (k_len - 1) : min(k_len - 1, pos + wr_eff);
-              lo = (args.wl < 0) ? 0 : max(0, pos - args.wl);
+              const int hi = (wr_eff < 0) ? (k_len - 1) : min(k_len - 1, pos + wr_eff);
+              const int lo = (args.wl < 0) ? 0 : max(0, pos - args.wl);
+              ok = key_ok && qrow < q_len && key >= lo && key <= hi;
             }
-            const bool ok = interior || (key_ok && qrow < q_len && key >= lo && key <= hi);
-            const float p = ok ? fast_exp2(fmaf(__uint_as_float(sv[2 * i + e]), sl2, -stat[col])) : 0.f;
+            const float p = ok ? fast_exp2(fmaf(__uint_as_float(sv[cc][2 * i + e]), sl2, -stat[col])) : 0.f;
             pv[e] = p;
             dv[e] = p * (__uint_as_float(dpv[2 * i + e]) - stat[kTile + col]) * sc;
           }
           pk[i] = pack_bf16x2(pv[0], pv[1]);
           dsk[i] = pack_bf16x2(dv[0], dv[1]);
         }
-        // P^T chunk -> TMEM R0 columns [16c, 16c+16) (S^T columns < 32c+32 of this lane were already read)
+        // P^T chunk -> TMEM R0 columns [16c, 16c+16)
         tmem_st_32x32b_x16(tmem_base + lane_off + R0 + c * 16, pk);
         // dS^T chunk -> smem row r (keys), 64 bytes = 4 x 16B units, 128B-swizzled
         const uint32_t row_base = sDS + (c >> 1) * 16384 + r * 128;
@@ -286,36 +303,41 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_ready);
       // prefetch the next tile's statistics while the tensor core works
-      if (it + 1 < n_iter) {
-        const int h2 = iter_head(it + 1), row = iter_m0(it + 1) + r;
-        const bool ok = row < q_len;
-        const float l = ok ? args.lse[(long long)h2 * args.Tq + q_start + row] : INFINITY;
-        lse_next = (l == -INFINITY) ? INFINITY : l * 1.4426950408889634f;
-        delta_next = ok ? args.delta[(long long)h2 * args.Tq + q_start + row] : 0.f;
-      }
-      // dQ tile: lane r = query row m0 + r
+      if (grp == 0 && it + 1 < n_iter) fetch_stats(it + 1);
+      // dQ tile (lane r = query row m0 + r): TMEM -> swizzled fp32 staging in this group's half of the dS^T buffer
+      // -> TMA bulk reduce-add into the fp32 dQ accumulator.  Group g owns D columns [g*D/2, (g+1)*D/2).
       mbar_wait(dq_full, it & 1);
       tc_fence_after();
-      const bool qok = (m0 + r) < q_len;
-      float* dqp = args.dq_acc + ((long long)(q_start + m0 + r) * args.Hq + h) * D;
+      constexpr int kBoxes = D / 64;   // 32-column fp32 boxes per group
+      const uint32_t stage = sDS + grp * 16384;
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
+      for (int bx = 0; bx < kBoxes; ++bx) {
+        const int col0 = grp * (D / 2) + bx * 32;
         uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + lane_off + R1 + c * 32, v);
+        tmem_ld_32x32b_x32(tmem_base + lane_off + R1 + col0, v);
         tmem_ld_wait();
-        if (qok) {
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
-            red_add_v4(dqp + c * 32 + u * 4, __uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]),
-                       __uint_as_float(v[4 * u + 2]), __uint_as_float(v[4 * u + 3]));
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t unit = (uint32_t)u ^ (uint32_t)(r & 7);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + r * 128 + unit * 16), "r"(v[4 * u]),
+                       "r"(v[4 * u + 1]), "r"(v[4 * u + 2]), "r"(v[4 * u + 3])
+                       : "memory");
         }
-        __syncwarp();
+        fence_proxy_async_smem();
+        if (grp == 0) asm volatile("bar.sync 3, 128;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");
+        if (q4 == 0 && lane == 0) {
+          tma_reduce_add_2d(&tmap_dq, stage, h * D + col0, q_start + m0);
+          tma_store_commit();
+          tma_store_wait_read<0>();   // staging tile may be overwritten again
+        }
+        if (grp == 0) asm volatile("bar.sync 3, 128;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(r1_free);
     }
-    // ---- epilogue: dV (R2), dK (R3) -> bf16 ----
+    if (q4 == 0 && lane == 0) tma_store_wait<0>();   // all bulk reductions of this thread have landed
+    // ---- epilogue: dV (R2), dK (R3) -> bf16; each group writes half of the D columns ----
     mbar_wait(dkv_full, 0);
     tc_fence_after();
     __nv_bfloat16* pdv = args.dv + (long long)(k_start + key) * args.dv_ts + (long long)hk * D;
@@ -325,7 +347,8 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       __nv_bfloat16* dst = which == 0 ? pdv : pdk;
       const uint32_t reg = which == 0 ? R2 : R3;
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
+      for (int cc = 0; cc < D / 64; ++cc) {
+        const int c = grp * (D / 64) + cc;
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + lane_off + reg + c * 32, v);
         tmem_ld_wait();
@@ -405,7 +428,8 @@ static CUtensorMap make_map_thd_b(const void* base, long long tokens, int heads,
 
 template <int D>
 static cudaError_t launch_bwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
-                              const CUtensorMap& mdo, const BwdArgs& a, int num_k_tiles, cudaStream_t stream) {
+                              const CUtensorMap& mdo, const CUtensorMap& mdq, const BwdArgs& a, int num_k_tiles,
+                              cudaStream_t stream) {
   using S = BwdSmem<D>;
   auto kern = flash_bwd_kernel<D>;
   static bool configured = false;
@@ -415,7 +439,7 @@ static cudaError_t launch_bwd(const CUtensorMap& mq, const CUtensorMap& mk, cons
     configured = true;
   }
   dim3 grid(num_k_tiles, a.Hk, a.B);
-  kern<<<grid, kBwdThreads, S::kTotal, stream>>>(mq, mk, mv, mdo, a);
+  kern<<<grid, kBwdThreads, S::kTotal, stream>>>(mq, mk, mv, mdo, mdq, a);
   return cudaGetLastError();
 }
 
@@ -444,12 +468,18 @@ cudaError_t flash_attn_bwd(const void* q, const void* k, const void* v, const vo
     if (e != cudaSuccess) return e;
   }
   // 2) main kernel
-  CUtensorMap mq, mk, mv, mdo;
+  CUtensorMap mq, mk, mv, mdo, mdq;
   try {
     mq = make_map_thd_b(q, Tq, Hq, D, q_ts);
     mk = make_map_thd_b(k, Tk, Hk, D, k_ts);
     mv = make_map_thd_b(v, Tk, Hk, D, v_ts);
     mdo = make_map_thd_b(dout, Tq, Hq, D, do_ts);
+    {  // fp32 dQ accumulator [Tq, Hq*D]: 128 x 32 boxes (128 B rows, SWIZZLE_128B) for the bulk reduce-add
+      uint64_t dims[2] = {(uint64_t)Hq * D, (uint64_t)Tq};
+      uint64_t strides[1] = {(uint64_t)Hq * D * 4};
+      uint32_t box[2] = {32, 128};
+      mdq = make_tensor_map(dq_acc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    }
   } catch (const std::exception& e) {
     fprintf(stderr, "%s\n", e.what());
     return cudaErrorInvalidValue;
@@ -467,8 +497,8 @@ cudaError_t flash_attn_bwd(const void* q, const void* k, const void* v, const vo
   a.wl = wl; a.wr = wr;
   const int max_k = cu_k ? (int)Tk : Sk;
   const int num_k_tiles = (max_k + kTile - 1) / kTile;
-  cudaError_t e = (D == 128) ? launch_bwd<128>(mq, mk, mv, mdo, a, num_k_tiles, stream)
-                             : launch_bwd<64>(mq, mk, mv, mdo, a, num_k_tiles, stream);
+  cudaError_t e = (D == 128) ? launch_bwd<128>(mq, mk, mv, mdo, mdq, a, num_k_tiles, stream)
+                             : launch_bwd<64>(mq, mk, mv, mdo, mdq, a, num_k_tiles, stream);
   if (e != cudaSuccess) return e;
   // 3) dq = bf16(dq_acc)
   {

@@ -1,7 +1,7 @@
 // FlashAttention forward on tcgen05 / TMEM / TMA for sm_100a.
 //
 // One CTA per (128-row query tile, q head, batch/sequence).  Warp roles:
-//   warp 0    : TMA producer  -- Q once, then a 2-stage ring of K and V tiles (3-D tensor maps over
+//   warp 0    : TMA producer  -- Q once, then separate rings of K (3 stages) and V (2 stages) tiles (3-D tensor maps over
 //               [tokens, heads, D], SWIZZLE_128B boxes of 64 x 1 x 128, so strided q/k/v views of a fused QKV
 //               activation are read in place)
 //   warp 1    : MMA issuer    -- S = Q K^T (UMMA 128x128xD, K-major/K-major) into a double-buffered TMEM S tile,
@@ -26,8 +26,9 @@ namespace tb {
 
 constexpr int kBM = 128;  // query rows per CTA
 constexpr int kBN = 128;  // keys per tile
-constexpr int kKVStages = 2;
-constexpr int kFwdThreads = 256;
+constexpr int kKStages = 3;   // K is needed one tile earlier than V (S(t+1) is issued before P V(t)): deeper ring
+constexpr int kVStages = 2;
+constexpr int kFwdThreads = 384;  // 4 control warps + 2 softmax warpgroups (64 key columns each)
 constexpr float kRescaleThreshold = 8.0f;  // log2 domain
 
 struct FwdArgs {
@@ -51,10 +52,11 @@ struct FwdSmem {
   static constexpr int kPBytes = kBM * kBN * 2;
   static constexpr int kQ = 0;
   static constexpr int kK = kQ + kQBytes;
-  static constexpr int kV = kK + kKVStages * kKBytes;
-  static constexpr int kP = kV + kKVStages * kKBytes;
+  static constexpr int kV = kK + kKStages * kKBytes;
+  static constexpr int kP = kV + kVStages * kKBytes;
   static constexpr int kBar = kP + kPBytes;
-  static constexpr int kTotal = kBar + 256 + 1024;
+  static constexpr int kXchg = kBar + 256;              // row max / row sum exchange between the two softmax groups
+  static constexpr int kTotal = kXchg + 2 * kBM * 4 + 1024;
 };
 
 // visible key range [lo, hi] for query row `row` (0-based inside its sequence)
@@ -113,13 +115,15 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t bar = base + S::kBar;
   const uint32_t q_full = bar;
   auto k_full = [&](int s) { return bar + 8u * (1 + s); };
-  auto v_full = [&](int s) { return bar + 8u * (1 + kKVStages + s); };
-  auto kv_empty = [&](int s) { return bar + 8u * (1 + 2 * kKVStages + s); };
-  auto s_full = [&](int i) { return bar + 8u * (1 + 3 * kKVStages + i); };
-  auto s_free = [&](int i) { return bar + 8u * (3 + 3 * kKVStages + i); };
-  const uint32_t p_ready = bar + 8u * (5 + 3 * kKVStages);
-  const uint32_t o_done = bar + 8u * (6 + 3 * kKVStages);
-  const uint32_t tmem_slot = bar + 8u * (7 + 3 * kKVStages);
+  auto k_empty = [&](int s) { return bar + 8u * (1 + kKStages + s); };
+  auto v_full = [&](int s) { return bar + 8u * (1 + 2 * kKStages + s); };
+  auto v_empty = [&](int s) { return bar + 8u * (1 + 2 * kKStages + kVStages + s); };
+  constexpr int kB0 = 1 + 2 * kKStages + 2 * kVStages;
+  auto s_full = [&](int i) { return bar + 8u * (kB0 + i); };
+  auto s_free = [&](int i) { return bar + 8u * (kB0 + 2 + i); };
+  const uint32_t p_ready = bar + 8u * (kB0 + 4);
+  const uint32_t o_done = bar + 8u * (kB0 + 5);
+  const uint32_t tmem_slot = bar + 8u * (kB0 + 6);
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -128,16 +132,19 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
   if (warp_idx == 1 && lane == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < kKVStages; ++s) {
+    for (int s = 0; s < kKStages; ++s) {
       mbar_init(k_full(s), 1);
+      mbar_init(k_empty(s), 1);
+    }
+    for (int s = 0; s < kVStages; ++s) {
       mbar_init(v_full(s), 1);
-      mbar_init(kv_empty(s), 1);
+      mbar_init(v_empty(s), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(s_full(i), 1);
-      mbar_init(s_free(i), 4);
+      mbar_init(s_free(i), 8);
     }
-    mbar_init(p_ready, 4);
+    mbar_init(p_ready, 8);
     mbar_init(o_done, 1);
     fence_mbar_init();
   }
@@ -154,26 +161,34 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_arrive_expect_tx(q_full, S::kQBytes);
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) tma_load_3d(sQ + c * 16384, &tmap_q, q_full, c * 64, h, q_start + m0);
-      for (int t = 0; t < n_tiles; ++t) {
-        const int s = t % kKVStages;
-        const uint32_t ph = (t / kKVStages) & 1;
-        mbar_wait(kv_empty(s), ph ^ 1);
-        const int row0 = k_start + (j_lo + t) * kBN;
+      // K runs ahead of V: issue K(t + 1) before V(t) so the next score tile is never starved
+      auto load_k = [&](int t) {
+        const int s = t % kKStages;
+        mbar_wait(k_empty(s), ((t / kKStages) & 1) ^ 1);
         mbar_arrive_expect_tx(k_full(s), S::kKBytes);
 #pragma unroll
         for (int c = 0; c < kChunks; ++c)
-          tma_load_3d(sK + s * S::kKBytes + c * 16384, &tmap_k, k_full(s), c * 64, hk, row0);
+          tma_load_3d(sK + s * S::kKBytes + c * 16384, &tmap_k, k_full(s), c * 64, hk, k_start + (j_lo + t) * kBN);
+      };
+      auto load_v = [&](int t) {
+        const int s = t % kVStages;
+        mbar_wait(v_empty(s), ((t / kVStages) & 1) ^ 1);
         mbar_arrive_expect_tx(v_full(s), S::kKBytes);
 #pragma unroll
         for (int c = 0; c < kChunks; ++c)
-          tma_load_3d(sV + s * S::kKBytes + c * 16384, &tmap_v, v_full(s), c * 64, hk, row0);
+          tma_load_3d(sV + s * S::kKBytes + c * 16384, &tmap_v, v_full(s), c * 64, hk, k_start + (j_lo + t) * kBN);
+      };
+      load_k(0);
+      for (int t = 0; t < n_tiles; ++t) {
+        if (t + 1 < n_tiles) load_k(t + 1);
+        load_v(t);
       }
     }
   } else if (warp_idx == 1) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
       auto issue_s = [&](int t) {
-        const int s = t % kKVStages;
+        const int s = t % kKStages;
         const uint32_t kb = sK + s * S::kKBytes;
         const uint32_t dst = tmem_base + kTmemS0 + (t & 1) * kBN;
 #pragma unroll
@@ -182,6 +197,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           const uint64_t db = desc_kmajor_sw128(kb + (kk / 4) * 16384, kk % 4);
           umma_ss_f16<1>(dst, da, db, kIdescS, kk != 0);
         }
+        umma_commit(k_empty(s));       // K tile is free as soon as the score MMAs retire
         umma_commit(s_full(t & 1));
       };
       mbar_wait(q_full, 0);
@@ -190,14 +206,14 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       issue_s(0);
       for (int t = 0; t < n_tiles; ++t) {
         if (t + 1 < n_tiles) {
-          const int s1 = (t + 1) % kKVStages;
-          mbar_wait(k_full(s1), ((t + 1) / kKVStages) & 1);
+          const int s1 = (t + 1) % kKStages;
+          mbar_wait(k_full(s1), ((t + 1) / kKStages) & 1);
           mbar_wait(s_free((t + 1) & 1), (((t + 1) >> 1) & 1) ^ 1);
           tc_fence_after();
           issue_s(t + 1);
         }
-        const int s = t % kKVStages;
-        mbar_wait(v_full(s), (t / kKVStages) & 1);
+        const int s = t % kVStages;
+        mbar_wait(v_full(s), (t / kVStages) & 1);
         mbar_wait(p_ready, t & 1);
         tc_fence_after();
         const uint32_t vb = sV + s * S::kKBytes;
@@ -207,45 +223,49 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           const uint64_t db = desc_mnmajor_sw128(vb, kk, 16384);
           umma_ss_f16<1>(tmem_base + kTmemO, da, db, kIdescO, (t | kk) != 0);
         }
-        umma_commit(kv_empty(s));
+        umma_commit(v_empty(s));
         umma_commit(o_done);
       }
     }
   } else if (warp_idx >= 4) {
     // ================================ softmax + epilogue ================================
+    // two warpgroups share every row: grp 0 (warps 4-7) owns key columns [0,64) of the tile and O columns
+    // [0,D/2); grp 1 (warps 8-11) owns the other halves.  Row max / row sum are exchanged through smem.
     const uint32_t q4 = warp_idx & 3;
+    const int grp = (warp_idx - 4) >> 2;
     const int r = q4 * 32 + lane;        // row inside the tile == TMEM lane
     const int row = m0 + r;              // row inside the sequence
     int lo, hi;
     key_bounds(min(row, q_len - 1), q_len, k_len, args.causal, args.wl, args.wr, lo, hi);
     const uint32_t lane_off = (q4 * 32u) << 16;
-    float m_used = -INFINITY, l_run = 0.f;
+    float* xchg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + S::kXchg);
+    float m_used = -INFINITY, l_part = 0.f;
     const float sl2 = args.scale_log2;
 
     for (int t = 0; t < n_tiles; ++t) {
-      const int n0 = (j_lo + t) * kBN;
+      const int n0 = (j_lo + t) * kBN + grp * 64;   // first key column owned by this thread
       mbar_wait(s_full(t & 1), (t >> 1) & 1);
       tc_fence_after();
-      uint32_t sv[4][32];
-      const uint32_t s_addr = tmem_base + lane_off + kTmemS0 + (t & 1) * kBN;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(s_addr + c * 32, sv[c]);
+      uint32_t sv[2][32];
+      const uint32_t s_addr = tmem_base + lane_off + kTmemS0 + (t & 1) * kBN + grp * 64;
+      tmem_ld_32x32b_x32(s_addr, sv[0]);
+      tmem_ld_32x32b_x32(s_addr + 32, sv[1]);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free(t & 1));  // S buffer may be overwritten by S(t+2)
 
-      const bool full_tile = (n0 >= lo) && (n0 + kBN - 1 <= hi);
+      const bool full_tile = (n0 >= lo) && (n0 + 63 <= hi);
       const bool warp_full = __all_sync(0xffffffffu, full_tile);
       float mx = -INFINITY;
       if (warp_full) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[c][i]));
       } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int kidx = n0 + c * 32 + i;
@@ -254,6 +274,11 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             mx = fmaxf(mx, v);
           }
       }
+      // combine the row max of the two column halves
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // previous tile's exchange reads are done
+      xchg[grp * kBM + r] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(mx, xchg[(grp ^ 1) * kBM + r]);
       const float m_new = fmaxf(m_used, mx * sl2);
       // lazy rescale: only move the reference max when it grew by more than the threshold
       float alpha = 1.f;
@@ -267,9 +292,9 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
       const float mref = (m_used == -INFINITY) ? 0.f : m_used;
       float psum = 0.f;
-      uint32_t pk[4][16];
+      uint32_t pk[2][16];
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float p0 = fast_exp2(fmaf(__uint_as_float(sv[c][2 * i]), sl2, -mref));
@@ -277,20 +302,21 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           psum += p0 + p1;
           pk[c][i] = pack_bf16x2(p0, p1);
         }
-      l_run = l_run * alpha + psum;
+      l_part = l_part * alpha + psum;
 
       // P buffer and O accumulator are free once P V(t-1) retired
       if (t > 0) {
         mbar_wait(o_done, (t - 1) & 1);
         tc_fence_after();
       }
-      // P -> smem, K-major SWIZZLE_128B: row r, 16-byte unit u lives at unit (u ^ (r & 7))
+      // P -> smem, K-major SWIZZLE_128B: this group's 64 columns form one 16 KB chunk; 16-byte unit u of row r
+      // lives at unit (u ^ (r & 7))
+      const uint32_t chunk_base = sP + grp * 16384 + r * 128;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t chunk_base = sP + (c >> 1) * 16384 + r * 128;
+      for (int c = 0; c < 2; ++c) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const uint32_t unit = (uint32_t)((c & 1) * 4 + u) ^ (uint32_t)(r & 7);
+          const uint32_t unit = (uint32_t)(c * 4 + u) ^ (uint32_t)(r & 7);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(chunk_base + unit * 16), "r"(pk[c][4 * u]),
                        "r"(pk[c][4 * u + 1]), "r"(pk[c][4 * u + 2]), "r"(pk[c][4 * u + 3])
                        : "memory");
@@ -298,13 +324,14 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
       if (t > 0 && __any_sync(0xffffffffu, rescale)) {
 #pragma unroll
-        for (int c = 0; c < D / 32; ++c) {
+        for (int c = 0; c < D / 64; ++c) {
+          const uint32_t o_addr = tmem_base + lane_off + kTmemO + grp * (D / 2) + c * 32;
           uint32_t ov[32];
-          tmem_ld_32x32b_x32(tmem_base + lane_off + kTmemO + c * 32, ov);
+          tmem_ld_32x32b_x32(o_addr, ov);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-          tmem_st_32x32b_x32(tmem_base + lane_off + kTmemO + c * 32, ov);
+          tmem_st_32x32b_x32(o_addr, ov);
         }
         tmem_st_wait();
       }
@@ -315,15 +342,19 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
 
     // ---- epilogue: O / l -> bf16, LSE ----
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    xchg[grp * kBM + r] = l_part;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float l_run = l_part + xchg[(grp ^ 1) * kBM + r];
     mbar_wait(o_done, (n_tiles - 1) & 1);
     tc_fence_after();
     const float inv_l = (l_run > 0.f) ? (1.f / l_run) : 0.f;
     const bool valid = row < q_len;
-    __nv_bfloat16* op = args.o + (long long)(q_start + row) * args.o_ts + (long long)h * D;
+    __nv_bfloat16* op = args.o + (long long)(q_start + row) * args.o_ts + (long long)h * D + grp * (D / 2);
 #pragma unroll
-    for (int c = 0; c < D / 32; ++c) {
+    for (int c = 0; c < D / 64; ++c) {
       uint32_t ov[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_off + kTmemO + c * 32, ov);
+      tmem_ld_32x32b_x32(tmem_base + lane_off + kTmemO + grp * (D / 2) + c * 32, ov);
       tmem_ld_wait();
       if (valid) {
 #pragma unroll
@@ -338,7 +369,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
       __syncwarp();
     }
-    if (valid)
+    if (valid && grp == 0)
       args.lse[(long long)h * args.Tq + q_start + row] =
           (l_run > 0.f) ? (m_used + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
   }

@@ -1,0 +1,311 @@
+"""Multi-process (gloo, CPU) tests of the parallel engines: DP, FSDP, HSDP, TP, PP, CP and checkpoints.
+These are the tests the reference can only run on GPUs (and mostly as 'runs without error' scripts);
+here every one asserts numerical parity with the single-process model."""
+import os
+
+import pytest
+import torch
+
+from dist_utils import run_distributed
+
+
+def _tiny(seed=0, **over):
+    from torchacc_b200.models import build_llama
+    torch.manual_seed(seed)
+    kw = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+              num_key_value_heads=2, head_dim=16, vocab_size=128, max_position_embeddings=128)
+    kw.update(over)
+    return build_llama("tiny", **kw)
+
+
+def _data(B=4, S=32, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 128, (B, S), generator=g)
+
+
+def _reference_loss_and_grads(ids):
+    m = _tiny()
+    out = m(ids, labels=ids)
+    out["loss"].backward()
+    return float(out["loss"]), {n: p.grad.clone() for n, p in m.named_parameters()}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _dp_worker(rank, world):
+    import torchacc_b200 as ta
+    ids = _data()
+    ref_loss, ref_grads = _reference_loss_and_grads(ids)
+    model = _tiny()
+    model = ta.accelerate(model)          # default config under a 2-rank launch == pure data parallel
+    assert type(model).__name__ == "DistributedParallel"
+    cfg = ta.get_global_context().config
+    assert cfg.dist.dp.size == world
+    local = ids.chunk(world)[rank]
+    out = model(local, labels=local)
+    out["loss"].backward()
+    # averaged gradients over the two halves == gradients of the full batch
+    eng = model.engine
+    meta = model._inner_engine_module().get_shard_metadata()
+    flat = torch.cat([g.float().reshape(-1) for g in eng.grads()])
+    ref_flat = []
+    for u in meta["units"]:
+        buf = torch.zeros(u["padded"])
+        for p in u["params"]:
+            name = (u["prefix"] + "." if u["prefix"] else "") + p["fqn"]
+            buf[p["offset"]:p["offset"] + p["numel"]] = ref_grads[name].reshape(-1)
+        ref_flat.append(buf)
+    ref_flat = torch.cat(ref_flat)
+    assert torch.allclose(flat, ref_flat, atol=2e-5, rtol=1e-4), float((flat - ref_flat).abs().max())
+
+
+def test_default_config_is_data_parallel():
+    run_distributed(_dp_worker, 2)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _fsdp_worker(rank, world, hybrid):
+    import torchacc_b200 as ta
+    ids = _data()
+    model = _tiny()
+    cfg = ta.Config()
+    cfg.dist.fsdp.size = 2
+    if hybrid:
+        cfg.dist.dp.size = 2
+    cfg.dist.fsdp.wrap_layer_cls = {"LlamaDecoderLayer"}
+    cfg.memory.gc = True
+    model = ta.accelerate(model, config=cfg)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)      # plain torch optimizer on the flat shards
+    nrep = world
+    local = ids.chunk(nrep)[rank]
+    ref = _tiny()
+    ref_opt = torch.optim.SGD(ref.parameters(), lr=0.1)
+    for _ in range(3):
+        out = model(local, labels=local)
+        out["loss"].backward()
+        opt.step()
+        model.zero_grad()
+        r = ref(ids, labels=ids)
+        r["loss"].backward()
+        ref_opt.step()
+        ref_opt.zero_grad()
+    full = model._inner_engine_module().full_state_dict(rank0_only=False)
+    for n, p in ref.named_parameters():
+        assert torch.allclose(full[n], p.detach(), atol=1e-4, rtol=1e-3), (n, float((full[n] - p).abs().max()))
+
+
+def test_fsdp_matches_single_process():
+    run_distributed(_fsdp_worker, 2, args=(False,))
+
+
+def test_hsdp_matches_single_process():
+    run_distributed(_fsdp_worker, 4, args=(True,))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _tp_worker(rank, world, sequence_parallel):
+    import torch.distributed as dist
+    import torchacc_b200 as ta
+    ids = _data(B=2, S=32)
+    ref_loss, ref_grads = _reference_loss_and_grads(ids)
+    model = _tiny()
+    cfg = ta.Config()
+    cfg.dist.tp.size = 2
+    cfg.dist.tp.sequence_parallel = sequence_parallel
+    model = ta.accelerate(model, config=cfg)
+    out = model(ids, labels=ids)
+    assert abs(float(out["loss"]) - ref_loss) < 1e-4, (float(out["loss"]), ref_loss)
+    out["loss"].backward()
+    eng = model.engine
+    meta = model._inner_engine_module().get_shard_metadata()
+    # compare a replicated parameter (norm weight) and a row-sharded one (o_proj columns)
+    grads = {}
+    for u, g in zip(meta["units"], eng.grads()):
+        for p in u["params"]:
+            name = (u["prefix"] + "." if u["prefix"] else "") + p["fqn"]
+            grads[name] = g[p["offset"]:p["offset"] + p["numel"]].view(p["shape"])
+    n = "model.layers.0.input_layernorm.weight"
+    assert torch.allclose(grads[n], ref_grads[n], atol=1e-5, rtol=1e-4), n
+    n = "model.layers.1.self_attn.o_proj.weight"
+    cols = ref_grads[n].shape[1] // world
+    assert torch.allclose(grads[n], ref_grads[n][:, rank * cols:(rank + 1) * cols], atol=1e-5, rtol=1e-4), n
+    n = "lm_head.weight"
+    rows = ref_grads[n].shape[0] // world
+    assert torch.allclose(grads[n], ref_grads[n][rank * rows:(rank + 1) * rows], atol=1e-5, rtol=1e-4), n
+    n = "model.embed_tokens.weight"
+    assert torch.allclose(grads[n], ref_grads[n], atol=1e-5, rtol=1e-4), n
+
+
+@pytest.mark.parametrize("sp", [True, False])
+def test_tensor_parallel_matches_single_process(sp):
+    run_distributed(_tp_worker, 2, args=(sp,))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _pp_worker(rank, world):
+    import torchacc_b200 as ta
+    ids = _data(B=4, S=16)
+    ref_loss, ref_grads = _reference_loss_and_grads(ids)
+    model = _tiny()
+    cfg = ta.Config()
+    cfg.dist.pp.size = 2
+    cfg.dist.pp.num_micro_batches = 2
+    cfg.dist.pp.split_points = ["model.layers.1"]
+    model = ta.accelerate(model, config=cfg)
+    loss = model.forward_backward(ids, labels=ids)
+    assert abs(float(loss) - ref_loss) < 1e-4, (float(loss), ref_loss)
+    names = [n for n, _ in model.named_parameters()]
+    assert names, "stage has no parameters"
+    meta = model._inner_engine_module().get_shard_metadata()
+    for u, g in zip(meta["units"], model.engine.grads()):
+        for p in u["params"]:
+            fqn = (u["prefix"] + "." if u["prefix"] else "") + p["fqn"]
+            # stage-local names: layers.K -> model.layers.(offset+K)
+            if fqn.startswith("layers."):
+                k = int(fqn.split(".")[1]) + (1 if rank == 1 else 0)
+                ref_name = "model.layers." + str(k) + "." + fqn.split(".", 2)[2]
+            elif fqn.startswith("embed_tokens"):
+                ref_name = "model." + fqn
+            elif fqn.startswith("norm"):
+                ref_name = "model." + fqn
+            else:
+                ref_name = fqn
+            got = g[p["offset"]:p["offset"] + p["numel"]].view(p["shape"])
+            assert torch.allclose(got, ref_grads[ref_name], atol=1e-5, rtol=1e-4), (fqn, ref_name)
+
+
+def test_pipeline_parallel_matches_single_process():
+    run_distributed(_pp_worker, 2)
+
+
+class _SkipNet(torch.nn.Module):
+    """Generic (non-native) model with a skip connection that crosses two stage boundaries."""
+
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Linear(8, 8)
+        self.b = torch.nn.Linear(8, 8)
+        self.c = torch.nn.Linear(8, 8)
+        self.head = torch.nn.Linear(8, 1)
+
+    def forward(self, x, y):
+        h0 = torch.relu(self.a(x))
+        h1 = torch.relu(self.b(h0))
+        h2 = torch.relu(self.c(h1)) + h0          # h0 produced in stage 0, consumed in stage 2
+        return ((self.head(h2).squeeze(-1) - y) ** 2).mean()
+
+
+def _pp_fx_worker(rank, world):
+    import torchacc_b200 as ta
+    torch.manual_seed(0)
+    ref = _SkipNet()
+    x, y = torch.randn(6, 8), torch.randn(6)
+    ref_loss = ref(x, y)
+    ref_loss.backward()
+    torch.manual_seed(0)
+    model = _SkipNet()
+    cfg = ta.Config()
+    cfg.dist.pp.size = 3
+    cfg.dist.pp.num_micro_batches = 3
+    cfg.dist.pp.split_points = [model.b, model.c]        # module objects, like the reference allows
+    cfg.dist.pp.input_names = ["x", "y"]
+    model = ta.accelerate(model, config=cfg)
+    loss = model.forward_backward(x, y)
+    # mean of per-micro-batch means == full mean for equal micro-batches
+    assert abs(float(loss) - float(ref_loss)) < 1e-5, (float(loss), float(ref_loss))
+    mine = {0: "a", 1: "b", 2: "c"}[rank]
+    g = dict(ref.named_parameters())[mine + ".weight"].grad
+    meta = model._inner_engine_module().get_shard_metadata()
+    found = False
+    for u, gg in zip(meta["units"], model.engine.grads()):
+        for p in u["params"]:
+            if p["fqn"].endswith(mine + ".weight"):
+                got = gg[p["offset"]:p["offset"] + p["numel"]].view(p["shape"])
+                assert torch.allclose(got, g, atol=1e-5), float((got - g).abs().max())
+                found = True
+    assert found
+
+
+def test_pipeline_fx_split_with_skip_connection():
+    run_distributed(_pp_fx_worker, 3)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _cp_worker(rank, world, mode, causal):
+    import torch.distributed as dist
+    from torchacc_b200.ops import attention as A
+    from torchacc_b200.ops import context_parallel as cp
+    g = torch.Generator().manual_seed(0)
+    B, S, Hq, Hk, D = 2, 32, 4, 2, 16
+    q = torch.randn(B, S, Hq, D, generator=g)
+    k = torch.randn(B, S, Hk, D, generator=g)
+    v = torch.randn(B, S, Hk, D, generator=g)
+    do = torch.randn(B, S, Hq, D, generator=g)
+    qf, kf, vf = (t.clone().requires_grad_() for t in (q, k, v))
+    ref, _ = A.attention_reference(qf, kf, vf, None, causal)
+    ref.backward(do)
+    group = dist.group.WORLD
+    zig = mode == "ring_zigzag"
+    if zig:
+        shard = lambda t: cp.zigzag_split(t, 1, group)
+    else:
+        shard = lambda t: t.chunk(world, 1)[rank].contiguous()
+    ql, kl, vl = (shard(t).requires_grad_() for t in (q, k, v))
+    if mode == "ulysses":
+        out = cp.ulysses(ql, kl, vl, causal=causal, process_group=group)
+    elif mode in ("ring", "ring_zigzag"):
+        out = cp.ring_attention(ql, kl, vl, causal=causal, process_group=group, zigzag=zig)
+    elif mode == "ring_p2p":
+        out = cp.ring_attention(ql, kl, vl, causal=causal, process_group=group, impl="p2p")
+    out.backward(shard(do))
+    assert torch.allclose(out, shard(ref.detach()), atol=1e-4, rtol=1e-3), float((out - shard(ref.detach())).abs().max())
+    for got, full in ((ql.grad, qf.grad), (kl.grad, kf.grad), (vl.grad, vf.grad)):
+        assert torch.allclose(got, shard(full), atol=1e-4, rtol=1e-3), float((got - shard(full)).abs().max())
+
+
+@pytest.mark.parametrize("mode,causal", [("ulysses", False), ("ulysses", True), ("ring", False), ("ring", True),
+                                         ("ring_zigzag", True), ("ring_p2p", True)])
+def test_context_parallel_attention(mode, causal):
+    run_distributed(_cp_worker, 2, args=(mode, causal))
+
+
+def _cp2d_worker(rank, world):
+    import torch.distributed as dist
+    from torchacc_b200.ops import attention as A
+    from torchacc_b200.ops import context_parallel as cp
+    cp.initialize_context_parallel(4, 2)
+    g = torch.Generator().manual_seed(0)
+    B, S, Hq, Hk, D = 1, 32, 4, 2, 16
+    q, k, v = (torch.randn(B, S, h, D, generator=g) for h in (Hq, Hk, Hk))
+    ref, _ = A.attention_reference(q, k, v, None, True)
+    shard = lambda t: t.chunk(world, 1)[rank].contiguous()
+    out = cp.context_parallel_2d(shard(q), shard(k), shard(v), causal=True,
+                                 inter_process_group=cp.get_inter_cp_process_group(),
+                                 intra_process_group=cp.get_intra_cp_process_group())
+    assert torch.allclose(out, shard(ref), atol=1e-4, rtol=1e-3)
+
+
+def test_context_parallel_2d():
+    run_distributed(_cp2d_worker, 4)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _cp_model_worker(rank, world, mode):
+    import torchacc_b200 as ta
+    ids = _data(B=2, S=32)
+    ref_loss, _ = _reference_loss_and_grads(ids)
+    model = _tiny()
+    cfg = ta.Config()
+    cfg.dist.sp.size = 2
+    cfg.dist.sp.mode = mode
+    model = ta.accelerate(model, config=cfg)
+    out = model(ids, labels=ids)
+    import torch.distributed as dist
+    l = out["loss"].detach().clone()
+    dist.all_reduce(l)
+    assert abs(float(l) / world - ref_loss) < 2e-2, (float(l) / world, ref_loss)
+    out["loss"].backward()
+
+
+@pytest.mark.parametrize("mode", ["ulysses", "ring"])
+def test_context_parallel_model(mode):
+    run_distributed(_cp_model_worker, 2, args=(mode,))

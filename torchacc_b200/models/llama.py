@@ -220,11 +220,18 @@ class LlamaModel(nn.Module):
         return self._rope
 
     def forward(self, input_ids, position_ids=None, cu_seqlens=None):
+        if self.pctx.cp_mesh is not None:
+            # context parallel: every rank receives the full sequence and keeps its own shard of the tokens
+            from ..ops.context_parallel import cp_shard_sequence
+            input_ids = cp_shard_sequence(input_ids, 1, self.pctx)
+            if position_ids is not None:
+                position_ids = cp_shard_sequence(position_ids, 1, self.pctx)
         B, S = input_ids.shape
         h = self.embed_tokens(input_ids.reshape(-1))                          # [T, H]
         rope = self.rope(h.device)
-        if S > rope[0].shape[0]:
-            raise ValueError(f"sequence length {S} exceeds max_position_embeddings {rope[0].shape[0]}")
+        s_full = S * (self.pctx.cp_mesh.get_sp_num() if self.pctx.cp_mesh is not None else 1)
+        if s_full > rope[0].shape[0]:
+            raise ValueError(f"sequence length {s_full} exceeds max_position_embeddings {rope[0].shape[0]}")
         pos = position_ids.reshape(-1).to(torch.int32) if position_ids is not None else None
         tp = self.pctx.tp
         wn = self.norm.weight
@@ -291,6 +298,9 @@ class LlamaForCausalLM(nn.Module):
                     lab = lab.masked_fill(nxt_is_start, -100)
             else:
                 lab = labels
+            if self.model.pctx.cp_mesh is not None:
+                from ..ops.context_parallel import cp_shard_sequence
+                lab = cp_shard_sequence(lab, 1, self.model.pctx)
             tp = self.model.pctx.tp
             if tp is not None:
                 from ..parallel.tp import gather_tokens, vocab_parallel_cross_entropy
@@ -302,6 +312,8 @@ class LlamaForCausalLM(nn.Module):
                                                          n_valid_total=n_valid_total)
         if return_logits or (labels is None and return_logits is None):
             tp = self.model.pctx.tp
+            if self.model.pctx.cp_mesh is not None:
+                S = S // self.model.pctx.cp_mesh.get_sp_num()      # logits of the local sequence shard
             if tp is not None:
                 from ..parallel.tp import gather_tokens
                 hid = gather_tokens(hidden, tp) if tp.sequence_parallel else hidden

@@ -30,7 +30,9 @@ class DistributedParallel(ParallelModule):
             inner = m._get_underlay_model()
         else:
             inner = m
-        wants_engine = self.has_fsdp or self.has_dp or config.compute.dtype != torch.float32 or kwargs.get("force_engine", False)
+        # every distributed configuration runs on the flat-parameter engine (uniform optimizer / clipping /
+        # checkpoint surface); with dp == fsdp == 1 it degenerates to a local engine without collectives
+        wants_engine = True
         if self.has_fsdp:
             inner = FullyShardedDataParallel(inner, config)
         elif wants_engine:

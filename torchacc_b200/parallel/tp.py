@@ -231,7 +231,11 @@ class _VocabParallelCE(torch.autograd.Function):
                 first = False
         if want_w and view is not None:
             w_local._tb_grad_ready = True
-        tp.coll.all_reduce(dh)   # each rank contributed the part of dh that flows through its vocab slice
+        # Each rank holds the part of dh that flows through ITS vocab slice.  With sequence parallelism the caller
+        # gathered the tokens (gather_tokens) and that op's backward reduce-scatters these partials; without it the
+        # hidden states are replicated and the full gradient is needed on every rank.
+        if not tp.sequence_parallel:
+            tp.coll.all_reduce(dh)
         ctx.save_for_backward(dh, dw if (want_w and view is None) else None)
         ctx.own_dw = want_w and view is None
         return total / n_valid
