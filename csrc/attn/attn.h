@@ -18,4 +18,7 @@ cudaError_t flash_attn_bwd(const void* q, const void* k, const void* v, const vo
                            int wl, int wr, long long Tq, long long Tk, long long dq_ts, long long dk_ts,
                            long long dv_ts, int num_sms, cudaStream_t stream);
 
+// Debug: when non-null, CTA (0,0,0) of the backward kernel writes clock64() stamps [64 iterations][16 slots].
+void flash_attn_bwd_set_trace(long long* p);
+
 }  // namespace tb

@@ -43,7 +43,14 @@ struct BwdArgs {
   long long dk_ts, dv_ts;
   float scale_log2, scale;
   int causal, wl, wr;
+  long long* trace;   // optional [64 iterations][16 slots] clock64 stamps of CTA (0,0,0) (debug / profiling)
 };
+
+#define TB_TRACE(slot)                                                                             \
+  do {                                                                                             \
+    if (args.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 64) \
+      args.trace[it * 16 + (slot)] = clock64();                                                    \
+  } while (0)
 
 template <int D>
 struct BwdSmem {
@@ -116,8 +123,10 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t kv_full = bar;
   auto qdo_full = [&](int s) { return bar + 8u * (1 + s); };
   auto qdo_empty = [&](int s) { return bar + 8u * (3 + s); };
-  const uint32_t sdp_full = bar + 8u * 5, pds_ready = bar + 8u * 6, dq_full = bar + 8u * 7, r1_free = bar + 8u * 8;
-  const uint32_t dkv_full = bar + 8u * 9, tmem_slot = bar + 8u * 10;
+  const uint32_t s_full = bar + 8u * 5, pds_ready = bar + 8u * 6, dq_full = bar + 8u * 7, r1_free = bar + 8u * 8;
+  const uint32_t dkv_full = bar + 8u * 9, dp_full = bar + 8u * 10;
+  auto qs_free = [&](int s) { return bar + 8u * (11 + s); };   // Q stage no longer read by the dQ bulk reduce
+  const uint32_t tmem_slot = bar + 8u * 13;
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
@@ -126,7 +135,9 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   if (warp_idx == 1 && lane == 0) {
     mbar_init(kv_full, 1);
     for (int s = 0; s < kQStages; ++s) { mbar_init(qdo_full(s), 1); mbar_init(qdo_empty(s), 1); }
-    mbar_init(sdp_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(dp_full, 1);
+    for (int s = 0; s < kQStages; ++s) mbar_init(qs_free(s), 2);
     mbar_init(pds_ready, 8);
     mbar_init(dq_full, 1);
     mbar_init(r1_free, 8);
@@ -156,6 +167,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % kQStages;
         mbar_wait(qdo_empty(s), ((it / kQStages) & 1) ^ 1);
+        mbar_wait(qs_free(s), ((it / kQStages) & 1) ^ 1);   // Q stage doubles as dQ staging for the bulk reduce
         mbar_arrive_expect_tx(qdo_full(s), 2 * S::kTileBytes);
         const int h = iter_head(it), row0 = q_start + iter_m0(it);
 #pragma unroll
@@ -174,22 +186,27 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const uint32_t q_s = sQ + s * S::kTileBytes, do_s = sDO + s * S::kTileBytes;
         mbar_wait(qdo_full(s), (it / kQStages) & 1);
         tc_fence_after();
+        TB_TRACE(0);
         // (a) S^T = K Q^T -> R0   (in-order pipe: runs after (c) of the previous iteration consumed P^T in R0)
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)
           umma_ss_f16<1>(tmem_base + R0, desc_kmajor_sw128(sK + (kk / 4) * 16384, kk % 4),
                          desc_kmajor_sw128(q_s + (kk / 4) * 16384, kk % 4), kIdescST, kk != 0);
+        umma_commit(s_full);    // the softmax warps start exponentiating while dP^T is still being produced
         // (b) dP^T = V dO^T -> R1 (needs dQ of the previous iteration read out of R1)
         mbar_wait(r1_free, (it & 1) ^ 1);
         tc_fence_after();
+        TB_TRACE(1);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)
           umma_ss_f16<1>(tmem_base + R1, desc_kmajor_sw128(sV + (kk / 4) * 16384, kk % 4),
                          desc_kmajor_sw128(do_s + (kk / 4) * 16384, kk % 4), kIdescST, kk != 0);
-        umma_commit(sdp_full);
+        umma_commit(dp_full);
+        TB_TRACE(2);
         // softmax warps: P^T -> R0 (TMEM), dS^T -> smem
         mbar_wait(pds_ready, it & 1);
         tc_fence_after();
+        TB_TRACE(3);
         // (e) dQ = dS K -> R1
 #pragma unroll
         for (int kk = 0; kk < kTile / 16; ++kk)
@@ -207,6 +224,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           umma_ts_f16(tmem_base + R2, tmem_base + R0 + kk * 8, desc_mnmajor_sw128(do_s, kk, 16384), kIdescDKV,
                       (it | kk) != 0);
         umma_commit(qdo_empty(s));
+        TB_TRACE(4);
       }
       umma_commit(dkv_full);
     }
@@ -238,8 +256,9 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         stat[kTile + r] = delta_next;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      mbar_wait(sdp_full, it & 1);
+      mbar_wait(s_full, it & 1);
       tc_fence_after();
+      if (warp_idx == 4 && lane == 0) TB_TRACE(5);
       // interior tile: every query row of the tile sees every key of the tile -> no per-element mask
       bool interior = (m0 + kTile <= q_len) && (n0 + kTile <= k_len);
       if (interior) {
@@ -248,14 +267,53 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const int lo_last = (args.wl < 0) ? 0 : max(0, pos_last - args.wl);
         interior = (hi_first >= n0 + kTile - 1) && (lo_last <= n0);
       }
-      // read this group's 64 S^T columns, then make sure BOTH groups are done reading before P^T (which aliases
-      // S^T columns [0,64)) is written
+      // ---- phase 1: P^T = exp2(S^T * scale - LSE) for this group's 64 query columns (needs only S^T) ----
       uint32_t sv[2][32];
       tmem_ld_32x32b_x32(tmem_base + lane_off + R0 + (2 * grp) * 32, sv[0]);
       tmem_ld_32x32b_x32(tmem_base + lane_off + R0 + (2 * grp + 1) * 32, sv[1]);
       tmem_ld_wait();
       tc_fence_before();
-      asm volatile("bar.sync 2, 256;" ::: "memory");
+      asm volatile("bar.sync 2, 256;" ::: "memory");   // both groups read S^T before P^T overwrites its columns
+      tc_fence_after();
+      if (warp_idx == 4 && lane == 0) TB_TRACE(6);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * grp + cc;
+        const float4* lse4 = reinterpret_cast<const float4*>(stat + c * 32);
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4) {
+          const float4 l = lse4[g4];
+          const float ls[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = g4 * 4 + e;
+            bool ok = true;
+            if (!interior) {
+              const int qrow = m0 + c * 32 + i;
+              const int pos = qrow + shift;
+              const int hi = (wr_eff < 0) ? (k_len - 1) : min(k_len - 1, pos + wr_eff);
+              const int lo = (args.wl < 0) ? 0 : max(0, pos - args.wl);
+              ok = key_ok && qrow < q_len && key >= lo && key <= hi;
+            }
+            const float pv = ok ? fast_exp2(fmaf(__uint_as_float(sv[cc][i]), sl2, -ls[e])) : 0.f;
+            sv[cc][i] = __float_as_uint(pv);
+          }
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(sv[cc][2 * i]), __uint_as_float(sv[cc][2 * i + 1]));
+        tmem_st_32x32b_x16(tmem_base + lane_off + R0 + c * 16, pk);   // P^T chunk -> TMEM R0 columns [16c, 16c+16)
+      }
+      // ---- the dS^T buffer (and the previous Q stage) were the staging tiles of the previous dQ bulk reduce ----
+      if (it > 0) {
+        if (q4 == 0 && lane == 0) {
+          tma_store_wait_read<0>();
+          mbar_arrive(qs_free((it - 1) % kQStages));
+        }
+        if (grp == 0) asm volatile("bar.sync 3, 128;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");
+      }
+      // ---- phase 2: dS^T = P^T o (dP^T - delta) * scale ----
+      mbar_wait(dp_full, it & 1);
       tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
@@ -263,30 +321,18 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         uint32_t dpv[32];
         tmem_ld_32x32b_x32(tmem_base + lane_off + R1 + c * 32, dpv);
         tmem_ld_wait();
-        uint32_t pk[16], dsk[16];
+        const float4* dl4 = reinterpret_cast<const float4*>(stat + kTile + c * 32);
+        uint32_t dsk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float pv[2], dv[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int col = c * 32 + 2 * i + e;   // query row inside the tile
-            bool ok = true;
-            if (!interior) {
-              const int qrow = m0 + col;
-              const int pos = qrow + shift;
-              const int hi = (wr_eff < 0) ? (k_len - 1) : min(k_len - 1, pos + wr_eff);
-              const int lo = (args.wl < 0) ? 0 : max(0, pos - args.wl);
-              ok = key_ok && qrow < q_len && key >= lo && key <= hi;
-            }
-            const float p = ok ? fast_exp2(fmaf(__uint_as_float(sv[cc][2 * i + e]), sl2, -stat[col])) : 0.f;
-            pv[e] = p;
-            dv[e] = p * (__uint_as_float(dpv[2 * i + e]) - stat[kTile + col]) * sc;
-          }
-          pk[i] = pack_bf16x2(pv[0], pv[1]);
-          dsk[i] = pack_bf16x2(dv[0], dv[1]);
+        for (int g4 = 0; g4 < 8; ++g4) {
+          const float4 dl = dl4[g4];
+          const float d0 = __uint_as_float(sv[cc][g4 * 4 + 0]) * (__uint_as_float(dpv[g4 * 4 + 0]) - dl.x) * sc;
+          const float d1 = __uint_as_float(sv[cc][g4 * 4 + 1]) * (__uint_as_float(dpv[g4 * 4 + 1]) - dl.y) * sc;
+          const float d2 = __uint_as_float(sv[cc][g4 * 4 + 2]) * (__uint_as_float(dpv[g4 * 4 + 2]) - dl.z) * sc;
+          const float d3 = __uint_as_float(sv[cc][g4 * 4 + 3]) * (__uint_as_float(dpv[g4 * 4 + 3]) - dl.w) * sc;
+          dsk[g4 * 2] = pack_bf16x2(d0, d1);
+          dsk[g4 * 2 + 1] = pack_bf16x2(d2, d3);
         }
-        // P^T chunk -> TMEM R0 columns [16c, 16c+16)
-        tmem_st_32x32b_x16(tmem_base + lane_off + R0 + c * 16, pk);
         // dS^T chunk -> smem row r (keys), 64 bytes = 4 x 16B units, 128B-swizzled
         const uint32_t row_base = sDS + (c >> 1) * 16384 + r * 128;
 #pragma unroll
@@ -302,17 +348,22 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_ready);
+      if (warp_idx == 4 && lane == 0) TB_TRACE(7);
       // prefetch the next tile's statistics while the tensor core works
       if (grp == 0 && it + 1 < n_iter) fetch_stats(it + 1);
-      // dQ tile (lane r = query row m0 + r): TMEM -> swizzled fp32 staging in this group's half of the dS^T buffer
-      // -> TMA bulk reduce-add into the fp32 dQ accumulator.  Group g owns D columns [g*D/2, (g+1)*D/2).
+      // ---- dQ tile (lane r = query row m0 + r): TMEM -> swizzled fp32 staging -> ONE round of TMA bulk
+      // reduce-adds per group; nobody waits for them here (the wait sits at the top of the next iteration).
+      // Group g owns D columns [g*D/2, (g+1)*D/2): box 0 is staged in its half of the dS^T buffer, box 1 in its
+      // half of the Q stage (both are dead once (e) and (d) retired).
       mbar_wait(dq_full, it & 1);
       tc_fence_after();
+      if (warp_idx == 4 && lane == 0) TB_TRACE(8);
       constexpr int kBoxes = D / 64;   // 32-column fp32 boxes per group
-      const uint32_t stage = sDS + grp * 16384;
+      const uint32_t q_stage = sQ + (it % kQStages) * S::kTileBytes;
 #pragma unroll
       for (int bx = 0; bx < kBoxes; ++bx) {
         const int col0 = grp * (D / 2) + bx * 32;
+        const uint32_t stage = (bx == 0 ? sDS : q_stage) + grp * 16384;
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + lane_off + R1 + col0, v);
         tmem_ld_wait();
@@ -323,18 +374,20 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                        "r"(v[4 * u + 1]), "r"(v[4 * u + 2]), "r"(v[4 * u + 3])
                        : "memory");
         }
-        fence_proxy_async_smem();
-        if (grp == 0) asm volatile("bar.sync 3, 128;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");
-        if (q4 == 0 && lane == 0) {
-          tma_reduce_add_2d(&tmap_dq, stage, h * D + col0, q_start + m0);
-          tma_store_commit();
-          tma_store_wait_read<0>();   // staging tile may be overwritten again
-        }
-        if (grp == 0) asm volatile("bar.sync 3, 128;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");
       }
+      fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(r1_free);
+      if (lane == 0) mbar_arrive(r1_free);        // R1 has been read out: dP^T of the next tile may land
+      if (grp == 0) asm volatile("bar.sync 3, 128;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");
+      if (q4 == 0 && lane == 0) {
+#pragma unroll
+        for (int bx = 0; bx < kBoxes; ++bx)
+          tma_reduce_add_2d(&tmap_dq, (bx == 0 ? sDS : q_stage) + grp * 16384, h * D + grp * (D / 2) + bx * 32,
+                            q_start + m0);
+        tma_store_commit();
+      }
+      if (warp_idx == 4 && lane == 0) TB_TRACE(9);
     }
     if (q4 == 0 && lane == 0) tma_store_wait<0>();   // all bulk reductions of this thread have landed
     // ---- epilogue: dV (R2), dK (R3) -> bf16; each group writes half of the D columns ----
@@ -419,6 +472,9 @@ bwd_convert_dq_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restric
   }
 }
 
+static long long* g_bwd_trace = nullptr;
+void flash_attn_bwd_set_trace(long long* p) { g_bwd_trace = p; }
+
 static CUtensorMap make_map_thd_b(const void* base, long long tokens, int heads, int D, long long ts) {
   uint64_t dims[3] = {(uint64_t)D, (uint64_t)heads, (uint64_t)tokens};
   uint64_t strides[2] = {(uint64_t)D * 2, (uint64_t)ts * 2};
@@ -495,6 +551,7 @@ cudaError_t flash_attn_bwd(const void* q, const void* k, const void* v, const vo
   a.scale_log2 = scale * 1.4426950408889634f;
   a.causal = causal ? 1 : 0;
   a.wl = wl; a.wr = wr;
+  a.trace = g_bwd_trace;
   const int max_k = cu_k ? (int)Tk : Sk;
   const int num_k_tiles = (max_k + kTile - 1) / kTile;
   cudaError_t e = (D == 128) ? launch_bwd<128>(mq, mk, mv, mdo, mdq, a, num_k_tiles, stream)

@@ -143,3 +143,7 @@ TB_API int tb_symm_all_to_all(const uint64_t* peers, const uint64_t* pads, long 
   return (int)tb::symm_all_to_all(peers, pads, (size_t)src_off, P<void>(out), (size_t)chunk_bytes, rank, world, channel,
                                   epoch, P<uint32_t>(counter), num_sms, S(stream));
 }
+TB_API int tb_flash_attn_bwd_set_trace(uint64_t ptr) {
+  tb::flash_attn_bwd_set_trace(P<long long>(ptr));
+  return 0;
+}

@@ -303,7 +303,7 @@ class FlatParamUnit:
                 self.grad_accumulated = True
             else:
                 if fp.grad is None:
-                    fp.grad = self.grad_full.to(torch.float32)
+                    fp.grad = self.grad_full.to(torch.float32, copy=True)   # never alias the reusable flat buffer
                 else:
                     fp.grad.add_(self.grad_full)
             self.grad_full = None
@@ -580,13 +580,16 @@ class ShardingEngine:
     def _final_callback(self):
         self._callback_queued = False
         for unit in self._final_units:
+            # units whose inputs carry no gradient (embedding/root): reduce now, after the whole backward.
+            # The list persists across backward passes (1F1B runs several forwards before the first backward).
+            pending = unit.grad_full is not None or any(i.tensor.grad is not None for i in unit.infos)
+            if not pending:
+                continue
             if unit.grad_full is None:
                 unit.prepare_grad_buffer()
-            # units whose inputs carry no gradient (embedding/root): reduce now, after the whole backward
             unit.reduce_grads()
             if self.reshard:
                 unit.reshard()
-        self._final_units = []
         for unit in self.units:  # anything still gathered from prefetch
             if self.reshard and unit.gathered:
                 unit.reshard()

@@ -233,12 +233,11 @@ class SymmCollectives(Collectives):
         per = n // self.world
         st = self._stage(n, t.dtype, "ar_big")
         st.copy_(t)
-        mine = st[self.rank * per:(self.rank + 1) * per]
-        tmp = torch.empty(per, dtype=t.dtype, device=t.device)
-        self.reduce_scatter(st, tmp, scale)
-        # the exit barrier of reduce_scatter guarantees every peer finished reading `st`
-        mine.copy_(tmp)
-        self.all_gather(mine, t)
+        # reduced slice goes to a second symmetric buffer at the SAME offset on every rank (the all-gather kernel
+        # applies one source offset to all peers)
+        red = self._stage(per, t.dtype, "ar_big_out")
+        self.reduce_scatter(st, red, scale)
+        self.all_gather(red, t)
 
     def all_to_all(self, inp: torch.Tensor, out: torch.Tensor) -> None:
         """``out[r*c:(r+1)*c] = inp_of_rank_r[rank*c:(rank+1)*c]`` for equal contiguous chunks."""
