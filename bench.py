@@ -246,8 +246,12 @@ def run_reference(a):
     try:
         import torch
         import torch.distributed as dist
-        import torchacc as ref_ta
+        # transformers first: importing the reference clears torch's decomposition tables at import time
+        # (torchacc/__init__.py:137 -> utils/decompose.py), which breaks a later `import transformers` on torch 2.11
         from transformers import LlamaConfig, LlamaForCausalLM
+        import transformers.models.llama.modeling_llama  # noqa: F401
+        import transformers.modeling_flash_attention_utils  # noqa: F401
+        import torchacc as ref_ta
     except Exception as e:  # noqa: BLE001
         unavailable(f"import failed: {type(e).__name__}: {e}"[:300])
 

@@ -20,5 +20,6 @@ cudaError_t flash_attn_bwd(const void* q, const void* k, const void* v, const vo
 
 // Debug: when non-null, CTA (0,0,0) of the backward kernel writes clock64() stamps [64 iterations][16 slots].
 void flash_attn_bwd_set_trace(long long* p);
+void flash_attn_fwd_set_trace(long long* p);
 
 }  // namespace tb

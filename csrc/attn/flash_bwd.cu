@@ -280,23 +280,25 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       for (int cc = 0; cc < 2; ++cc) {
         const int c = 2 * grp + cc;
         const float4* lse4 = reinterpret_cast<const float4*>(stat + c * 32);
+        // branch-free: exponentiate everything (straight-line FFMA + MUFU so the SFU latency pipelines), then zero
+        // the masked entries of boundary tiles with selects
 #pragma unroll
         for (int g4 = 0; g4 < 8; ++g4) {
           const float4 l = lse4[g4];
-          const float ls[4] = {l.x, l.y, l.z, l.w};
+          sv[cc][g4 * 4 + 0] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(sv[cc][g4 * 4 + 0]), sl2, -l.x)));
+          sv[cc][g4 * 4 + 1] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(sv[cc][g4 * 4 + 1]), sl2, -l.y)));
+          sv[cc][g4 * 4 + 2] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(sv[cc][g4 * 4 + 2]), sl2, -l.z)));
+          sv[cc][g4 * 4 + 3] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(sv[cc][g4 * 4 + 3]), sl2, -l.w)));
+        }
+        if (!interior) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int i = g4 * 4 + e;
-            bool ok = true;
-            if (!interior) {
-              const int qrow = m0 + c * 32 + i;
-              const int pos = qrow + shift;
-              const int hi = (wr_eff < 0) ? (k_len - 1) : min(k_len - 1, pos + wr_eff);
-              const int lo = (args.wl < 0) ? 0 : max(0, pos - args.wl);
-              ok = key_ok && qrow < q_len && key >= lo && key <= hi;
-            }
-            const float pv = ok ? fast_exp2(fmaf(__uint_as_float(sv[cc][i]), sl2, -ls[e])) : 0.f;
-            sv[cc][i] = __float_as_uint(pv);
+          for (int i = 0; i < 32; ++i) {
+            const int qrow = m0 + c * 32 + i;
+            const int pos = qrow + shift;
+            const int hi = (wr_eff < 0) ? (k_len - 1) : min(k_len - 1, pos + wr_eff);
+            const int lo = (args.wl < 0) ? 0 : max(0, pos - args.wl);
+            const bool ok = key_ok && qrow < q_len && key >= lo && key <= hi;
+            sv[cc][i] = ok ? sv[cc][i] : 0u;
           }
         }
         uint32_t pk[16];
@@ -304,6 +306,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(sv[cc][2 * i]), __uint_as_float(sv[cc][2 * i + 1]));
         tmem_st_32x32b_x16(tmem_base + lane_off + R0 + c * 16, pk);   // P^T chunk -> TMEM R0 columns [16c, 16c+16)
       }
+      if (warp_idx == 4 && lane == 0) TB_TRACE(10);   // phase 1 done (P^T stores issued)
       // ---- the dS^T buffer (and the previous Q stage) were the staging tiles of the previous dQ bulk reduce ----
       if (it > 0) {
         if (q4 == 0 && lane == 0) {
@@ -312,9 +315,11 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         if (grp == 0) asm volatile("bar.sync 3, 128;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");
       }
+      if (warp_idx == 4 && lane == 0) TB_TRACE(11);   // staging released
       // ---- phase 2: dS^T = P^T o (dP^T - delta) * scale ----
       mbar_wait(dp_full, it & 1);
       tc_fence_after();
+      if (warp_idx == 4 && lane == 0) TB_TRACE(12);
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int c = 2 * grp + cc;
@@ -343,6 +348,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                        : "memory");
         }
       }
+      if (warp_idx == 4 && lane == 0) TB_TRACE(13);   // phase 2 compute + smem stores issued
       tmem_st_wait();
       fence_proxy_async_smem();
       tc_fence_before();

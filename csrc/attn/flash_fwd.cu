@@ -42,7 +42,14 @@ struct FwdArgs {
   float scale_log2;
   int causal, wl, wr;
   int num_q_tiles;
+  long long* trace;   // optional [64 tiles][16 slots] clock64 stamps of the first CTA (debug / profiling)
 };
+
+#define TB_FTRACE(slot)                                                                            \
+  do {                                                                                             \
+    if (args.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && t < 64)  \
+      args.trace[t * 16 + (slot)] = clock64();                                                     \
+  } while (0)
 
 template <int D>
 struct FwdSmem {
@@ -211,11 +218,13 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           mbar_wait(s_free((t + 1) & 1), (((t + 1) >> 1) & 1) ^ 1);
           tc_fence_after();
           issue_s(t + 1);
+          TB_FTRACE(0);
         }
         const int s = t % kVStages;
         mbar_wait(v_full(s), (t / kVStages) & 1);
         mbar_wait(p_ready, t & 1);
         tc_fence_after();
+        TB_FTRACE(1);
         const uint32_t vb = sV + s * S::kKBytes;
 #pragma unroll
         for (int kk = 0; kk < kBN / 16; ++kk) {
@@ -246,6 +255,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       const int n0 = (j_lo + t) * kBN + grp * 64;   // first key column owned by this thread
       mbar_wait(s_full(t & 1), (t >> 1) & 1);
       tc_fence_after();
+      if (warp_idx == 4 && lane == 0) TB_FTRACE(2);
       uint32_t sv[2][32];
       const uint32_t s_addr = tmem_base + lane_off + kTmemS0 + (t & 1) * kBN + grp * 64;
       tmem_ld_32x32b_x32(s_addr, sv[0]);
@@ -279,6 +289,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       xchg[grp * kBM + r] = mx;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mx = fmaxf(mx, xchg[(grp ^ 1) * kBM + r]);
+      if (warp_idx == 4 && lane == 0) TB_FTRACE(3);
       const float m_new = fmaxf(m_used, mx * sl2);
       // lazy rescale: only move the reference max when it grew by more than the threshold
       float alpha = 1.f;
@@ -303,12 +314,14 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           pk[c][i] = pack_bf16x2(p0, p1);
         }
       l_part = l_part * alpha + psum;
+      if (warp_idx == 4 && lane == 0) TB_FTRACE(4);
 
       // P buffer and O accumulator are free once P V(t-1) retired
       if (t > 0) {
         mbar_wait(o_done, (t - 1) & 1);
         tc_fence_after();
       }
+      if (warp_idx == 4 && lane == 0) TB_FTRACE(5);
       // P -> smem, K-major SWIZZLE_128B: this group's 64 columns form one 16 KB chunk; 16-byte unit u of row r
       // lives at unit (u ^ (r & 7))
       const uint32_t chunk_base = sP + grp * 16384 + r * 128;
@@ -339,6 +352,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
+      if (warp_idx == 4 && lane == 0) TB_FTRACE(6);
     }
 
     // ---- epilogue: O / l -> bf16, LSE ----
@@ -382,6 +396,9 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     tmem_dealloc<1>(tmem_base, 512);
   }
 }
+
+static long long* g_fwd_trace = nullptr;
+void flash_attn_fwd_set_trace(long long* p) { g_fwd_trace = p; }
 
 // 3-D tensor map over a token-major [tokens, heads, D] bf16 tensor with token stride `ts` elements.
 static CUtensorMap make_map_thd(const void* base, long long tokens, int heads, int D, long long ts) {
@@ -434,6 +451,7 @@ cudaError_t flash_attn_fwd(const void* q, const void* k, const void* v, void* o,
   a.scale_log2 = scale * 1.4426950408889634f;
   a.causal = causal ? 1 : 0;
   a.wl = wl; a.wr = wr;
+  a.trace = g_fwd_trace;
   const int mq_len = cu_q ? (max_q_len > 0 ? max_q_len : (int)Tq) : Sq;
   a.num_q_tiles = (mq_len + kBM - 1) / kBM;
   if (D == 128) return launch_fwd<128>(mq, mk, mv, a, mq_len, stream);

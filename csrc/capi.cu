@@ -147,3 +147,7 @@ TB_API int tb_flash_attn_bwd_set_trace(uint64_t ptr) {
   tb::flash_attn_bwd_set_trace(P<long long>(ptr));
   return 0;
 }
+TB_API int tb_flash_attn_fwd_set_trace(uint64_t ptr) {
+  tb::flash_attn_fwd_set_trace(P<long long>(ptr));
+  return 0;
+}
