@@ -269,6 +269,12 @@ def run_reference(a):
         with torch.no_grad():
             for p in model.parameters():
                 p.normal_(0, 0.02)
+        # transformers 5.x builds `SiLUActivation` objects; the reference's liger MLP patch only accepts `nn.SiLU`
+        # (torchacc/ops/liger.py:21-24).  Swapping the activation OBJECT on the user's model keeps the reference's
+        # kernel patches active (the alternative, config.compute.disable_kernel_patches, would slow the reference).
+        for m in model.modules():
+            if type(getattr(m, "act_fn", None)).__name__ == "SiLUActivation":
+                m.act_fn = torch.nn.SiLU()
         if not a.no_gc:
             model.gradient_checkpointing_enable()   # the reference's eager path has no working GC of its own
         cfg = ref_ta.Config()

@@ -151,3 +151,25 @@ TB_API int tb_flash_attn_fwd_set_trace(uint64_t ptr) {
   tb::flash_attn_fwd_set_trace(P<long long>(ptr));
   return 0;
 }
+
+// ---- fused tensor-parallel GEMMs ---------------------------------------------------------------------------
+TB_API int tb_ag_gemm_bf16(const uint64_t* peer_a_full, const uint64_t* pads, uint64_t a_full, uint64_t B, uint64_t D,
+                           uint64_t bias, int rows_per_rank, int N, int K, long long ldb, long long ldd, int b_mn_major,
+                           int rank, int world, uint64_t flags, uint32_t flag_target, uint64_t block_counter,
+                           int channel, uint32_t epoch, int comm_clusters, int num_sms, uint64_t stream) {
+  return (int)tb::ag_gemm_bf16(peer_a_full, pads, P<void>(a_full), P<void>(B), P<void>(D), P<void>(bias), rows_per_rank,
+                               N, K, ldb, ldd, b_mn_major != 0, rank, world, P<uint32_t>(flags), flag_target,
+                               P<uint32_t>(block_counter), channel, epoch, comm_clusters, num_sms, S(stream));
+}
+TB_API int tb_gemm_rs_bf16(uint64_t A, uint64_t B, const uint64_t* peer_stage, const uint64_t* peer_counters,
+                           const uint64_t* pads, int rows_per_rank, int N, int K, long long lda, long long ldb,
+                           int a_mn_major, int b_mn_major, int rank, int world, int channel, uint32_t epoch,
+                           int num_sms, uint64_t stream) {
+  return (int)tb::gemm_rs_bf16(P<void>(A), P<void>(B), peer_stage, peer_counters, pads, rows_per_rank, N, K, lda, ldb,
+                               a_mn_major != 0, b_mn_major != 0, rank, world, channel, epoch, num_sms, S(stream));
+}
+TB_API int tb_rs_reduce_bf16(uint64_t stage, uint64_t counters, uint32_t expected, uint64_t residual, uint64_t out,
+                             long long n, int world, long long slot_stride, int num_sms, uint64_t stream) {
+  return (int)tb::rs_reduce_bf16(P<void>(stage), P<uint32_t>(counters), expected, P<void>(residual), P<void>(out), n,
+                                 world, slot_stride, num_sms, S(stream));
+}

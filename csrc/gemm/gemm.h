@@ -2,6 +2,7 @@
 // without any PyTorch headers; csrc/bindings.cpp wraps them as torch ops.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 namespace tb {
 
@@ -14,5 +15,23 @@ namespace tb {
 cudaError_t gemm_bf16(const void* A, const void* B, void* D, const void* bias, int M, int N, int K, long long lda,
                       long long ldb, long long ldd, bool a_mn_major, bool b_mn_major, bool out_fp32, bool accumulate,
                       int cluster, int num_sms, cudaStream_t stream);
+
+// ---- fused tensor-parallel kernels (see the FuseArgs comment in gemm_bf16.cu) ----
+// all-gather -> GEMM: D[world*rows, N] = gather(A)[world*rows, K] * B_op^T.  `a_full` is this rank's symmetric
+// gathered buffer whose own row block is already filled; `peer_a_full[r]` is rank r's mapping of the same buffer.
+cudaError_t ag_gemm_bf16(const uint64_t* peer_a_full, const uint64_t* pad_ptrs, void* a_full, const void* B, void* D,
+                         const void* bias, int rows_per_rank, int N, int K, long long ldb, long long ldd,
+                         bool b_mn_major, int rank, int world, uint32_t* flags, uint32_t flag_target,
+                         uint32_t* block_counter, int channel, uint32_t epoch, int comm_clusters, int num_sms,
+                         cudaStream_t stream);
+// GEMM -> reduce-scatter, part 1: partial tiles are stored into the owner rank's staging slot [rank] (peer stores)
+// and counted in peer_counters[owner][rank] (4 arrivals per 128-row CTA tile).
+cudaError_t gemm_rs_bf16(const void* A, const void* B, const uint64_t* peer_stage, const uint64_t* peer_counters,
+                         const uint64_t* pad_ptrs, int rows_per_rank, int N, int K, long long lda, long long ldb,
+                         bool a_mn_major, bool b_mn_major, int rank, int world, int channel, uint32_t epoch,
+                         int num_sms, cudaStream_t stream);
+// part 2: out = sum over sources of stage[src] (+ residual) once counters[src] >= expected for every source.
+cudaError_t rs_reduce_bf16(const void* stage, const uint32_t* counters, uint32_t expected, const void* residual,
+                           void* out, long long n, int world, long long slot_stride, int num_sms, cudaStream_t stream);
 
 }  // namespace tb

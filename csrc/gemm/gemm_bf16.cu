@@ -20,6 +20,7 @@
 // Reference parity: replaces the cuBLAS GEMMs the reference reaches through nn.Linear
 // (reference torchacc/__init__.py:97-98 forces XLA onto cuBLAS; eager path uses cuBLASLt).
 #include <stdio.h>
+#include <string.h>
 
 #include "../common/ptx.cuh"
 #include "../common/tensormap.h"
@@ -34,6 +35,31 @@ constexpr int kUmmaK = 16;
 constexpr int kNumThreads = 256;
 constexpr int kGroupM = 8;       // tile rasterisation: sweep 8 row-tiles before moving along N
 
+constexpr int kMaxPeers = 8;
+
+// Fusion of the GEMM with the adjacent tensor-parallel collective over NVLink peer memory.
+//   kFuse == 1 (all-gather -> GEMM): the A operand is the token-gathered activation.  Every rank owns a symmetric
+//     [world*rows, K] buffer and has already written ITS row block; the leading `comm_clusters` clusters of this
+//     kernel pull the other ranks' row blocks from peer memory into the local buffer and publish one ready counter
+//     per source rank; the GEMM clusters consume M-tiles in shard order (own block first) and their TMA producers
+//     spin on the counter of the shard they are about to read.  The transfer of shard r+1 overlaps the MMAs of shard r.
+//   kFuse == 2 (GEMM -> reduce-scatter): output row block d belongs to rank d.  The epilogue stores the bf16 partial
+//     tile straight into rank d's staging slot [my_rank] with peer stores and bumps a per-(dst, src) arrival counter
+//     (release.sys); a small reduce kernel on each rank sums the `world` slots in fp32 once all sources have arrived.
+struct FuseArgs {
+  void* peer[kMaxPeers];          // kFuse 1: peers' gathered-A buffers; kFuse 2: peers' staging buffers
+  uint32_t* pads[kMaxPeers];      // symmetric signal pads (entry / exit barriers)
+  uint32_t* peer_cnt[kMaxPeers];  // kFuse 2: peers' arrival counters (array of `world` uint32 per rank)
+  void* a_full;                   // kFuse 1: local gathered buffer
+  uint32_t* flags;                // kFuse 1: local per-source ready counters
+  uint32_t* block_counter;        // exit barrier bookkeeping (local)
+  int rank, world, rows_per_rank, channel;
+  uint32_t epoch;                 // monotonically increasing per call on this channel
+  uint32_t flag_target;           // kFuse 1: counter value that means "shard complete" for this call
+  int comm_clusters;              // kFuse 1: leading clusters acting as copy engines
+  long long slot_stride;          // kFuse 2: elements between two source slots of a staging buffer
+};
+
 struct GemmArgs {
   void* D;
   const __nv_bfloat16* bias;
@@ -42,7 +68,85 @@ struct GemmArgs {
   int accumulate;  // D += result
   int out_fp32;
   int num_m_tiles, num_n_tiles;
+  FuseArgs fuse;
 };
+
+TB_DEVICE void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+TB_DEVICE uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+TB_DEVICE uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+TB_DEVICE void red_release_sys_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+TB_DEVICE void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+TB_DEVICE uint4 ld_volatile_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+
+// Cross-rank barrier on the symmetric signal pad (slot layout as in comm/symm_comm.cu: 16 words per channel,
+// [0,8) entry flags, [8,16) exit flags).  `signal` is true for exactly one CTA per rank.
+// `tid` enumerates the calling threads (threadIdx.x for a whole CTA, the lane id for a single warp).
+TB_DEVICE void fused_barrier(const FuseArgs& f, bool signal, int slot_base, int tid) {
+  if (signal && tid < f.world) {
+    __threadfence_system();
+    st_release_sys_u32(f.pads[tid] + f.channel * 16 + slot_base + f.rank, f.epoch);
+  }
+  if (tid < f.world) {
+    const uint32_t* mine = f.pads[f.rank] + f.channel * 16 + slot_base + tid;
+    while ((int32_t)(ld_acquire_sys_u32(mine) - f.epoch) < 0) {
+    }
+  }
+}
+
+// Copy-engine role of the all-gather -> GEMM kernel (executed by whole clusters).
+TB_DEVICE void gather_role(const FuseArgs& f, int K, int comm_cta, int num_comm_ctas) {
+  fused_barrier(f, comm_cta == 0, 0, threadIdx.x);   // every rank has written its own row block
+  __syncthreads();
+  const size_t shard_vecs = (size_t)f.rows_per_rank * K * 2 / 16;
+  const size_t stride = (size_t)num_comm_ctas * blockDim.x;
+  for (int step = 1; step < f.world; ++step) {
+    const int r = (f.rank + step) % f.world;
+    const uint4* src = reinterpret_cast<const uint4*>(f.peer[r]) + (size_t)r * shard_vecs;
+    uint4* dst = reinterpret_cast<uint4*>(f.a_full) + (size_t)r * shard_vecs;
+    size_t i = (size_t)comm_cta * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < shard_vecs; i += 4 * stride) {
+      uint4 a = ld_volatile_v4(src + i), b = ld_volatile_v4(src + i + stride), c = ld_volatile_v4(src + i + 2 * stride),
+            d = ld_volatile_v4(src + i + 3 * stride);
+      dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+    }
+    for (; i < shard_vecs; i += stride) dst[i] = ld_volatile_v4(src + i);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(f.flags + r, 1u);   // shard r is complete once all comm CTAs have added
+    }
+  }
+  // exit: all my copy CTAs are done reading peers -> tell them; stay until every peer is done reading me
+  __shared__ uint32_t s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(f.block_counter, 1u) == (uint32_t)num_comm_ctas - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) *f.block_counter = 0;
+  fused_barrier(f, true, 8, threadIdx.x);
+}
 
 template <int kCluster>
 struct GemmSmem {
@@ -65,7 +169,19 @@ __device__ __forceinline__ void tile_coords(int t, int num_m_tiles, int num_n_ti
   tn = r / gsize;
 }
 
-template <int kCluster, Major kAMajor, Major kBMajor>
+// tile order for the fused variants: row blocks ("shards") are visited in ring order starting from `first`
+__device__ __forceinline__ void tile_coords_sharded(int t, int tiles_m_per_shard, int num_n_tiles, int first, int world,
+                                                    int& tm, int& tn, int& shard) {
+  const int per_shard = tiles_m_per_shard * num_n_tiles;
+  const int si = t / per_shard;
+  shard = (first + si) % world;
+  int lm, ln;
+  tile_coords(t - si * per_shard, tiles_m_per_shard, num_n_tiles, lm, ln);
+  tm = shard * tiles_m_per_shard + lm;
+  tn = ln;
+}
+
+template <int kCluster, Major kAMajor, Major kBMajor, int kFuse>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmArgs args) {
@@ -94,8 +210,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int num_tiles = args.num_m_tiles * args.num_n_tiles;
   const int num_k_blocks = (args.K + kBlockK - 1) / kBlockK;
-  const int cluster_id = blockIdx.x / kCluster;
-  const int num_clusters = gridDim.x / kCluster;
+  int cluster_id = blockIdx.x / kCluster;
+  int num_clusters = gridDim.x / kCluster;
+  if constexpr (kFuse == 1) {
+    const int cc = args.fuse.comm_clusters;
+    if (cluster_id < cc) {   // copy-engine clusters: no TMEM, no MMA
+      gather_role(args.fuse, args.K, (int)blockIdx.x, cc * kCluster);
+      return;
+    }
+    cluster_id -= cc;
+    num_clusters -= cc;
+  }
+  const int tiles_m_per_shard = (kFuse != 0) ? args.fuse.rows_per_rank / (kBlockMCta * kCluster) : 0;
+  // fused tile order: all-gather starts with the local row block; reduce-scatter ends with it (peers first)
+  const int first_shard = (kFuse == 1) ? args.fuse.rank : ((kFuse == 2) ? (args.fuse.rank + 1) % args.fuse.world : 0);
+  auto coords = [&](int t, int& tm, int& tn, int& shard) {
+    if constexpr (kFuse != 0) {
+      tile_coords_sharded(t, tiles_m_per_shard, args.num_n_tiles, first_shard, args.fuse.world, tm, tn, shard);
+    } else {
+      shard = 0;
+      tile_coords(t, args.num_m_tiles, args.num_n_tiles, tm, tn);
+    }
+  };
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -124,10 +260,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       int it = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        int tm, tn;
-        tile_coords(t, args.num_m_tiles, args.num_n_tiles, tm, tn);
+        int tm, tn, shard;
+        coords(t, tm, tn, shard);
         const int m0 = tm * (int)kUmmaM + (int)cta_rank * kBlockMCta;
         const int n0 = tn * kBlockN + (int)cta_rank * kLoadN;
+        if constexpr (kFuse == 1) {
+          if (shard != args.fuse.rank) {   // wait until the copy clusters have landed this source rank's rows
+            while ((int32_t)(ld_acquire_gpu_u32(args.fuse.flags + shard) - args.fuse.flag_target) < 0) {
+            }
+            fence_proxy_async_all();       // generic-proxy writes of the copy CTAs -> visible to TMA
+          }
+        }
         for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
@@ -191,9 +334,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t tempty_leader =
         (kCluster == 2) ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);  // barrier lives in the leader CTA
     int lt = 0;
+    if constexpr (kFuse == 2) {
+      // nobody may write into a peer's staging buffer before that peer finished reducing the previous call
+      fused_barrier(args.fuse, blockIdx.x == 0 && warp_idx == 4, 0, (int)lane);
+      __syncwarp();
+    }
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++lt) {
-      int tm, tn;
-      tile_coords(t, args.num_m_tiles, args.num_n_tiles, tm, tn);
+      int tm, tn, shard;
+      coords(t, tm, tn, shard);
       const int as = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
       mbar_wait(tfull_bar(as), aph);
@@ -201,6 +349,40 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const long long grow = (long long)tm * kUmmaM + cta_rank * kBlockMCta + q * 32 + lane;
       const int n0 = tn * kBlockN;
       const bool row_ok = grow < args.M;
+      if constexpr (kFuse == 2) {
+        // bf16 partial tile -> staging slot [my rank] of the rank that owns this row block (peer store over NVLink)
+        __nv_bfloat16* dbase = reinterpret_cast<__nv_bfloat16*>(args.fuse.peer[shard]) +
+                               (long long)args.fuse.rank * args.fuse.slot_stride +
+                               (grow - (long long)shard * args.fuse.rows_per_rank) * args.ldd;
+#pragma unroll 1
+        for (int c = 0; c < kBlockN / 32; ++c) {
+          __syncwarp();
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + ((q * 32u) << 16) + as * kBlockN + c * 32, r);
+          tmem_ld_wait();
+          const int gcol = n0 + c * 32;
+          if (!row_ok || gcol + 32 > args.N) continue;
+          uint4* d4 = reinterpret_cast<uint4*>(dbase + gcol);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
+            o.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+            o.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+            o.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+            d4[j] = o;
+          }
+        }
+        tc_fence_before();
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) {
+          red_release_sys_add(args.fuse.peer_cnt[shard] + args.fuse.rank, 1u);   // one arrival per epilogue warp
+          if constexpr (kCluster == 2) mbar_arrive_cluster(tempty_leader + 8u * as);
+          else mbar_arrive(tempty_leader + 8u * as);
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < kBlockN / 32; ++c) {
         __syncwarp();  // tcgen05.ld is warp-collective (.sync.aligned): reconverge after the guarded stores
@@ -294,11 +476,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // ------------------------------------------------------------------------------------------------------
 // Host launcher
 // ------------------------------------------------------------------------------------------------------
-template <int kCluster, Major kAMajor, Major kBMajor>
+template <int kCluster, Major kAMajor, Major kBMajor, int kFuse>
 static cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb_, const GemmArgs& args, int num_sms,
                               cudaStream_t stream) {
   using S = GemmSmem<kCluster>;
-  auto kern = gemm_bf16_kernel<kCluster, kAMajor, kBMajor>;
+  auto kern = gemm_bf16_kernel<kCluster, kAMajor, kBMajor, kFuse>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
@@ -307,7 +489,10 @@ static cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb_, con
   }
   const int num_tiles = args.num_m_tiles * args.num_n_tiles;
   int clusters = num_sms / kCluster;
+  if (kFuse == 1) clusters -= args.fuse.comm_clusters;   // copy clusters share their SMs with nobody
   if (clusters > num_tiles) clusters = num_tiles;
+  if (clusters < 1) clusters = 1;
+  if (kFuse == 1) clusters += args.fuse.comm_clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * kCluster);
   cfg.blockDim = dim3(kNumThreads);
@@ -321,6 +506,21 @@ static cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb_, con
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, ta, tb_, args);
+}
+
+static bool fill_common(GemmArgs& args, void* D, const void* bias, int M, int N, int K, long long ldd, bool out_fp32,
+                        bool accumulate, int cluster) {
+  args.D = D;
+  args.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  args.M = M; args.N = N; args.K = K;
+  args.ldd = ldd;
+  args.accumulate = accumulate ? 1 : 0;
+  args.out_fp32 = out_fp32 ? 1 : 0;
+  const int tile_m = kBlockMCta * cluster;
+  args.num_m_tiles = (M + tile_m - 1) / tile_m;
+  args.num_n_tiles = (N + kBlockN - 1) / kBlockN;
+  memset(&args.fuse, 0, sizeof(args.fuse));
+  return true;
 }
 
 cudaError_t gemm_bf16(const void* A, const void* B, void* D, const void* bias, int M, int N, int K, long long lda,
@@ -340,17 +540,9 @@ cudaError_t gemm_bf16(const void* A, const void* B, void* D, const void* bias, i
     return cudaErrorInvalidValue;
   }
   GemmArgs args;
-  args.D = D;
-  args.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
-  args.M = M; args.N = N; args.K = K;
-  args.ldd = ldd;
-  args.accumulate = accumulate ? 1 : 0;
-  args.out_fp32 = out_fp32 ? 1 : 0;
-  const int tile_m = kBlockMCta * cluster;
-  args.num_m_tiles = (M + tile_m - 1) / tile_m;
-  args.num_n_tiles = (N + kBlockN - 1) / kBlockN;
+  fill_common(args, D, bias, M, N, K, ldd, out_fp32, accumulate, cluster);
 
-#define TB_DISPATCH(CL, AM, BM) return launch_one<CL, AM, BM>(ta, tbm, args, num_sms, stream)
+#define TB_DISPATCH(CL, AM, BM) return launch_one<CL, AM, BM, 0>(ta, tbm, args, num_sms, stream)
   if (cluster == 2) {
     if (!a_mn_major && !b_mn_major) TB_DISPATCH(2, Major::K, Major::K);
     if (!a_mn_major && b_mn_major) TB_DISPATCH(2, Major::K, Major::MN);
@@ -363,6 +555,123 @@ cudaError_t gemm_bf16(const void* A, const void* B, void* D, const void* bias, i
     TB_DISPATCH(1, Major::MN, Major::MN);
   }
 #undef TB_DISPATCH
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Fused tensor-parallel entry points (cta_group::2 kernels only)
+// ------------------------------------------------------------------------------------------------------
+static cudaError_t check_fused(int world, int rows_per_rank, int N, int channel) {
+  if (world < 2 || world > kMaxPeers || channel < 0 || channel >= 64) return cudaErrorInvalidValue;
+  if (rows_per_rank % (kBlockMCta * 2) != 0) return cudaErrorInvalidValue;   // M tiles must not straddle ranks
+  if (N % 8 != 0) return cudaErrorInvalidValue;
+  return cudaSuccess;
+}
+
+cudaError_t ag_gemm_bf16(const uint64_t* peer_a_full, const uint64_t* pad_ptrs, void* a_full, const void* B, void* D,
+                         const void* bias, int rows_per_rank, int N, int K, long long ldb, long long ldd,
+                         bool b_mn_major, int rank, int world, uint32_t* flags, uint32_t flag_target,
+                         uint32_t* block_counter, int channel, uint32_t epoch, int comm_clusters, int num_sms,
+                         cudaStream_t stream) {
+  cudaError_t e = check_fused(world, rows_per_rank, N, channel);
+  if (e != cudaSuccess) return e;
+  if (K % 8 != 0 || comm_clusters < 1 || comm_clusters * 2 >= num_sms) return cudaErrorInvalidValue;
+  const int M = rows_per_rank * world;
+  CUtensorMap ta, tbm;
+  try {
+    ta = make_map_2d_bf16(a_full, M, K, K, kBlockK, kBlockMCta);
+    tbm = b_mn_major ? make_map_2d_bf16(B, K, N, ldb, 64, kBlockK) : make_map_2d_bf16(B, N, K, ldb, kBlockK, kBlockN / 2);
+  } catch (const std::exception& ex) {
+    fprintf(stderr, "%s\n", ex.what());
+    return cudaErrorInvalidValue;
+  }
+  GemmArgs args;
+  fill_common(args, D, bias, M, N, K, ldd, false, false, 2);
+  FuseArgs& f = args.fuse;
+  for (int i = 0; i < world; ++i) {
+    f.peer[i] = reinterpret_cast<void*>(peer_a_full[i]);
+    f.pads[i] = reinterpret_cast<uint32_t*>(pad_ptrs[i]);
+  }
+  f.a_full = a_full; f.flags = flags; f.block_counter = block_counter;
+  f.rank = rank; f.world = world; f.rows_per_rank = rows_per_rank; f.channel = channel;
+  f.epoch = epoch; f.flag_target = flag_target; f.comm_clusters = comm_clusters;
+  if (b_mn_major) return launch_one<2, Major::K, Major::MN, 1>(ta, tbm, args, num_sms, stream);
+  return launch_one<2, Major::K, Major::K, 1>(ta, tbm, args, num_sms, stream);
+}
+
+cudaError_t gemm_rs_bf16(const void* A, const void* B, const uint64_t* peer_stage, const uint64_t* peer_counters,
+                         const uint64_t* pad_ptrs, int rows_per_rank, int N, int K, long long lda, long long ldb,
+                         bool a_mn_major, bool b_mn_major, int rank, int world, int channel, uint32_t epoch,
+                         int num_sms, cudaStream_t stream) {
+  cudaError_t e = check_fused(world, rows_per_rank, N, channel);
+  if (e != cudaSuccess) return e;
+  if (N % 32 != 0) return cudaErrorInvalidValue;
+  const int M = rows_per_rank * world;
+  CUtensorMap ta, tbm;
+  try {
+    ta = a_mn_major ? make_map_2d_bf16(A, K, M, lda, 64, kBlockK) : make_map_2d_bf16(A, M, K, lda, kBlockK, kBlockMCta);
+    tbm = b_mn_major ? make_map_2d_bf16(B, K, N, ldb, 64, kBlockK) : make_map_2d_bf16(B, N, K, ldb, kBlockK, kBlockN / 2);
+  } catch (const std::exception& ex) {
+    fprintf(stderr, "%s\n", ex.what());
+    return cudaErrorInvalidValue;
+  }
+  GemmArgs args;
+  fill_common(args, nullptr, nullptr, M, N, K, /*ldd=*/N, false, false, 2);
+  FuseArgs& f = args.fuse;
+  for (int i = 0; i < world; ++i) {
+    f.peer[i] = reinterpret_cast<void*>(peer_stage[i]);
+    f.peer_cnt[i] = reinterpret_cast<uint32_t*>(peer_counters[i]);
+    f.pads[i] = reinterpret_cast<uint32_t*>(pad_ptrs[i]);
+  }
+  f.rank = rank; f.world = world; f.rows_per_rank = rows_per_rank; f.channel = channel; f.epoch = epoch;
+  f.slot_stride = (long long)rows_per_rank * N;
+#define TB_RS(AM, BM) return launch_one<2, AM, BM, 2>(ta, tbm, args, num_sms, stream)
+  if (!a_mn_major && !b_mn_major) TB_RS(Major::K, Major::K);
+  if (!a_mn_major && b_mn_major) TB_RS(Major::K, Major::MN);
+  if (a_mn_major && !b_mn_major) TB_RS(Major::MN, Major::K);
+  TB_RS(Major::MN, Major::MN);
+#undef TB_RS
+}
+
+// out[rows, N] = sum_src stage[src][rows, N] (+ residual), once every source has delivered `expected` arrivals.
+__global__ void __launch_bounds__(256)
+rs_reduce_kernel(const __nv_bfloat16* __restrict__ stage, const uint32_t* __restrict__ counters, uint32_t expected,
+                 const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out, long long n, int world,
+                 long long slot_stride) {
+  if (threadIdx.x < world) {
+    while ((int32_t)(ld_acquire_sys_u32(counters + threadIdx.x) - expected) < 0) {
+    }
+  }
+  __syncthreads();
+  const long long nvec = n >> 3;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < world; ++s) {
+      const uint4 u = ld_volatile_v4(reinterpret_cast<const uint4*>(stage + s * slot_stride) + i);
+      float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    }
+    if (residual) {
+      const uint4 u = reinterpret_cast<const uint4*>(residual)[i];
+      float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+    reinterpret_cast<uint4*>(out)[i] = o;
+  }
+}
+
+cudaError_t rs_reduce_bf16(const void* stage, const uint32_t* counters, uint32_t expected, const void* residual,
+                           void* out, long long n, int world, long long slot_stride, int num_sms, cudaStream_t stream) {
+  if (n % 8 != 0) return cudaErrorInvalidValue;
+  long long blocks = ((n >> 3) + 255) / 256;
+  if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
+  if (blocks < 1) blocks = 1;
+  rs_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)stage, counters, expected,
+                                                          (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, n, world,
+                                                          slot_stride);
+  return cudaGetLastError();
 }
 
 }  // namespace tb

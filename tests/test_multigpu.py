@@ -170,3 +170,38 @@ def test_context_parallel_matches_single_gpu(mode):
     dist.all_reduce(t)
     got = (t / WORLD).tolist()
     assert all(abs(a - b) < 6e-2 for a, b in zip(got, ref)), (got, ref)
+
+
+def test_fused_tp_kernels_match_unfused():
+    """all-gather->GEMM and GEMM->reduce-scatter (one kernel each, peer memory) vs NCCL collective + plain GEMM."""
+    from torchacc_b200.parallel.fused_tp import make_fused_tp
+    f = make_fused_tp(dist.group.WORLD, _dev())
+    assert f is not None
+    torch.manual_seed(100 + dist.get_rank())
+    rows, K, N = 512, 1024, 768
+    for it in range(3):   # several calls: exercises buffer / counter / epoch reuse
+        x = (torch.randn(rows, K, device=_dev()) * 0.5).bfloat16()
+        torch.manual_seed(7 + it)
+        w = (torch.randn(N, K, device=_dev()) * 0.05).bfloat16()     # same weight on every rank
+        y, xf = f.ag_gemm(x, w)
+        ref_x = torch.empty(rows * WORLD, K, dtype=torch.bfloat16, device=_dev())
+        dist.all_gather_into_tensor(ref_x, x)
+        assert torch.equal(xf, ref_x), "gathered activation differs"
+        ref_y = ref_x.float() @ w.float().t()
+        assert torch.allclose(y.float(), ref_y, atol=0.15, rtol=3e-2), float((y.float() - ref_y).abs().max())
+        # MN-major B (the dgrad form): y2 = gather(x) @ w2 with w2 stored [K, N2]
+        w2 = (torch.randn(K, 512, device=_dev()) * 0.05).bfloat16()
+        dist.broadcast(w2, 0)
+        y2, _ = f.ag_gemm(x, w2, b_mn_major=True)
+        assert torch.allclose(y2.float(), ref_x.float() @ w2.float(), atol=0.15, rtol=3e-2)
+        # GEMM -> reduce-scatter
+        torch.manual_seed(200 + dist.get_rank() + 10 * it)
+        a = (torch.randn(rows * WORLD, K, device=_dev()) * 0.5).bfloat16()
+        wl = (torch.randn(N, K, device=_dev()) * 0.05).bfloat16()
+        res = torch.randn(rows, N, device=_dev()).bfloat16()
+        out = f.gemm_rs(a, wl, residual=res)
+        part = (a.float() @ wl.float().t()).bfloat16().float()
+        ref = torch.empty(rows, N, device=_dev())
+        dist.reduce_scatter_tensor(ref, part)
+        ref = ref + res.float()
+        assert torch.allclose(out.float(), ref, atol=0.25, rtol=3e-2), float((out.float() - ref).abs().max())

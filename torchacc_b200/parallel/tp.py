@@ -39,6 +39,15 @@ class TPContext:
         self.rank = dist.get_rank(group) if group is not None else 0
         self.sequence_parallel = sequence_parallel and self.size > 1
         self.coll: Collectives = make_collectives(group, device, prefer_symm)
+        # fused all-gather->GEMM / GEMM->reduce-scatter kernels over peer memory (None on CPU / multi-node groups)
+        self.fused = None
+        if prefer_symm and self.size > 1:
+            try:
+                from .fused_tp import make_fused_tp
+                self.fused = make_fused_tp(group, device)
+            except Exception as e:  # pragma: no cover - depends on the box
+                from ..utils.logger import logger
+                logger.warning("fused TP kernels unavailable (%s); using separate collectives", e)
 
 
 def _mm(a, b, **kw):
@@ -74,8 +83,12 @@ class _ColumnParallel(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, bias, tp: TPContext):
         x2 = x.reshape(-1, x.shape[-1])
-        xf = _all_gather_rows(x2, tp) if tp.sequence_parallel else x2
-        y = _mm(xf, w, bias=bias, out_dtype=x.dtype)
+        f = tp.fused
+        if tp.sequence_parallel and f is not None and x2.is_cuda and f.ok_ag(x2.shape[0], w.shape[0], x2.shape[1], x2.dtype):
+            y, _ = f.ag_gemm(x2.contiguous(), w, bias)          # ONE kernel: peer pull of the token shards + tcgen05 GEMM
+        else:
+            xf = _all_gather_rows(x2, tp) if tp.sequence_parallel else x2
+            y = _mm(xf, w, bias=bias, out_dtype=x.dtype)
         ctx.save_for_backward(x2, w)
         ctx.tp, ctx.has_bias = tp, bias is not None
         return y
@@ -86,11 +99,16 @@ class _ColumnParallel(torch.autograd.Function):
         tp: TPContext = ctx.tp
         dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
         xf = _all_gather_rows(x2, tp) if tp.sequence_parallel else x2       # re-gather instead of saving [T, K]
-        dx = _mm(dy2, w, b_mn_major=True, out_dtype=dy2.dtype)               # partial over the tp group
-        if tp.sequence_parallel:
-            dx = _reduce_scatter_rows(dx, tp)
+        f = tp.fused
+        if tp.sequence_parallel and f is not None and dy2.is_cuda and \
+                f.ok_rs(dy2.shape[0] // tp.size, w.shape[1], w.shape[0], dy2.dtype):
+            dx = f.gemm_rs(dy2, w, b_mn_major=True)                          # dgrad GEMM -> reduce-scatter, fused
         else:
-            tp.coll.all_reduce(dx)
+            dx = _mm(dy2, w, b_mn_major=True, out_dtype=dy2.dtype)           # partial over the tp group
+            if tp.sequence_parallel:
+                dx = _reduce_scatter_rows(dx, tp)
+            else:
+                tp.coll.all_reduce(dx)
         dw = _wgrad(dy2, xf, w) if ctx.needs_input_grad[1] else None
         db = dy2.float().sum(0).to(dy2.dtype) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx, dw, db, None
@@ -102,11 +120,16 @@ class _RowParallel(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, tp: TPContext):
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
-        y = _mm(x2, w, out_dtype=x.dtype)
-        if tp.sequence_parallel:
-            y = _reduce_scatter_rows(y, tp)
+        f = tp.fused
+        if tp.sequence_parallel and f is not None and x2.is_cuda and \
+                f.ok_rs(x2.shape[0] // tp.size, w.shape[0], x2.shape[1], x2.dtype):
+            y = f.gemm_rs(x2, w)                                              # GEMM -> reduce-scatter, fused
         else:
-            tp.coll.all_reduce(y)
+            y = _mm(x2, w, out_dtype=x.dtype)
+            if tp.sequence_parallel:
+                y = _reduce_scatter_rows(y, tp)
+            else:
+                tp.coll.all_reduce(y)
         ctx.save_for_backward(x2, w)
         ctx.tp = tp
         return y
@@ -116,8 +139,13 @@ class _RowParallel(torch.autograd.Function):
         x2, w = ctx.saved_tensors
         tp: TPContext = ctx.tp
         dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
-        dyf = _all_gather_rows(dy2, tp) if tp.sequence_parallel else dy2
-        dx = _mm(dyf, w, b_mn_major=True, out_dtype=dy2.dtype)
+        f = tp.fused
+        if tp.sequence_parallel and f is not None and dy2.is_cuda and \
+                f.ok_ag(dy2.shape[0], w.shape[1], dy2.shape[1], dy2.dtype):
+            dx, dyf = f.ag_gemm(dy2, w, b_mn_major=True)                      # all-gather(dy) -> dgrad GEMM, fused
+        else:
+            dyf = _all_gather_rows(dy2, tp) if tp.sequence_parallel else dy2
+            dx = _mm(dyf, w, b_mn_major=True, out_dtype=dy2.dtype)
         dw = _wgrad(dyf, x2, w) if ctx.needs_input_grad[1] else None
         return dx, dw, None
 
