@@ -1,0 +1,25 @@
+# Developer entry points (counterpart of the reference Makefile: `make test` / format).
+PY ?= python
+
+build:
+	$(PY) -c "import __graft_entry__ as g; g.build()"
+
+test: build
+	$(PY) -m pytest tests/ -x -q -m "not gpu"
+
+test-gpu: build
+	$(PY) -m pytest tests/ -x -q -m "gpu and not multigpu"
+
+test-multigpu: build
+	$(PY) -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 -m pytest tests/test_multigpu.py -m multigpu -q
+
+smoke: build
+	$(PY) -c "import __graft_entry__ as g; g.smoke()"
+
+bench: build
+	$(PY) bench.py
+
+sass:
+	cuobjdump -sass torchacc_b200/_C.so | grep -oE "UTC[A-Z0-9.]*MMA[A-Z0-9.]*|UTMA[A-Z0-9.]*|LDTM[A-Z0-9.]*|STTM[A-Z0-9.]*|UTMARED[A-Z0-9.]*" | sort | uniq -c
+
+.PHONY: build test test-gpu test-multigpu smoke bench sass
