@@ -23,6 +23,25 @@ def _data(B=4, S=32, seed=1):
     return torch.randint(0, 128, (B, S), generator=g)
 
 
+def _assert_engine_grads_match(model, ref_grads, atol=2e-5, rtol=1e-4):
+    eng = model.engine
+    meta = model._inner_engine_module().get_shard_metadata()
+    flat = torch.cat([g.float().reshape(-1) for g in eng.grads()])
+    ref_flat = []
+    names = []
+    for u in meta["units"]:
+        buf = torch.zeros(u["padded"])
+        for p in u["params"]:
+            name = (u["prefix"] + "." if u["prefix"] else "") + p["fqn"]
+            buf[p["offset"]:p["offset"] + p["numel"]] = ref_grads[name].reshape(-1)
+            names.append((name, sum(len(b) for b in ref_flat) + p["offset"], p["numel"]))
+        ref_flat.append(buf)
+    ref_flat = torch.cat(ref_flat)
+    bad = [(n, float((flat[o:o + k] - ref_flat[o:o + k]).abs().max()), float(ref_flat[o:o + k].abs().max()))
+           for n, o, k in names if not torch.allclose(flat[o:o + k], ref_flat[o:o + k], atol=atol, rtol=rtol)]
+    assert not bad, bad
+
+
 def _reference_loss_and_grads(ids):
     m = _tiny()
     out = m(ids, labels=ids)
@@ -63,7 +82,7 @@ def test_default_config_is_data_parallel():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def _fsdp_worker(rank, world, hybrid):
+def _fsdp_worker(rank, world, hybrid, sp=1):
     import torchacc_b200 as ta
     ids = _data()
     model = _tiny()
@@ -71,12 +90,15 @@ def _fsdp_worker(rank, world, hybrid):
     cfg.dist.fsdp.size = 2
     if hybrid:
         cfg.dist.dp.size = 2
+    if sp > 1:
+        cfg.dist.sp.size = sp
+        cfg.dist.sp.mode = "ring"
     cfg.dist.fsdp.wrap_layer_cls = {"LlamaDecoderLayer"}
     cfg.memory.gc = True
     model = ta.accelerate(model, config=cfg)
     opt = torch.optim.SGD(model.parameters(), lr=0.1)      # plain torch optimizer on the flat shards
-    nrep = world
-    local = ids.chunk(nrep)[rank]
+    nrep = world // sp
+    local = ids.chunk(nrep)[rank // sp]       # sp is the faster axis: sp peers share one batch shard
     ref = _tiny()
     ref_opt = torch.optim.SGD(ref.parameters(), lr=0.1)
     for _ in range(3):
@@ -99,6 +121,11 @@ def test_fsdp_matches_single_process():
 
 def test_hsdp_matches_single_process():
     run_distributed(_fsdp_worker, 4, args=(True,))
+
+
+def test_fsdp_with_context_parallel_matches_single_process():
+    """fsdp=2 x sp=2: context-parallel peers replicate each parameter shard (HYBRID over the dp x sp group)."""
+    run_distributed(_fsdp_worker, 4, args=(False, 2))
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -304,6 +331,7 @@ def _cp_model_worker(rank, world, mode):
     dist.all_reduce(l)
     assert abs(float(l) / world - ref_loss) < 2e-2, (float(l) / world, ref_loss)
     out["loss"].backward()
+    _assert_engine_grads_match(model, _)
 
 
 @pytest.mark.parametrize("mode", ["ulysses", "ring"])

@@ -300,12 +300,17 @@ class LlamaForCausalLM(nn.Module):
                 lab = labels
             if self.model.pctx.cp_mesh is not None:
                 from ..ops.context_parallel import cp_shard_sequence
+                if n_valid_total is None:
+                    # every rank holds the full labels: normalise by (global valid tokens / sp) so that the mean of
+                    # the per-rank losses (and of their gradients over the replica group) is the exact global loss
+                    n_valid_total = (lab != -100).sum().clamp(min=1).float() / self.model.pctx.cp_mesh.get_sp_num()
                 lab = cp_shard_sequence(lab, 1, self.model.pctx)
             tp = self.model.pctx.tp
             if tp is not None:
                 from ..parallel.tp import gather_tokens, vocab_parallel_cross_entropy
                 hid = gather_tokens(hidden, tp) if tp.sequence_parallel else hidden
-                out["loss"] = vocab_parallel_cross_entropy(hid, self.lm_head.weight, lab.reshape(-1), tp)
+                out["loss"] = vocab_parallel_cross_entropy(hid, self.lm_head.weight, lab.reshape(-1), tp,
+                                                          n_valid_total=n_valid_total)
             else:
                 out["loss"] = fused_linear_cross_entropy(hidden, self.lm_head.weight, lab.reshape(-1),
                                                          chunk_tokens=self.config.loss_chunk_tokens,

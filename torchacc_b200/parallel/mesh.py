@@ -133,6 +133,9 @@ class Mesh:
             self._rank_groups[a] = self.topology.get_axis_comm_lists(a)
         # joint data-parallel group (dp x fsdp): loss averaging, HSDP replicas, grad-norm
         self._rank_groups["data"] = self.topology.get_multi_axis_comm_lists(("dp", "fsdp"))
+        # ranks holding the same parameter shard and seeing different tokens: dp x sp (gradient all-reduce group of
+        # DP / HSDP; context-parallel ranks are data-parallel as far as parameters are concerned)
+        self._rank_groups["replica"] = self.topology.get_multi_axis_comm_lists(("dp", "sp"))
         # sub-groups of the sp axis
         ul, ring = [], []
         for line in self._rank_groups["sp"]:
@@ -145,10 +148,17 @@ class Mesh:
 
     # ---- group construction ---------------------------------------------------------------------------
     def _create_groups(self):
-        for name in ("dp", "fsdp", "pp", "sp", "tp", "data", "ulysses", "ring"):
+        made = {}
+        for name in ("dp", "fsdp", "pp", "sp", "tp", "data", "replica", "ulysses", "ring"):
             lists = self._rank_groups[name]
             if len(lists[0]) == 1:
                 continue
+            key = tuple(sorted(tuple(sorted(r)) for r in lists))
+            if key in made:                      # identical partition already has communicators (e.g. replica == dp)
+                if made[key] in self._groups:
+                    self._groups[name] = self._groups[made[key]]
+                continue
+            made[key] = name
             if len(lists[0]) == self.world_size:
                 self._groups[name] = dist.group.WORLD
                 continue
@@ -216,6 +226,8 @@ class Mesh:
     def get_ulysses_proc_group(self): return self.get_proc_group("ulysses")
     def get_ring_proc_group(self): return self.get_proc_group("ring")
 
+    def get_replica_proc_group(self): return self.get_proc_group("replica")
+    def get_replica_num(self): return self.sizes["dp"] * self.sizes["sp"]
     def get_data_proc_group(self): return self.get_proc_group("data")
     def get_data_num(self): return self.sizes["dp"] * self.sizes["fsdp"]
     def get_data_rank(self): return self._my_ranks("data").index(self.global_rank)

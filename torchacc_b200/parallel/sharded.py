@@ -136,10 +136,10 @@ class FullyShardedDataParallel(_EngineModule):
 
     def __init__(self, model: nn.Module, config, **kwargs):
         mesh = config.get_mesh()
-        hybrid = mesh.get_dp_num() > 1
+        hybrid = mesh.get_replica_num() > 1          # dp x sp ranks replicate each shard
         self.STRATEGY = "HYBRID" if hybrid else "FULL_SHARD"
         super().__init__(model, config, shard_group=mesh.get_fsdp_proc_group(),
-                         replica_group=mesh.get_dp_proc_group() if hybrid else None, **kwargs)
+                         replica_group=mesh.get_replica_proc_group() if hybrid else None, **kwargs)
 
     def fsdp(self, *a, **k):  # reference-compat no-op hook
         return self
@@ -152,7 +152,7 @@ class DataParallel(_EngineModule):
 
     def __init__(self, model: nn.Module, config, **kwargs):
         mesh = config.get_mesh()
-        super().__init__(model, config, shard_group=None, replica_group=mesh.get_dp_proc_group(), **kwargs)
+        super().__init__(model, config, shard_group=None, replica_group=mesh.get_replica_proc_group(), **kwargs)
 
 
 class SpmdFullyShardedDataParallel(FullyShardedDataParallel):

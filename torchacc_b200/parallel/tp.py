@@ -221,12 +221,13 @@ class _VocabParallelCE(torch.autograd.Function):
     token chunks; per chunk two all-reduces move [chunk] fp32 statistics (max, then sum-exp and label logit)."""
 
     @staticmethod
-    def forward(ctx, hidden, w_local, labels, tp: TPContext, ignore_index, chunk):
+    def forward(ctx, hidden, w_local, labels, tp: TPContext, ignore_index, chunk, n_valid_total=None):
         T, V_local = hidden.shape[0], w_local.shape[0]
         v0 = tp.rank * V_local
         lab = labels.reshape(-1)
         valid = lab != ignore_index
-        n_valid = valid.sum().clamp(min=1).float()
+        n_valid = valid.sum().clamp(min=1).float() if n_valid_total is None else \
+            torch.as_tensor(n_valid_total, dtype=torch.float32, device=hidden.device).reshape(())
         dh = torch.zeros_like(hidden)
         want_w = ctx.needs_input_grad[1]
         view = getattr(w_local, "_tb_grad_view", None)
@@ -271,12 +272,13 @@ class _VocabParallelCE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss):
         dh, dw = ctx.saved_tensors
-        return dh * dloss.to(dh.dtype), (dw * dloss.to(dw.dtype) if ctx.own_dw else None), None, None, None, None
+        return (dh * dloss.to(dh.dtype), (dw * dloss.to(dw.dtype) if ctx.own_dw else None), None, None, None, None,
+                None)
 
 
 def vocab_parallel_cross_entropy(hidden, w_local, labels, tp: TPContext, ignore_index: int = -100,
-                                 chunk_tokens: int = 2048):
-    return _VocabParallelCE.apply(hidden, w_local, labels, tp, ignore_index, chunk_tokens)
+                                 chunk_tokens: int = 2048, n_valid_total=None):
+    return _VocabParallelCE.apply(hidden, w_local, labels, tp, ignore_index, chunk_tokens, n_valid_total)
 
 
 # ------------------------------------------------------------------------------------------------------------
