@@ -38,6 +38,7 @@ def parse():
     p.add_argument("--no-gc", action="store_true")
     p.add_argument("--attn", default=None, help="attention backend override (native|sdpa)")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--trace", default=None, help="write a kernel timeline (chrome trace) of one extra, untimed step")
     return p.parse_args()
 
 
@@ -205,6 +206,18 @@ def run_ours(a):
         e2e = {"value": tokens / (float(ems) / 1e3), "unit": "tokens/s",
                "h2d_bytes_per_step": int(2 * a.mbs * a.seq_len * 8), "d2h_bytes_per_step": 4,
                "last_loss": loss_val}
+
+    if a.trace:
+        # one extra step under the CUPTI-based torch profiler, AFTER every timed region (never part of a number);
+        # tools/trace_summary.py turns the trace into stream-utilisation / overlap tables for profiles/
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize(device)
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize(device)
+        if rank == 0:
+            os.makedirs(os.path.dirname(os.path.abspath(a.trace)), exist_ok=True)
+            prof.export_chrome_trace(a.trace)
 
     if rank == 0:
         res = {

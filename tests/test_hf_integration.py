@@ -1,0 +1,147 @@
+"""HuggingFace integration: kernel patches (reference torchacc/ops/liger.py, utils/patch.py) keep HF Llama / Qwen2
+numerics, load_hf_state_dict maps an HF checkpoint onto the native model, accelerate() accepts an HF model."""
+import copy
+
+import pytest
+import torch
+
+transformers = pytest.importorskip("transformers")
+
+
+def _hf_llama(attn="eager"):
+    from transformers import LlamaConfig, LlamaForCausalLM
+    cfg = LlamaConfig(vocab_size=160, hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                      num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=64,
+                      attn_implementation=attn)
+    torch.manual_seed(0)
+    return LlamaForCausalLM(cfg)
+
+
+def _hf_qwen2():
+    from transformers import Qwen2Config, Qwen2ForCausalLM
+    cfg = Qwen2Config(vocab_size=160, hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                      num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=64,
+                      attn_implementation="eager")
+    torch.manual_seed(0)
+    return Qwen2ForCausalLM(cfg)
+
+
+@pytest.fixture
+def restore_hf_classes():
+    from transformers.models.llama import modeling_llama as ml
+    from transformers.models.qwen2 import modeling_qwen2 as mq
+    saved = [(c, c.forward) for c in (ml.LlamaRMSNorm, ml.LlamaMLP, ml.LlamaForCausalLM, mq.Qwen2RMSNorm, mq.Qwen2MLP,
+                                      mq.Qwen2ForCausalLM)]
+    yield
+    for c, f in saved:
+        c.forward = f
+        if hasattr(c, "_tb_lce_patched"):
+            del c._tb_lce_patched
+    from torchacc_b200.utils.patch import unpatch_all
+    unpatch_all()
+
+
+@pytest.mark.parametrize("family", ["llama", "qwen2"])
+def test_liger_style_patches_preserve_loss_and_grads(family, restore_hf_classes):
+    import torchacc_b200 as ta
+    model = _hf_llama() if family == "llama" else _hf_qwen2()
+    ids = torch.randint(0, 160, (2, 24), generator=torch.Generator().manual_seed(3))
+    ref = model(input_ids=ids, labels=ids)
+    ref.loss.backward()
+    ref_grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+    model.zero_grad()
+    (ta.ops.apply_liger_kernel_to_llama if family == "llama" else ta.ops.apply_liger_kernel_to_qwen2)()
+    out = model(input_ids=ids, labels=ids)
+    assert out.logits is None                     # fused linear + cross-entropy: no [T, V] logits
+    assert abs(float(out.loss) - float(ref.loss)) < 1e-4
+    out.loss.backward()
+    for n, p in model.named_parameters():
+        assert torch.allclose(p.grad, ref_grads[n], atol=2e-5, rtol=1e-3), n
+    # without labels the original forward (with logits) is used
+    assert model(input_ids=ids).logits.shape == (2, 24, 160)
+
+
+def test_patch_fa_registers_attention_interface(restore_hf_classes):
+    """The 'flash_attention_2' entry of HF's attention registry is served by our attention op."""
+    from torchacc_b200.utils.patch import patch_fa
+    assert patch_fa()
+    from transformers.modeling_utils import ALL_ATTENTION_FUNCTIONS
+    fn = ALL_ATTENTION_FUNCTIONS["torchacc_b200"]
+    g = torch.Generator().manual_seed(0)
+    q = torch.randn(2, 4, 16, 16, generator=g)        # HF layout [B, H, S, D]
+    k = torch.randn(2, 2, 16, 16, generator=g)
+    v = torch.randn(2, 2, 16, 16, generator=g)
+
+    class M:
+        is_causal = True
+    out, _ = fn(M(), q, k, v, None, scaling=16 ** -0.5)
+    kk, vv = k.repeat_interleave(2, 1), v.repeat_interleave(2, 1)
+    ref = torch.nn.functional.scaled_dot_product_attention(q, kk, vv, is_causal=True).transpose(1, 2)
+    assert torch.allclose(out, ref, atol=1e-5)
+
+
+def test_native_model_loads_hf_checkpoint():
+    from torchacc_b200.models import build_llama
+    hf = _hf_llama()
+    native = build_llama("tiny", hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                         num_key_value_heads=2, head_dim=16, vocab_size=160, max_position_embeddings=64,
+                         rope_theta=hf.config.rope_parameters["rope_theta"] if hasattr(hf.config, "rope_parameters")
+                         else hf.config.rope_theta, rms_norm_eps=hf.config.rms_norm_eps)
+    native.load_hf_state_dict(hf.state_dict())
+    ids = torch.randint(0, 160, (2, 24), generator=torch.Generator().manual_seed(3))
+    a = hf(input_ids=ids, labels=ids)
+    b = native(ids, labels=ids, return_logits=True)
+    assert abs(float(a.loss) - float(b["loss"])) < 1e-4
+    assert torch.allclose(a.logits, b["logits"], atol=1e-4)
+    # and back
+    sd = native.to_hf_state_dict()
+    for k, v in hf.state_dict().items():
+        assert torch.equal(sd[k], v), k
+
+
+def test_accelerate_hf_model_single_process(restore_hf_classes):
+    import torchacc_b200 as ta
+    model = _hf_llama()
+    ref = copy.deepcopy(model)
+    cfg = ta.Config()
+    cfg.memory.gc = True
+    cfg.memory.gc_cls = {"LlamaDecoderLayer"}
+    m = ta.accelerate(model, config=cfg)
+    ids = torch.randint(0, 160, (2, 24), generator=torch.Generator().manual_seed(3))
+    out = m(input_ids=ids, labels=ids)
+    loss = out.loss if hasattr(out, "loss") else out["loss"]
+    r = ref(input_ids=ids, labels=ids)
+    assert abs(float(loss) - float(r.loss)) < 1e-4
+    loss.backward()
+
+
+def _hf_fsdp_worker(rank, world):
+    import torchacc_b200 as ta
+    model = _hf_llama()
+    ref = copy.deepcopy(model)
+    cfg = ta.Config()
+    cfg.dist.fsdp.size = world
+    cfg.dist.fsdp.wrap_layer_cls = {"LlamaDecoderLayer"}
+    cfg.memory.gc = True
+    m = ta.accelerate(model, config=cfg)
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)
+    ref_opt = torch.optim.SGD(ref.parameters(), lr=0.1)
+    ids = torch.randint(0, 160, (4, 24), generator=torch.Generator().manual_seed(3))
+    local = ids.chunk(world)[rank]
+    for _ in range(2):
+        out = m(input_ids=local, labels=local)
+        (out.loss if hasattr(out, "loss") else out["loss"]).backward()
+        opt.step()
+        m.zero_grad()
+        ref(input_ids=ids, labels=ids).loss.backward()
+        ref_opt.step()
+        ref_opt.zero_grad()
+    full = m._inner_engine_module().full_state_dict(rank0_only=False)
+    for n, p in ref.named_parameters():
+        assert torch.allclose(full[n], p.detach(), atol=1e-4, rtol=1e-3), (n, float((full[n] - p).abs().max()))
+
+
+def test_accelerate_hf_model_fsdp_two_ranks():
+    """An unmodified HuggingFace model through accelerate(): class patches + FSDP engine + GC == single process."""
+    from dist_utils import run_distributed
+    run_distributed(_hf_fsdp_worker, 2)

@@ -77,8 +77,9 @@ def accelerate(model: nn.Module, dataloader=None, config: Optional[Config] = Non
             from .utils.checkpoint import gradient_checkpoint
             model = gradient_checkpoint(model, config.memory.gc_cls, config.memory.gc_cnt)
         model = model.to(device)
-    try:
-        model.device = device
-    except Exception:
-        object.__setattr__(model, "device", device)
+    if not isinstance(getattr(type(model), "device", None), property):   # HF models expose a read-only property
+        try:
+            model.device = device
+        except Exception:
+            object.__setattr__(model, "device", device)
     return (model, loader) if dataloader is not None else model

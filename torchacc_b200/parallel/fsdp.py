@@ -695,7 +695,8 @@ def shard_model(model: nn.Module, engine: ShardingEngine, wrap_classes: Sequence
     root = ShardedUnit(engine, model, root_unit, False)
     # non-wrapped gc classes (gc without fsdp wrapping of the same class)
     if gc_classes:
-        from ..utils.checkpoint import gradient_checkpoint
+        from ..utils.checkpoint import disable_kv_cache, gradient_checkpoint
         gradient_checkpoint(model, gc_classes, gc_left[0] if gc_left[0] != math.inf else None,
                             skip_types=(ShardedUnit,))
+        disable_kv_cache(model)
     return root

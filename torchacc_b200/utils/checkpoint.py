@@ -57,6 +57,7 @@ def gradient_checkpoint(model: nn.Module, gc_cls: Iterable[Union[str, type]], gc
     if not classes:
         return model
     left = [gc_cnt if gc_cnt is not None else float("inf")]
+    wrapped = []
 
     def recurse(parent):
         for name, child in list(parent.named_children()):
@@ -65,11 +66,26 @@ def gradient_checkpoint(model: nn.Module, gc_cls: Iterable[Union[str, type]], gc
             if isinstance(child, classes) and left[0] > 0:
                 parent._modules[name] = CheckpointedModule(child)
                 left[0] -= 1
+                wrapped.append(name)
             else:
                 recurse(child)
 
     recurse(model)
+    if wrapped:
+        disable_kv_cache(model)
     return model
+
+
+def disable_kv_cache(model: nn.Module) -> None:
+    """HF models: a KV cache filled in the forward would be appended to again by the recomputation, so training
+    with activation checkpointing turns ``config.use_cache`` off (what HF's own gradient_checkpointing does)."""
+    for m in model.modules():
+        cfg = getattr(m, "config", None)
+        if cfg is not None and getattr(cfg, "use_cache", False):
+            try:
+                cfg.use_cache = False
+            except Exception:
+                pass
 
 
 def fx_checkpoint(graph_module, gc_cls):
