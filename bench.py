@@ -281,7 +281,10 @@ def run_reference(a):
         model = model.to_empty(device="cpu" if world > 1 else device)
         with torch.no_grad():
             for p in model.parameters():
-                p.normal_(0, 0.02)
+                if p.dim() == 1:
+                    p.fill_(1.0)            # RMSNorm weights (same initialisation as our arm)
+                else:
+                    p.normal_(0, 0.02)
         # transformers 5.x builds `SiLUActivation` objects; the reference's liger MLP patch only accepts `nn.SiLU`
         # (torchacc/ops/liger.py:21-24).  Swapping the activation OBJECT on the user's model keeps the reference's
         # kernel patches active (the alternative, config.compute.disable_kernel_patches, would slow the reference).

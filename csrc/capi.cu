@@ -45,9 +45,9 @@ TB_API int tb_rmsnorm_fwd(uint64_t x, uint64_t res, uint64_t w, uint64_t y, uint
                               H, eps, num_sms, S(stream));
 }
 TB_API int tb_rmsnorm_bwd(uint64_t dy, uint64_t x, uint64_t w, uint64_t rstd, uint64_t dres, uint64_t dx, uint64_t dw,
-                          int rows, int H, int num_sms, uint64_t stream) {
+                          int dw_rows, int rows, int H, int num_sms, uint64_t stream) {
   return (int)tb::rmsnorm_bwd(P<void>(dy), P<void>(x), P<void>(w), P<float>(rstd), P<void>(dres), P<void>(dx),
-                              P<float>(dw), rows, H, num_sms, S(stream));
+                              P<float>(dw), dw_rows, rows, H, num_sms, S(stream));
 }
 TB_API int tb_rope_inplace(uint64_t x, uint64_t cos_t, uint64_t sin_t, uint64_t positions, long long T, int nheads,
                            int D, long long token_stride, int seq_len, int backward, int num_sms, uint64_t stream) {
@@ -169,7 +169,7 @@ TB_API int tb_gemm_rs_bf16(uint64_t A, uint64_t B, const uint64_t* peer_stage, c
                                a_mn_major != 0, b_mn_major != 0, rank, world, channel, epoch, num_sms, S(stream));
 }
 TB_API int tb_rs_reduce_bf16(uint64_t stage, uint64_t counters, uint32_t expected, uint64_t residual, uint64_t out,
-                             long long n, int world, long long slot_stride, int num_sms, uint64_t stream) {
-  return (int)tb::rs_reduce_bf16(P<void>(stage), P<uint32_t>(counters), expected, P<void>(residual), P<void>(out), n,
-                                 world, slot_stride, num_sms, S(stream));
+                             int rows, int N, int world, long long slot_stride, int num_sms, uint64_t stream) {
+  return (int)tb::rs_reduce_bf16(P<void>(stage), P<uint32_t>(counters), expected, P<void>(residual), P<void>(out), rows,
+                                 N, world, slot_stride, num_sms, S(stream));
 }

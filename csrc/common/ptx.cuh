@@ -182,6 +182,17 @@ TB_DEVICE void tma_reduce_add_2d(const void* desc, uint32_t smem_src, int32_t c0
                "r"(smem_src), "r"(c0), "r"(c1)
                : "memory");
 }
+// non-tensor bulk copies (contiguous bytes; 16-byte aligned, size % 16 == 0).  Source / destination may be any
+// global address, including a peer GPU's memory mapped over NVLink.
+TB_DEVICE void bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar)
+               : "memory");
+}
+TB_DEVICE void bulk_store(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes)
+               : "memory");
+}
 TB_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 TB_DEVICE void tma_store_wait_read() {

@@ -32,6 +32,6 @@ cudaError_t gemm_rs_bf16(const void* A, const void* B, const uint64_t* peer_stag
                          int num_sms, cudaStream_t stream);
 // part 2: out = sum over sources of stage[src] (+ residual) once counters[src] >= expected for every source.
 cudaError_t rs_reduce_bf16(const void* stage, const uint32_t* counters, uint32_t expected, const void* residual,
-                           void* out, long long n, int world, long long slot_stride, int num_sms, cudaStream_t stream);
+                           void* out, int rows, int N, int world, long long slot_stride, int num_sms, cudaStream_t stream);
 
 }  // namespace tb

@@ -112,28 +112,58 @@ TB_DEVICE void fused_barrier(const FuseArgs& f, bool signal, int slot_base, int 
   }
 }
 
-// Copy-engine role of the all-gather -> GEMM kernel (executed by whole clusters).
-TB_DEVICE void gather_role(const FuseArgs& f, int K, int comm_cta, int num_comm_ctas) {
+// Copy-engine role of the all-gather -> GEMM kernel (executed by whole clusters).  One thread per CTA drives a ring
+// of 32 KB TMA bulk copies  peer HBM --NVLink--> smem --> local gathered buffer:  (stages-1) x 32 KB are in flight per
+// CTA, so a handful of CTAs keep the link full (16-byte register loads would need ~100 CTAs for the same bytes in
+// flight).  Shard r is announced to the MMA clusters' TMA producers through flags[r] when all copy CTAs finished it.
+TB_DEVICE void gather_role(const FuseArgs& f, int K, int comm_cta, int num_comm_ctas, uint32_t smem_base,
+                           uint32_t bar_base, int num_stages) {
+  constexpr uint32_t kChunk = 32768;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < num_stages; ++s) mbar_init(bar_base + 8u * s, 1);
+    fence_mbar_init();
+  }
   fused_barrier(f, comm_cta == 0, 0, threadIdx.x);   // every rank has written its own row block
   __syncthreads();
-  const size_t shard_vecs = (size_t)f.rows_per_rank * K * 2 / 16;
-  const size_t stride = (size_t)num_comm_ctas * blockDim.x;
-  for (int step = 1; step < f.world; ++step) {
-    const int r = (f.rank + step) % f.world;
-    const uint4* src = reinterpret_cast<const uint4*>(f.peer[r]) + (size_t)r * shard_vecs;
-    uint4* dst = reinterpret_cast<uint4*>(f.a_full) + (size_t)r * shard_vecs;
-    size_t i = (size_t)comm_cta * blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < shard_vecs; i += 4 * stride) {
-      uint4 a = ld_volatile_v4(src + i), b = ld_volatile_v4(src + i + stride), c = ld_volatile_v4(src + i + 2 * stride),
-            d = ld_volatile_v4(src + i + 3 * stride);
-      dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+  if (threadIdx.x == 0 && f.world > 1) {
+    const size_t shard_bytes = (size_t)f.rows_per_rank * K * 2;
+    const int chunks = (int)(shard_bytes / kChunk);            // rows % 256 == 0 and K % 64 == 0 -> exact
+    const int per = chunks > comm_cta ? (chunks - comm_cta + num_comm_ctas - 1) / num_comm_ctas : 0;
+    const int total = per * (f.world - 1);
+    auto locate = [&](int j, const uint8_t*& src, uint8_t*& dst) {
+      const int r = (f.rank + 1 + j / per) % f.world;
+      const size_t off = (size_t)r * shard_bytes + (size_t)(comm_cta + (j % per) * num_comm_ctas) * kChunk;
+      src = reinterpret_cast<const uint8_t*>(f.peer[r]) + off;
+      dst = reinterpret_cast<uint8_t*>(f.a_full) + off;
+    };
+    auto issue = [&](int j) {
+      const uint8_t* src; uint8_t* dst;
+      locate(j, src, dst);
+      const int s = j % num_stages;
+      mbar_arrive_expect_tx(bar_base + 8u * s, kChunk);
+      bulk_load(smem_base + s * kChunk, src, kChunk, bar_base + 8u * s);
+    };
+    int issued = 0;
+    for (; issued < num_stages - 1 && issued < total; ++issued) issue(issued);
+    for (int i = 0; i < total; ++i) {
+      const int s = i % num_stages;
+      mbar_wait(bar_base + 8u * s, (i / num_stages) & 1);
+      const uint8_t* src; uint8_t* dst;
+      locate(i, src, dst);
+      bulk_store(dst, smem_base + s * kChunk, kChunk);
+      tma_store_commit();
+      if (issued < total) {
+        tma_store_wait_read<1>();       // every store but the newest has left smem -> stage (i-1) % stages is free
+        issue(issued++);
+      }
+      if ((i + 1) % per == 0) {         // last chunk of a source rank handled by this CTA
+        tma_store_wait<0>();            // writes complete
+        __threadfence();
+        atomicAdd(f.flags + (f.rank + 1 + i / per) % f.world, 1u);
+      }
     }
-    for (; i < shard_vecs; i += stride) dst[i] = ld_volatile_v4(src + i);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      atomicAdd(f.flags + r, 1u);   // shard r is complete once all comm CTAs have added
-    }
+    if (per == 0)                       // more copy CTAs than chunks: still count towards every shard's flag
+      for (int st = 1; st < f.world; ++st) atomicAdd(f.flags + (f.rank + st) % f.world, 1u);
   }
   // exit: all my copy CTAs are done reading peers -> tell them; stay until every peer is done reading me
   __shared__ uint32_t s_last;
@@ -215,7 +245,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if constexpr (kFuse == 1) {
     const int cc = args.fuse.comm_clusters;
     if (cluster_id < cc) {   // copy-engine clusters: no TMEM, no MMA
-      gather_role(args.fuse, args.K, (int)blockIdx.x, cc * kCluster);
+      gather_role(args.fuse, args.K, (int)blockIdx.x, cc * kCluster, smem_base, bar_base,
+                  kStages * S::kStageBytes / 32768);
       return;
     }
     cluster_id -= cc;
@@ -339,6 +370,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       fused_barrier(args.fuse, blockIdx.x == 0 && warp_idx == 4, 0, (int)lane);
       __syncwarp();
     }
+    // kFuse == 2: arrivals are batched per destination rank -- ONE system-scope fence + counter add per warp and
+    // shard instead of one per tile (a fence.sys costs an NVLink round trip, longer than a whole K=2048 mainloop).
+    int cur_shard = -1;
+    uint32_t pending = 0;
+    auto flush_arrivals = [&]() {
+      if constexpr (kFuse == 2) {
+        if (pending != 0) {
+          __threadfence_system();
+          __syncwarp();
+          if (lane == 0) red_release_sys_add(args.fuse.peer_cnt[cur_shard] + args.fuse.rank, pending);
+          pending = 0;
+        }
+      }
+    };
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++lt) {
       int tm, tn, shard;
       coords(t, tm, tn, shard);
@@ -350,19 +395,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int n0 = tn * kBlockN;
       const bool row_ok = grow < args.M;
       if constexpr (kFuse == 2) {
-        // bf16 partial tile -> staging slot [my rank] of the rank that owns this row block (peer store over NVLink)
-        __nv_bfloat16* dbase = reinterpret_cast<__nv_bfloat16*>(args.fuse.peer[shard]) +
-                               (long long)args.fuse.rank * args.fuse.slot_stride +
-                               (grow - (long long)shard * args.fuse.rows_per_rank) * args.ldd;
+        // bf16 partial tile -> staging slot [my rank] of the rank that owns this row block (peer stores over NVLink).
+        // The staging layout is block-major: one 2 KB block per (tile, CTA half, lane quarter, 32-column chunk),
+        // inside a block [j][lane][8 columns], so every warp-wide store instruction writes 512 contiguous bytes
+        // (full NVLink packets) instead of 32 scattered 16-byte pieces.  rs_reduce_kernel undoes the permutation.
+        if (shard != cur_shard) {
+          flush_arrivals();
+          cur_shard = shard;
+        }
+        const int tm_local = tm - shard * tiles_m_per_shard;
+        const long long blk0 = ((((long long)tm_local * args.num_n_tiles + tn) * 2 + cta_rank) * 4 + q) * 8;
+        uint4* dbase = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(args.fuse.peer[shard]) +
+                                                (long long)args.fuse.rank * args.fuse.slot_stride) + blk0 * 128 + lane;
 #pragma unroll 1
         for (int c = 0; c < kBlockN / 32; ++c) {
           __syncwarp();
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + ((q * 32u) << 16) + as * kBlockN + c * 32, r);
           tmem_ld_wait();
-          const int gcol = n0 + c * 32;
-          if (!row_ok || gcol + 32 > args.N) continue;
-          uint4* d4 = reinterpret_cast<uint4*>(dbase + gcol);
+          if (n0 + c * 32 + 32 > args.N) continue;     // (rows are always in range: rows_per_rank % 256 == 0)
+          uint4* d4 = dbase + c * 128;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 o;
@@ -370,14 +422,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             o.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
             o.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
             o.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
-            d4[j] = o;
+            d4[j * 32] = o;
           }
         }
+        ++pending;
         tc_fence_before();
-        __threadfence_system();
         __syncwarp();
         if (lane == 0) {
-          red_release_sys_add(args.fuse.peer_cnt[shard] + args.fuse.rank, 1u);   // one arrival per epilogue warp
           if constexpr (kCluster == 2) mbar_arrive_cluster(tempty_leader + 8u * as);
           else mbar_arrive(tempty_leader + 8u * as);
         }
@@ -461,6 +512,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         else mbar_arrive(tempty_leader + 8u * as);
       }
     }
+    flush_arrivals();
   }
 
   // ================================ Teardown ================================
@@ -623,7 +675,7 @@ cudaError_t gemm_rs_bf16(const void* A, const void* B, const uint64_t* peer_stag
     f.pads[i] = reinterpret_cast<uint32_t*>(pad_ptrs[i]);
   }
   f.rank = rank; f.world = world; f.rows_per_rank = rows_per_rank; f.channel = channel; f.epoch = epoch;
-  f.slot_stride = (long long)rows_per_rank * N;
+  f.slot_stride = (long long)rows_per_rank * ((N + kBlockN - 1) / kBlockN * kBlockN);   // block-major, padded N
 #define TB_RS(AM, BM) return launch_one<2, AM, BM, 2>(ta, tbm, args, num_sms, stream)
   if (!a_mn_major && !b_mn_major) TB_RS(Major::K, Major::K);
   if (!a_mn_major && b_mn_major) TB_RS(Major::K, Major::MN);
@@ -632,45 +684,77 @@ cudaError_t gemm_rs_bf16(const void* A, const void* B, const uint64_t* peer_stag
 #undef TB_RS
 }
 
-// out[rows, N] = sum_src stage[src][rows, N] (+ residual), once every source has delivered `expected` arrivals.
+// out[rows, N] = sum_src stage[src] (+ residual), once every source has delivered `expected` arrivals.
+// Staging slots are block-major (see the kFuse == 2 epilogue): one warp handles one 2 KB block = 32 rows x 32 columns;
+// its four loads per source are 512-byte coalesced, each lane then owns 64 contiguous output bytes of one row.
 __global__ void __launch_bounds__(256)
 rs_reduce_kernel(const __nv_bfloat16* __restrict__ stage, const uint32_t* __restrict__ counters, uint32_t expected,
-                 const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out, long long n, int world,
+                 const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out, int rows, int N, int world,
                  long long slot_stride) {
   if (threadIdx.x < world) {
     while ((int32_t)(ld_acquire_sys_u32(counters + threadIdx.x) - expected) < 0) {
     }
   }
   __syncthreads();
-  const long long nvec = n >> 3;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int num_n_tiles = (N + 255) / 256;
+  const long long num_blocks = (long long)(rows / 256) * num_n_tiles * 64;
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long w = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); w < num_blocks; w += warps) {
+    const int c = (int)(w & 7), q = (int)((w >> 3) & 3), cta = (int)((w >> 5) & 1);
+    const long long tile = w >> 6;
+    const int tn = (int)(tile % num_n_tiles);
+    const long long tm = tile / num_n_tiles;
+    const int col = tn * 256 + c * 32;
+    if (col + 32 > N) continue;
+    const long long row = tm * 256 + cta * 128 + q * 32 + lane;
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
     for (int s = 0; s < world; ++s) {
-      const uint4 u = ld_volatile_v4(reinterpret_cast<const uint4*>(stage + s * slot_stride) + i);
-      float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+      const uint4* src = reinterpret_cast<const uint4*>(stage + s * slot_stride) + w * 128 + lane;
+      uint4 u[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) u[j] = ld_volatile_v4(src + j * 32);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 a = unpack_bf16x2(u[j].x), b = unpack_bf16x2(u[j].y), cc = unpack_bf16x2(u[j].z), d = unpack_bf16x2(u[j].w);
+        acc[8 * j + 0] += a.x; acc[8 * j + 1] += a.y; acc[8 * j + 2] += b.x; acc[8 * j + 3] += b.y;
+        acc[8 * j + 4] += cc.x; acc[8 * j + 5] += cc.y; acc[8 * j + 6] += d.x; acc[8 * j + 7] += d.y;
+      }
     }
+    const long long o_off = row * N + col;
     if (residual) {
-      const uint4 u = reinterpret_cast<const uint4*>(residual)[i];
-      float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+      const uint4* rp = reinterpret_cast<const uint4*>(residual + o_off);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 u = rp[j];
+        float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        acc[8 * j + 0] += a.x; acc[8 * j + 1] += a.y; acc[8 * j + 2] += b.x; acc[8 * j + 3] += b.y;
+        acc[8 * j + 4] += cc.x; acc[8 * j + 5] += cc.y; acc[8 * j + 6] += d.x; acc[8 * j + 7] += d.y;
+      }
     }
-    uint4 o;
-    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
-    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
-    reinterpret_cast<uint4*>(out)[i] = o;
+    uint4* op = reinterpret_cast<uint4*>(out + o_off);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 o;
+      o.x = pack_bf16x2(acc[8 * j + 0], acc[8 * j + 1]); o.y = pack_bf16x2(acc[8 * j + 2], acc[8 * j + 3]);
+      o.z = pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5]); o.w = pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]);
+      op[j] = o;
+    }
   }
 }
 
 cudaError_t rs_reduce_bf16(const void* stage, const uint32_t* counters, uint32_t expected, const void* residual,
-                           void* out, long long n, int world, long long slot_stride, int num_sms, cudaStream_t stream) {
-  if (n % 8 != 0) return cudaErrorInvalidValue;
-  long long blocks = ((n >> 3) + 255) / 256;
-  if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
+                           void* out, int rows, int N, int world, long long slot_stride, int num_sms,
+                           cudaStream_t stream) {
+  if (N % 32 != 0 || rows % 256 != 0) return cudaErrorInvalidValue;
+  long long blocks = (long long)(rows / 256) * ((N + 255) / 256) * 64 / 8;   // 8 warps per CTA
+  if (blocks > (long long)num_sms * 4) blocks = (long long)num_sms * 4;
   if (blocks < 1) blocks = 1;
   rs_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)stage, counters, expected,
-                                                          (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, n, world,
-                                                          slot_stride);
+                                                          (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, rows, N,
+                                                          world, slot_stride);
   return cudaGetLastError();
 }
 

@@ -93,37 +93,58 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
   }
 }
 
-// RMSNorm backward.  dx = rstd * (dy*w - xhat * mean(dy*w*xhat)) [+ dres];  dw += sum_rows dy * xhat (fp32 atomics,
-// one atomic per column per CTA).
-template <int kVpt>
-__global__ void __launch_bounds__(kNormThreads)
+// RMSNorm backward.  dx = rstd * (dy*w - xhat * mean(dy*w*xhat)) [+ dres];  dw partial sums per CTA are written to
+// row blockIdx.x of dw_partial[gridDim.x, H] (fp32, no atomics; the caller sums the rows).
+// The next row's x / dy / dres are prefetched as raw 16-byte vectors before the current row's block reduction, so two
+// rows of loads are in flight per CTA and the reduction latency is hidden.
+template <int kVpt, int kThreads>
+__global__ void __launch_bounds__(kThreads, (kVpt == 1) ? (1024 / kThreads) : 1)
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                    const __nv_bfloat16* __restrict__ w, const float* __restrict__ rstd,
-                   const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ dw,
-                   int rows, int H) {
+                   const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx,
+                   float* __restrict__ dw_partial, int rows, int H) {
   __shared__ float red[32];
   const int nvec = H >> 3;
   float wv[kVpt][8], dwv[kVpt][8];
 #pragma unroll
   for (int i = 0; i < kVpt; ++i) {
-    const int v = threadIdx.x + i * kNormThreads;
+    const int v = threadIdx.x + i * kThreads;
     if (v < nvec) unpack8(__ldg(reinterpret_cast<const uint4*>(w) + v), wv[i]);
 #pragma unroll
     for (int j = 0; j < 8; ++j) dwv[i][j] = 0.f;
   }
+  uint4 xn[kVpt], gn[kVpt], rn[kVpt];
+  float rs_n = 0.f;
+  auto prefetch = [&](int row) {
+    if (row < rows) {
+      rs_n = rstd[row];
+#pragma unroll
+      for (int i = 0; i < kVpt; ++i) {
+        const int v = threadIdx.x + i * kThreads;
+        if (v < nvec) {
+          xn[i] = reinterpret_cast<const uint4*>(x + (size_t)row * H)[v];
+          gn[i] = reinterpret_cast<const uint4*>(dy + (size_t)row * H)[v];
+          if (dres) rn[i] = reinterpret_cast<const uint4*>(dres + (size_t)row * H)[v];
+        }
+      }
+    }
+  };
+  prefetch(blockIdx.x);
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * H);
-    const uint4* gr = reinterpret_cast<const uint4*>(dy + (size_t)row * H);
-    const float rs = rstd[row];
+    uint4 xc[kVpt], gc[kVpt], rc[kVpt];
+    const float rs = rs_n;
+#pragma unroll
+    for (int i = 0; i < kVpt; ++i) { xc[i] = xn[i]; gc[i] = gn[i]; rc[i] = rn[i]; }
+    prefetch(row + gridDim.x);
     float xh[kVpt][8], gw[kVpt][8];
     float dot = 0.f;
 #pragma unroll
     for (int i = 0; i < kVpt; ++i) {
-      const int v = threadIdx.x + i * kNormThreads;
+      const int v = threadIdx.x + i * kThreads;
       if (v < nvec) {
         float g[8];
-        unpack8(xr[v], xh[i]);
-        unpack8(gr[v], g);
+        unpack8(xc[i], xh[i]);
+        unpack8(gc[i], g);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xh[i][j] *= rs;
@@ -133,31 +154,32 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
         }
       }
     }
-    dot = block_reduce_sum<kNormThreads>(dot, red) / (float)H;
+    dot = block_reduce_sum<kThreads>(dot, red) / (float)H;
 #pragma unroll
     for (int i = 0; i < kVpt; ++i) {
-      const int v = threadIdx.x + i * kNormThreads;
+      const int v = threadIdx.x + i * kThreads;
       if (v < nvec) {
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = rs * (gw[i][j] - xh[i][j] * dot);
         if (dres) {
           float r[8];
-          unpack8(reinterpret_cast<const uint4*>(dres + (size_t)row * H)[v], r);
+          unpack8(rc[i], r);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] += r[j];
         }
-        reinterpret_cast<uint4*>(dx + (size_t)row * H)[v] = pack8(o);
+        __stcs(reinterpret_cast<uint4*>(dx + (size_t)row * H) + v, pack8(o));
       }
     }
   }
-  if (dw) {
+  if (dw_partial) {
+    float* dst = dw_partial + (size_t)blockIdx.x * H;
 #pragma unroll
     for (int i = 0; i < kVpt; ++i) {
-      const int v = threadIdx.x + i * kNormThreads;
+      const int v = threadIdx.x + i * kThreads;
       if (v < nvec) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(dw + v * 8 + j, dwv[i][j]);
+        reinterpret_cast<float4*>(dst + v * 8)[0] = make_float4(dwv[i][0], dwv[i][1], dwv[i][2], dwv[i][3]);
+        reinterpret_cast<float4*>(dst + v * 8)[1] = make_float4(dwv[i][4], dwv[i][5], dwv[i][6], dwv[i][7]);
       }
     }
   }
@@ -179,17 +201,27 @@ cudaError_t rmsnorm_fwd(const void* x, const void* res, const void* w, void* y, 
 }
 
 cudaError_t rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx,
-                        float* dw, int rows, int H, int num_sms, cudaStream_t stream) {
+                        float* dw, int dw_rows, int rows, int H, int num_sms, cudaStream_t stream) {
   if (rows == 0) return cudaSuccess;
   if (H % 8 != 0 || H > kNormThreads * 8 * kMaxVec) return cudaErrorInvalidValue;
-  int grid = rows < num_sms * 4 ? rows : num_sms * 4;
-  const int vpt = (H / 8 + kNormThreads - 1) / kNormThreads;
-#define TB_LAUNCH(V)                                                                                            \
-  rmsnorm_bwd_kernel<V><<<grid, kNormThreads, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,   \
-                                                           (const __nv_bfloat16*)w, rstd,                       \
-                                                           (const __nv_bfloat16*)dres, (__nv_bfloat16*)dx, dw,  \
-                                                           rows, H)
-  if (vpt <= 1) TB_LAUNCH(1); else if (vpt <= 2) TB_LAUNCH(2); else if (vpt <= 4) TB_LAUNCH(4); else TB_LAUNCH(8);
+  // dw is a [dw_rows, H] fp32 partial-sum buffer: exactly dw_rows CTAs run and each writes its own row
+  int grid = dw_rows;
+  if (grid < 1 || grid > rows || dw == nullptr) return cudaErrorInvalidValue;
+  (void)num_sms;
+  const int nvec = H / 8;
+  // wide rows use 512-thread CTAs so a thread keeps at most a few 16-byte vectors (x, dy, dres; current + prefetched)
+  const bool wide = nvec >= 512;
+  const int threads = wide ? 512 : 256;
+  const int vpt = (nvec + threads - 1) / threads;
+#define TB_LAUNCH(V, T)                                                                                         \
+  rmsnorm_bwd_kernel<V, T><<<grid, T, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,            \
+                                                    (const __nv_bfloat16*)w, rstd, (const __nv_bfloat16*)dres,   \
+                                                    (__nv_bfloat16*)dx, dw, rows, H)
+  if (wide) {
+    if (vpt <= 1) TB_LAUNCH(1, 512); else if (vpt <= 2) TB_LAUNCH(2, 512); else TB_LAUNCH(4, 512);
+  } else {
+    if (vpt <= 1) TB_LAUNCH(1, 256); else TB_LAUNCH(2, 256);
+  }
 #undef TB_LAUNCH
   return cudaGetLastError();
 }

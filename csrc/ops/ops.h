@@ -7,7 +7,7 @@ namespace tb {
 cudaError_t rmsnorm_fwd(const void* x, const void* res, const void* w, void* y, void* h_out, float* rstd, int rows,
                         int H, float eps, int num_sms, cudaStream_t stream);
 cudaError_t rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx,
-                        float* dw, int rows, int H, int num_sms, cudaStream_t stream);
+                        float* dw_partial, int dw_rows, int rows, int H, int num_sms, cudaStream_t stream);
 cudaError_t rope_inplace(void* x, const float* cos_t, const float* sin_t, const int* positions, long long T,
                          int nheads, int D, long long token_stride, int seq_len, bool backward, int num_sms,
                          cudaStream_t stream);

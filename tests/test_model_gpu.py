@@ -56,6 +56,9 @@ def test_engine_trains_and_uses_native_kernels():
         losses.append(float(out["loss"]))
     assert nat.LAUNCHES > n0
     assert losses[-1] < losses[0] - 0.5, losses
+    # every GEMM weight gradient was written straight into the flat buffer by the wgrad epilogue, also under
+    # activation checkpointing (whose saved-tensor hooks hand back attribute-less aliases of the weights)
+    assert model.engine.stats.get("wgrad_fallbacks", 0) == 0, model.engine.stats
 
 
 def test_grad_accumulation_matches_single_batch():

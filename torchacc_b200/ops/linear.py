@@ -80,6 +80,9 @@ class _LinearFn(torch.autograd.Function):
         y = torch.empty((*shp[:-1], w.shape[0]), dtype=x.dtype, device=x.device)
         gemm(x2, w, bias=bias, out=y.view(-1, w.shape[0]))
         ctx.save_for_backward(x2, w)
+        # the engine's hand-off attributes (_tb_grad_view / _tb_grad_ready) live on the parameter OBJECT; under
+        # non-reentrant activation checkpointing ctx.saved_tensors returns detached aliases without them
+        ctx.w_obj = w
         ctx.has_bias = bias is not None
         ctx.x_shape = shp
         return y
@@ -95,11 +98,12 @@ class _LinearFn(torch.autograd.Function):
             dx = torch.empty(ctx.x_shape, dtype=dy2.dtype, device=dy2.device)
             gemm(dy2, w, b_mn_major=True, out=dx.view(-1, ctx.x_shape[-1]))
         if ctx.needs_input_grad[1]:
-            view = getattr(w, "_tb_grad_view", None)
+            wo = ctx.w_obj
+            view = getattr(wo, "_tb_grad_view", None)
             if view is not None:
-                acc = bool(getattr(w, "_tb_grad_ready", False))
+                acc = bool(getattr(wo, "_tb_grad_ready", False))
                 gemm(dy2, x2, a_mn_major=True, b_mn_major=True, out=view, accumulate=acc)
-                w._tb_grad_ready = True
+                wo._tb_grad_ready = True
             else:
                 dw = gemm(dy2, x2, a_mn_major=True, b_mn_major=True)
         if ctx.has_bias and ctx.needs_input_grad[2]:

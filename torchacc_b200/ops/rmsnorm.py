@@ -52,13 +52,16 @@ class _RMSNormFn(torch.autograd.Function):
         dy2 = dy.contiguous().view(-1, H)
         dres = dh.contiguous().view(-1, H) if (dh is not None and ctx.has_res) else None
         dx = torch.empty(ctx.shape, dtype=h.dtype, device=h.device)
-        dw = torch.zeros(H, dtype=torch.float32, device=h.device)
+        # one CTA per partial row: each writes its fp32 column sums (no atomics), summed below
+        parts = max(1, min(rows, nat.num_sms() * 2))   # = resident CTAs (2 x 512 threads per SM): persistent rows loop
+        dw_part = torch.empty((parts, H), dtype=torch.float32, device=h.device)
         L = nat.require()
         nat.check(
             L.tb_rmsnorm_bwd(dy2.data_ptr(), h.data_ptr(), w.data_ptr(), rstd.data_ptr(), nat.ptr(dres),
-                             dx.data_ptr(), dw.data_ptr(), rows, H, nat.num_sms(), nat.stream()), "tb_rmsnorm_bwd")
+                             dx.data_ptr(), dw_part.data_ptr(), parts, rows, H, nat.num_sms(), nat.stream()),
+            "tb_rmsnorm_bwd")
         nat.count_launch()
-        return dx, dw.to(w.dtype), (dx if ctx.has_res else None), None
+        return dx, dw_part.sum(0).to(w.dtype), (dx if ctx.has_res else None), None
 
 
 def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-6,

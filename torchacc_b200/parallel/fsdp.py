@@ -277,6 +277,7 @@ class FlatParamUnit:
                 if t.grad is not None:  # e.g. the weight was also used through a non-fused path
                     dst.add_(t.grad.reshape(-1).to(dst.dtype))
                     t.grad = None
+                    self.engine.stats["wgrad_fallbacks"] = self.engine.stats.get("wgrad_fallbacks", 0) + 1
                 t._tb_grad_ready = False
                 continue
             if t.grad is not None:
@@ -453,6 +454,7 @@ class ShardingEngine:
         self.world_all = self.world_data
         self.reshard = strategy in ("FULL_SHARD", "HYBRID") and self.shard_world > 1
         self.root_unit = None
+        self.stats = {}                      # diagnostics (e.g. 'wgrad_fallbacks': wgrads that missed the flat buffer)
         self.shard_coll: Collectives = make_collectives(shard_group, device, prefer_symm)
         self.replica_coll: Collectives = make_collectives(replica_group, device, prefer_symm)
         # bf16 on the wire, fp32 accumulation at the destination (our kernels); plain fp32 training keeps fp32

@@ -29,8 +29,8 @@ nat.register_signatures({
                          nat.i32, nat.u64], nat.i32),
     "tb_gemm_rs_bf16": ([nat.u64, nat.u64, u64p, u64p, u64p, nat.i32, nat.i32, nat.i32, nat.i64, nat.i64, nat.i32,
                          nat.i32, nat.i32, nat.i32, nat.i32, ctypes.c_uint32, nat.i32, nat.u64], nat.i32),
-    "tb_rs_reduce_bf16": ([nat.u64, nat.u64, ctypes.c_uint32, nat.u64, nat.u64, nat.i64, nat.i32, nat.i64, nat.i32,
-                           nat.u64], nat.i32),
+    "tb_rs_reduce_bf16": ([nat.u64, nat.u64, ctypes.c_uint32, nat.u64, nat.u64, nat.i32, nat.i32, nat.i32, nat.i64,
+                           nat.i32, nat.u64], nat.i32),
 })
 
 CH_AG_GEMM, CH_GEMM_RS = 8, 9
@@ -40,7 +40,10 @@ TILE_M = 256
 class FusedTP:
     """Per-process-group state of the fused kernels: symmetric gather / staging buffers, counters, epochs."""
 
-    def __init__(self, group, device: torch.device, comm_clusters: int = 8):
+    def __init__(self, group, device: torch.device, comm_clusters: Optional[int] = None):
+        if comm_clusters is None:
+            import os
+            comm_clusters = int(os.environ.get("TORCHACC_B200_AG_CLUSTERS", "4"))
         self.domain = SymmDomain.get(group, device)
         self.device = device
         self.world, self.rank = self.domain.world, self.domain.rank
@@ -99,8 +102,9 @@ class FusedTP:
         N = w.shape[1] if b_mn_major else w.shape[0]
         rows = M // self.world
         key = (rows, N)
+        slot = rows * ((N + 255) // 256 * 256)       # block-major slots, N padded to the 256-column tile
         if key not in self._stage:
-            self._stage[key] = self.domain.alloc(self.world * rows * N, torch.bfloat16)
+            self._stage[key] = self.domain.alloc(self.world * slot, torch.bfloat16)
         stage = self._stage[key]
         d = self.domain
         sbuf, cbuf = d.find(stage), d.find(self.counters)
@@ -114,7 +118,7 @@ class FusedTP:
         out = torch.empty((rows, N), dtype=torch.bfloat16, device=x.device)
         nat.check(
             L.tb_rs_reduce_bf16(stage.data_ptr(), self.counters.data_ptr(), self.counter_expected, nat.ptr(residual),
-                                out.data_ptr(), rows * N, self.world, rows * N, nat.num_sms(), nat.stream()),
+                                out.data_ptr(), rows, N, self.world, slot, nat.num_sms(), nat.stream()),
             "tb_rs_reduce_bf16")
         nat.count_launch(2)
         return out

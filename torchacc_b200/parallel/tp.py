@@ -90,6 +90,7 @@ class _ColumnParallel(torch.autograd.Function):
             xf = _all_gather_rows(x2, tp) if tp.sequence_parallel else x2
             y = _mm(xf, w, bias=bias, out_dtype=x.dtype)
         ctx.save_for_backward(x2, w)
+        ctx.w_obj = w            # parameter object carrying the engine's _tb_grad_view (see ops/linear.py)
         ctx.tp, ctx.has_bias = tp, bias is not None
         return y
 
@@ -109,7 +110,7 @@ class _ColumnParallel(torch.autograd.Function):
                 dx = _reduce_scatter_rows(dx, tp)
             else:
                 tp.coll.all_reduce(dx)
-        dw = _wgrad(dy2, xf, w) if ctx.needs_input_grad[1] else None
+        dw = _wgrad(dy2, xf, ctx.w_obj) if ctx.needs_input_grad[1] else None
         db = dy2.float().sum(0).to(dy2.dtype) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx, dw, db, None
 
@@ -131,6 +132,7 @@ class _RowParallel(torch.autograd.Function):
             else:
                 tp.coll.all_reduce(y)
         ctx.save_for_backward(x2, w)
+        ctx.w_obj = w
         ctx.tp = tp
         return y
 
@@ -146,7 +148,7 @@ class _RowParallel(torch.autograd.Function):
         else:
             dyf = _all_gather_rows(dy2, tp) if tp.sequence_parallel else dy2
             dx = _mm(dyf, w, b_mn_major=True, out_dtype=dy2.dtype)
-        dw = _wgrad(dyf, x2, w) if ctx.needs_input_grad[1] else None
+        dw = _wgrad(dyf, x2, ctx.w_obj) if ctx.needs_input_grad[1] else None
         return dx, dw, None
 
 
