@@ -38,6 +38,13 @@ TB_API int tb_gemm_bf16(uint64_t A, uint64_t B, uint64_t D, uint64_t bias, int M
                             S(stream));
 }
 
+TB_API int tb_gemm_bf16_ex(uint64_t A, uint64_t B, uint64_t D, uint64_t bias, uint64_t C, int M, int N, int K,
+                           long long lda, long long ldb, long long ldd, long long ldc, int a_mn_major, int b_mn_major,
+                           int out_fp32, int cluster, int num_sms, uint64_t stream) {
+  return (int)tb::gemm_bf16_ex(P<void>(A), P<void>(B), P<void>(D), P<void>(bias), P<void>(C), M, N, K, lda, ldb, ldd, ldc,
+                               a_mn_major != 0, b_mn_major != 0, out_fp32 != 0, cluster, num_sms, S(stream));
+}
+
 // ---- norm / rope / activation -----------------------------------------------------------------------
 TB_API int tb_rmsnorm_fwd(uint64_t x, uint64_t res, uint64_t w, uint64_t y, uint64_t h_out, uint64_t rstd, int rows,
                           int H, float eps, int num_sms, uint64_t stream) {

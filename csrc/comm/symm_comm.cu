@@ -19,6 +19,7 @@
 // DDP and torch.distributed.
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../common/ptx.cuh"
 #include "comm.h"
@@ -195,9 +196,20 @@ all_to_all_kernel(Peers src, Pads pads, uint8_t* __restrict__ out, size_t chunk_
 // ----------------------------------------------------------------------------------------------------------
 // host API
 // ----------------------------------------------------------------------------------------------------------
+static int comm_cta_cap() {
+  static int cap = [] {
+    const char* e = getenv("TORCHACC_B200_COMM_CTAS");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : 64;
+  }();
+  return cap;
+}
+
 static int grid_for(size_t bytes, int num_sms) {
   size_t blocks = (bytes / 16 + 511) / 512;
-  const int cap = num_sms < 64 ? num_sms : 64;  // ~64 CTAs of 512 threads saturate NVLink; leave SMs for compute
+  // ~64 CTAs of 512 threads (4 x 16 B in flight per thread) saturate NVLink; the collectives run next to persistent
+  // GEMMs, so fewer CTAs leave more issue slots / L2 bandwidth to the tensor-core kernels
+  const int cap = num_sms < comm_cta_cap() ? num_sms : comm_cta_cap();
   if (blocks > (size_t)cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;

@@ -16,6 +16,12 @@ cudaError_t gemm_bf16(const void* A, const void* B, void* D, const void* bias, i
                       long long ldb, long long ldd, bool a_mn_major, bool b_mn_major, bool out_fp32, bool accumulate,
                       int cluster, int num_sms, cudaStream_t stream);
 
+// Same with a separate addend: D = A_op * B_op^T (+ bias) + C, C with D's dtype and row pitch ldc (C may alias D).
+// Used to fuse the transformer residual add into the down-projection epilogue.
+cudaError_t gemm_bf16_ex(const void* A, const void* B, void* D, const void* bias, const void* C, int M, int N, int K,
+                         long long lda, long long ldb, long long ldd, long long ldc, bool a_mn_major, bool b_mn_major,
+                         bool out_fp32, int cluster, int num_sms, cudaStream_t stream);
+
 // ---- fused tensor-parallel kernels (see the FuseArgs comment in gemm_bf16.cu) ----
 // all-gather -> GEMM: D[world*rows, N] = gather(A)[world*rows, K] * B_op^T.  `a_full` is this rank's symmetric
 // gathered buffer whose own row block is already filled; `peer_a_full[r]` is rank r's mapping of the same buffer.

@@ -65,7 +65,8 @@ struct GemmArgs {
   const __nv_bfloat16* bias;
   int M, N, K;
   long long ldd;
-  int accumulate;  // D += result
+  const void* C;   // optional addend with D's dtype: D = result (+ bias) + C.  C == D is gradient accumulation;
+  long long ldc;   // a different C fuses a residual add into the epilogue (h + x W^T).
   int out_fp32;
   int num_m_tiles, num_n_tiles;
   FuseArgs fuse;
@@ -463,29 +464,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         if (args.out_fp32) {
           float* dp = reinterpret_cast<float*>(args.D) + grow * args.ldd + gcol;
+          const float* cp = args.C ? reinterpret_cast<const float*>(args.C) + grow * args.ldc + gcol : nullptr;
           if (full) {
             float4* d4 = reinterpret_cast<float4*>(dp);
+            const float4* c4 = reinterpret_cast<const float4*>(cp);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-              if (args.accumulate) {
-                float4 old = d4[j];
+              if (cp) {
+                float4 old = c4[j];
                 o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
               }
               d4[j] = o;
             }
           } else {
             for (int j = 0; j < 32; ++j)
-              if (gcol + j < args.N) dp[j] = v[j] + (args.accumulate ? dp[j] : 0.f);
+              if (gcol + j < args.N) dp[j] = v[j] + (cp ? cp[j] : 0.f);
           }
         } else {
           __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(args.D) + grow * args.ldd + gcol;
+          const __nv_bfloat16* cp =
+              args.C ? reinterpret_cast<const __nv_bfloat16*>(args.C) + grow * args.ldc + gcol : nullptr;
           if (full) {
             uint4* d4 = reinterpret_cast<uint4*>(dp);
+            const uint4* c4 = reinterpret_cast<const uint4*>(cp);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              if (args.accumulate) {
-                uint4 old = d4[j];
+              if (cp) {
+                uint4 old = c4[j];
                 float2 f0 = unpack_bf16x2(old.x), f1 = unpack_bf16x2(old.y), f2 = unpack_bf16x2(old.z), f3 = unpack_bf16x2(old.w);
                 v[8 * j + 0] += f0.x; v[8 * j + 1] += f0.y; v[8 * j + 2] += f1.x; v[8 * j + 3] += f1.y;
                 v[8 * j + 4] += f2.x; v[8 * j + 5] += f2.y; v[8 * j + 6] += f3.x; v[8 * j + 7] += f3.y;
@@ -500,7 +506,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           } else {
             for (int j = 0; j < 32; ++j)
               if (gcol + j < args.N)
-                dp[j] = __float2bfloat16(v[j] + (args.accumulate ? __bfloat162float(dp[j]) : 0.f));
+                dp[j] = __float2bfloat16(v[j] + (cp ? __bfloat162float(cp[j]) : 0.f));
           }
         }
       }
@@ -561,12 +567,12 @@ static cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb_, con
 }
 
 static bool fill_common(GemmArgs& args, void* D, const void* bias, int M, int N, int K, long long ldd, bool out_fp32,
-                        bool accumulate, int cluster) {
+                        const void* C, long long ldc, int cluster) {
   args.D = D;
   args.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
   args.M = M; args.N = N; args.K = K;
   args.ldd = ldd;
-  args.accumulate = accumulate ? 1 : 0;
+  args.C = C; args.ldc = ldc;
   args.out_fp32 = out_fp32 ? 1 : 0;
   const int tile_m = kBlockMCta * cluster;
   args.num_m_tiles = (M + tile_m - 1) / tile_m;
@@ -578,6 +584,13 @@ static bool fill_common(GemmArgs& args, void* D, const void* bias, int M, int N,
 cudaError_t gemm_bf16(const void* A, const void* B, void* D, const void* bias, int M, int N, int K, long long lda,
                       long long ldb, long long ldd, bool a_mn_major, bool b_mn_major, bool out_fp32, bool accumulate,
                       int cluster, int num_sms, cudaStream_t stream) {
+  return gemm_bf16_ex(A, B, D, bias, accumulate ? D : nullptr, M, N, K, lda, ldb, ldd, ldd, a_mn_major, b_mn_major,
+                      out_fp32, cluster, num_sms, stream);
+}
+
+cudaError_t gemm_bf16_ex(const void* A, const void* B, void* D, const void* bias, const void* C, int M, int N, int K,
+                         long long lda, long long ldb, long long ldd, long long ldc, bool a_mn_major, bool b_mn_major,
+                         bool out_fp32, int cluster, int num_sms, cudaStream_t stream) {
   if (M <= 0 || N <= 0) return cudaSuccess;
   if (K <= 0) return cudaErrorInvalidValue;
   if (cluster != 1 && cluster != 2) return cudaErrorInvalidValue;
@@ -592,7 +605,7 @@ cudaError_t gemm_bf16(const void* A, const void* B, void* D, const void* bias, i
     return cudaErrorInvalidValue;
   }
   GemmArgs args;
-  fill_common(args, D, bias, M, N, K, ldd, out_fp32, accumulate, cluster);
+  fill_common(args, D, bias, M, N, K, ldd, out_fp32, C, ldc, cluster);
 
 #define TB_DISPATCH(CL, AM, BM) return launch_one<CL, AM, BM, 0>(ta, tbm, args, num_sms, stream)
   if (cluster == 2) {
@@ -637,7 +650,7 @@ cudaError_t ag_gemm_bf16(const uint64_t* peer_a_full, const uint64_t* pad_ptrs, 
     return cudaErrorInvalidValue;
   }
   GemmArgs args;
-  fill_common(args, D, bias, M, N, K, ldd, false, false, 2);
+  fill_common(args, D, bias, M, N, K, ldd, false, nullptr, 0, 2);
   FuseArgs& f = args.fuse;
   for (int i = 0; i < world; ++i) {
     f.peer[i] = reinterpret_cast<void*>(peer_a_full[i]);
@@ -667,7 +680,7 @@ cudaError_t gemm_rs_bf16(const void* A, const void* B, const uint64_t* peer_stag
     return cudaErrorInvalidValue;
   }
   GemmArgs args;
-  fill_common(args, nullptr, nullptr, M, N, K, /*ldd=*/N, false, false, 2);
+  fill_common(args, nullptr, nullptr, M, N, K, /*ldd=*/N, false, nullptr, 0, 2);
   FuseArgs& f = args.fuse;
   for (int i = 0; i < world; ++i) {
     f.peer[i] = reinterpret_cast<void*>(peer_stage[i]);

@@ -285,21 +285,43 @@ cudaError_t rope_inplace(void* x, const float* cos_t, const float* sin_t, const 
 // SwiGLU: h = silu(g) * u.  g and u are separate row-strided matrices [T, F] (for the fused gate|up projection
 // u = g + F and both strides are 2F); h is [T, F] contiguous.
 // ---------------------------------------------------------------------------------------------------
+// sigmoid through ONE MUFU op: sigmoid(x) = 0.5 + 0.5 * tanh(0.5 x)  (tanh.approx.f32, rel. error 2^-11 -- far below
+// the bf16 rounding of the result; exp + divide would be two MUFU ops plus the divide's fix-up code and makes the
+// kernel issue-bound instead of HBM-bound).
+TB_DEVICE float fast_sigmoid(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
+
+// One CTA walks whole rows (no per-element index division); two independent 16-byte vector pairs per thread and
+// iteration keep 4 loads in flight per thread.
 __global__ void __launch_bounds__(256)
 swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ g_, const __nv_bfloat16* __restrict__ u_,
                   __nv_bfloat16* __restrict__ h, long long T, int F, long long ldg, long long ldu) {
   const int vpr = F >> 3;
-  const long long total = T * vpr;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long t = i / vpr;
-    const int v = (int)(i - t * vpr);
-    float g[8], u[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(g_ + t * ldg + v * 8), g);
-    unpack8(*reinterpret_cast<const uint4*>(u_ + t * ldu + v * 8), u);
+  for (long long t = blockIdx.x; t < T; t += gridDim.x) {
+    const uint4* gp = reinterpret_cast<const uint4*>(g_ + t * ldg);
+    const uint4* up = reinterpret_cast<const uint4*>(u_ + t * ldu);
+    uint4* hp = reinterpret_cast<uint4*>(h + t * (long long)F);
+    for (int v = threadIdx.x; v < vpr; v += 512) {
+      const int v1 = v + 256;
+      const bool has1 = v1 < vpr;
+      const uint4 gr0 = __ldcs(gp + v), ur0 = __ldcs(up + v);
+      uint4 gr1 = gr0, ur1 = ur0;
+      if (has1) { gr1 = __ldcs(gp + v1); ur1 = __ldcs(up + v1); }
+      float g[8], u[8], o[8];
+      unpack8(gr0, g); unpack8(ur0, u);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = g[j] / (1.f + __expf(-g[j])) * u[j];
-    *reinterpret_cast<uint4*>(h + t * F + v * 8) = pack8(o);
+      for (int j = 0; j < 8; ++j) o[j] = g[j] * fast_sigmoid(g[j]) * u[j];
+      hp[v] = pack8(o);
+      if (has1) {
+        unpack8(gr1, g); unpack8(ur1, u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = g[j] * fast_sigmoid(g[j]) * u[j];
+        hp[v1] = pack8(o);
+      }
+    }
   }
 }
 
@@ -309,24 +331,42 @@ swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __r
                   __nv_bfloat16* __restrict__ du_, long long T, int F, long long ldg, long long ldu, long long lddg,
                   long long lddu) {
   const int vpr = F >> 3;
-  const long long total = T * vpr;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long t = i / vpr;
-    const int v = (int)(i - t * vpr);
-    float g[8], u[8], d[8], dg[8], du[8];
-    unpack8(*reinterpret_cast<const uint4*>(g_ + t * ldg + v * 8), g);
-    unpack8(*reinterpret_cast<const uint4*>(u_ + t * ldu + v * 8), u);
-    unpack8(*reinterpret_cast<const uint4*>(dh + t * F + v * 8), d);
+  for (long long t = blockIdx.x; t < T; t += gridDim.x) {
+    const uint4* gp = reinterpret_cast<const uint4*>(g_ + t * ldg);
+    const uint4* up = reinterpret_cast<const uint4*>(u_ + t * ldu);
+    const uint4* dp = reinterpret_cast<const uint4*>(dh + t * (long long)F);
+    uint4* dgp = reinterpret_cast<uint4*>(dg_ + t * lddg);
+    uint4* dup = reinterpret_cast<uint4*>(du_ + t * lddu);
+    for (int v = threadIdx.x; v < vpr; v += 512) {
+      const int v1 = v + 256;
+      const bool has1 = v1 < vpr;
+      const uint4 gr0 = __ldcs(gp + v), ur0 = __ldcs(up + v), dr0 = __ldcs(dp + v);
+      uint4 gr1 = gr0, ur1 = ur0, dr1 = dr0;
+      if (has1) { gr1 = __ldcs(gp + v1); ur1 = __ldcs(up + v1); dr1 = __ldcs(dp + v1); }
+      float g[8], u[8], d[8], dg[8], du[8];
+      unpack8(gr0, g); unpack8(ur0, u); unpack8(dr0, d);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float sg = 1.f / (1.f + __expf(-g[j]));
-      const float silu = g[j] * sg;
-      du[j] = d[j] * silu;
-      dg[j] = d[j] * u[j] * (sg + silu * (1.f - sg));
+      for (int j = 0; j < 8; ++j) {
+        const float sg = fast_sigmoid(g[j]);
+        const float silu = g[j] * sg;
+        du[j] = d[j] * silu;
+        dg[j] = d[j] * u[j] * (sg + silu * (1.f - sg));
+      }
+      dgp[v] = pack8(dg);
+      dup[v] = pack8(du);
+      if (has1) {
+        unpack8(gr1, g); unpack8(ur1, u); unpack8(dr1, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float sg = fast_sigmoid(g[j]);
+          const float silu = g[j] * sg;
+          du[j] = d[j] * silu;
+          dg[j] = d[j] * u[j] * (sg + silu * (1.f - sg));
+        }
+        dgp[v1] = pack8(dg);
+        dup[v1] = pack8(du);
+      }
     }
-    *reinterpret_cast<uint4*>(dg_ + t * lddg + v * 8) = pack8(dg);
-    *reinterpret_cast<uint4*>(du_ + t * lddu + v * 8) = pack8(du);
   }
 }
 
@@ -334,8 +374,7 @@ cudaError_t swiglu_fwd(const void* g, const void* u, void* h, long long T, int F
                        int num_sms, cudaStream_t stream) {
   if (T == 0) return cudaSuccess;
   if (F % 8 != 0 || ldg % 8 != 0 || ldu % 8 != 0) return cudaErrorInvalidValue;
-  long long blocks = (T * (F / 8) + 255) / 256;
-  int grid = (int)(blocks < (long long)num_sms * 16 ? blocks : (long long)num_sms * 16);
+  int grid = (int)(T < (long long)num_sms * 8 ? T : (long long)num_sms * 8);
   swiglu_fwd_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)u, (__nv_bfloat16*)h, T,
                                                F, ldg, ldu);
   return cudaGetLastError();
@@ -346,8 +385,7 @@ cudaError_t swiglu_bwd(const void* dh, const void* g, const void* u, void* dg, v
                        cudaStream_t stream) {
   if (T == 0) return cudaSuccess;
   if (F % 8 != 0 || ldg % 8 != 0 || ldu % 8 != 0 || lddg % 8 != 0 || lddu % 8 != 0) return cudaErrorInvalidValue;
-  long long blocks = (T * (F / 8) + 255) / 256;
-  int grid = (int)(blocks < (long long)num_sms * 16 ? blocks : (long long)num_sms * 16);
+  int grid = (int)(T < (long long)num_sms * 8 ? T : (long long)num_sms * 8);
   swiglu_bwd_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)dh, (const __nv_bfloat16*)g,
                                                (const __nv_bfloat16*)u, (__nv_bfloat16*)dg, (__nv_bfloat16*)du, T, F,
                                                ldg, ldu, lddg, lddu);

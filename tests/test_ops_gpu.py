@@ -62,6 +62,51 @@ def test_gemm_accumulate_into_view():
     _close(out32, ref / 2, 1e-3, 1e-2, "fp32 out")
 
 
+@pytest.mark.parametrize("shape", [(512, 384, 256), (200, 328, 136)])
+def test_linear_with_fused_residual(shape):
+    """y = x W^T + b + residual in ONE GEMM (epilogue addend); gradients of x, W, b and of the residual branch."""
+    from torchacc_b200.ops.linear import gemm, linear
+    M, N, K = shape
+    torch.manual_seed(2)
+    x = (torch.randn(M, K, device=_dev()) * 0.5).bfloat16().requires_grad_()
+    w = (torch.randn(N, K, device=_dev()) * 0.1).bfloat16().requires_grad_()
+    b = torch.randn(N, device=_dev()).bfloat16().requires_grad_()
+    r = torch.randn(M, N, device=_dev()).bfloat16().requires_grad_()
+    y = linear(x, w, b, residual=r)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xf, wf, bf, rf = (t.detach().float().requires_grad_() for t in (x, w, b, r))
+    yr = F.linear(xf, wf, bf) + rf
+    yr.backward(dy.float())
+    _close(y, yr, 2e-2, 5e-2, "y")
+    _close(x.grad, xf.grad, 2e-2, 5e-2, "dx")
+    _close(w.grad, wf.grad, 2e-2, 0.3, "dw")
+    _close(r.grad, rf.grad, 0, 0, "dresidual")
+    # fp32 output with an fp32 addend that is not the output buffer
+    c32 = torch.randn(M, N, device=_dev())
+    o32 = gemm(x.detach(), w.detach(), out_dtype=torch.float32, addend=c32)
+    _close(o32, x.detach().float() @ w.detach().float().t() + c32, 1e-3, 1e-2, "fp32 addend")
+
+
+def test_rmsnorm_passthrough_sums_skip_gradient():
+    """rmsnorm(..., passthrough=True) hands the input back as a second output; the gradient arriving on it is added
+    to dx inside the backward kernel (no separate accumulation pass)."""
+    from torchacc_b200.ops.rmsnorm import rmsnorm
+    torch.manual_seed(3)
+    T, H = 257, 4096
+    x = torch.randn(T, H, device=_dev()).bfloat16().requires_grad_()
+    w = (1 + 0.1 * torch.randn(H, device=_dev())).bfloat16().requires_grad_()
+    y, skip = rmsnorm(x, w, 1e-5, passthrough=True)
+    assert skip.data_ptr() == x.data_ptr()
+    dy, ds = torch.randn_like(y), torch.randn_like(y)
+    torch.autograd.backward([y, skip], [dy, ds])
+    xf, wf = x.detach().float().requires_grad_(), w.detach().float().requires_grad_()
+    yr = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5) * wf
+    torch.autograd.backward([yr, xf * 1.0], [dy.float(), ds.float()])
+    _close(x.grad, xf.grad, 3e-2, 3e-2, "dx")
+    _close(w.grad, wf.grad, 3e-2, 0.3, "dw")
+
+
 @pytest.mark.parametrize("H", [256, 4096, 8192, 1000 * 8])
 @pytest.mark.parametrize("residual", [False, True])
 def test_rmsnorm(H, residual):

@@ -23,6 +23,7 @@ _SIGS = {
     "tb_abi_version": ([], i32),
     "tb_device_info": ([i32, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i64)], i32),
     "tb_gemm_bf16": ([u64, u64, u64, u64, i32, i32, i32, i64, i64, i64, i32, i32, i32, i32, i32, i32, u64], i32),
+    "tb_gemm_bf16_ex": ([u64, u64, u64, u64, u64, i32, i32, i32, i64, i64, i64, i64, i32, i32, i32, i32, i32, u64], i32),
     "tb_rmsnorm_fwd": ([u64, u64, u64, u64, u64, u64, i32, i32, f32, i32, u64], i32),
     "tb_rmsnorm_bwd": ([u64, u64, u64, u64, u64, u64, u64, i32, i32, i32, i32, u64], i32),
     "tb_rope_inplace": ([u64, u64, u64, u64, i64, i32, i32, i64, i32, i32, i32, u64], i32),

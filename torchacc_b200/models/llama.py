@@ -154,13 +154,15 @@ class LlamaMLP(nn.Module):
         self.gate_up_proj = nn.Linear(cfg.hidden_size, 2 * cfg.intermediate_size, bias=False, **kw)
         self.down_proj = nn.Linear(cfg.intermediate_size, cfg.hidden_size, bias=False, **kw)
 
-    def forward(self, x, pctx=None):
+    def forward(self, x, pctx=None, residual=None):
+        """``residual`` (the skip branch) is added in the down-projection's GEMM epilogue."""
         tp = pctx.tp if pctx is not None else None
         if tp is not None:
             from ..parallel.tp import column_parallel_linear, row_parallel_linear
-            return row_parallel_linear(swiglu(column_parallel_linear(x, self.gate_up_proj.weight, None, tp)),
-                                       self.down_proj.weight, tp)
-        return linear(swiglu(linear(x, self.gate_up_proj.weight)), self.down_proj.weight)
+            m = row_parallel_linear(swiglu(column_parallel_linear(x, self.gate_up_proj.weight, None, tp)),
+                                    self.down_proj.weight, tp)
+            return m if residual is None else residual + m
+        return linear(swiglu(linear(x, self.gate_up_proj.weight)), self.down_proj.weight, residual=residual)
 
 
 class LlamaDecoderLayer(nn.Module):
@@ -180,11 +182,13 @@ class LlamaDecoderLayer(nn.Module):
         if pctx is not None and pctx.tp is not None:
             from ..parallel.tp import tp_replicated
             w1, w2 = tp_replicated(w1, pctx.tp), tp_replicated(w2, pctx.tp)
-        y, _ = rmsnorm(h, w1, self.input_layernorm.eps)
+        # no stand-alone elementwise adds: the skip branch leaves norm 1 as a pass-through output (its gradient is
+        # summed inside the norm's backward kernel), the attention residual is fused into norm 2, the MLP residual
+        # into the down-projection's GEMM epilogue
+        y, h_skip = rmsnorm(h, w1, self.input_layernorm.eps, passthrough=True)
         a = self.self_attn(y, rope, batch, seq_len, position_ids, cu_seqlens, pctx)
-        y2, h2 = rmsnorm(a, w2, self.post_attention_layernorm.eps, residual=h)
-        m = self.mlp(y2, pctx)
-        return h2 + m
+        y2, h2 = rmsnorm(a, w2, self.post_attention_layernorm.eps, residual=h_skip)
+        return self.mlp(y2, pctx, residual=h2)
 
 
 class _NormWeight(nn.Module):

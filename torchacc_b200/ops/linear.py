@@ -23,10 +23,12 @@ _CLUSTER = int(os.environ.get("TORCHACC_B200_GEMM_CLUSTER", "2"))
 
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_major: bool = False,
          out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, accumulate: bool = False,
-         out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
-    """``D[M,N] (+)= A_op[M,K] @ B_op[N,K]^T (+ bias)`` on 2-D bf16 tensors (last dim contiguous).
+         out_dtype: torch.dtype = torch.bfloat16, addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``D[M,N] (+)= A_op[M,K] @ B_op[N,K]^T (+ bias) (+ addend)`` on 2-D bf16 tensors (last dim contiguous).
 
     ``a`` is ``[M,K]`` (or ``[K,M]`` when ``a_mn_major``); ``b`` is ``[N,K]`` (or ``[K,N]`` when ``b_mn_major``).
+    ``addend`` ([M,N], D's dtype) is added in the GEMM epilogue (fused residual add); ``accumulate`` is the special
+    case addend == out.
     """
     assert a.dim() == 2 and b.dim() == 2
     if a_mn_major:
@@ -41,12 +43,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
     if out is None:
         assert not accumulate
         out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    assert not (accumulate and addend is not None)
     if not nat.use_native(a, b):
         A = a.t() if a_mn_major else a
         B = b if b_mn_major else b.t()
         r = A.float() @ B.float()
         if bias is not None:
             r = r + bias.float()
+        if addend is not None:
+            r = r + addend.float()
         if accumulate:
             out.add_(r.to(out.dtype))
         else:
@@ -59,10 +64,19 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
     if bias is not None:
         assert bias.dtype == torch.bfloat16 and bias.is_contiguous()
     L = nat.require()
-    nat.check(
-        L.tb_gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), nat.ptr(bias), M, N, K, a.stride(0), b.stride(0),
-                       out.stride(0), int(a_mn_major), int(b_mn_major), int(out.dtype == torch.float32),
-                       int(accumulate), _CLUSTER, nat.num_sms(), nat.stream()), "tb_gemm_bf16")
+    if addend is not None:
+        assert addend.dtype == out.dtype and addend.shape == out.shape and addend.stride(1) == 1 \
+            and addend.stride(0) % 8 == 0
+        nat.check(
+            L.tb_gemm_bf16_ex(a.data_ptr(), b.data_ptr(), out.data_ptr(), nat.ptr(bias), addend.data_ptr(), M, N, K,
+                              a.stride(0), b.stride(0), out.stride(0), addend.stride(0), int(a_mn_major),
+                              int(b_mn_major), int(out.dtype == torch.float32), _CLUSTER, nat.num_sms(), nat.stream()),
+            "tb_gemm_bf16_ex")
+    else:
+        nat.check(
+            L.tb_gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), nat.ptr(bias), M, N, K, a.stride(0), b.stride(0),
+                           out.stride(0), int(a_mn_major), int(b_mn_major), int(out.dtype == torch.float32),
+                           int(accumulate), _CLUSTER, nat.num_sms(), nat.stream()), "tb_gemm_bf16")
     nat.count_launch()
     return out
 
@@ -70,7 +84,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
 class _LinearFn(torch.autograd.Function):
 
     @staticmethod
-    def forward(ctx, x, w, bias):
+    def forward(ctx, x, w, bias, residual=None):
         shp = x.shape
         x2 = x.reshape(-1, shp[-1])
         if x2.stride(-1) != 1 or x2.stride(0) % 8 != 0:
@@ -78,7 +92,13 @@ class _LinearFn(torch.autograd.Function):
         # allocate with the final shape: returning a view made inside a custom Function would forbid later
         # in-place ops on the result (RoPE rotates the QKV activation in place)
         y = torch.empty((*shp[:-1], w.shape[0]), dtype=x.dtype, device=x.device)
-        gemm(x2, w, bias=bias, out=y.view(-1, w.shape[0]))
+        r2 = None
+        if residual is not None:
+            r2 = residual.reshape(-1, w.shape[0])
+            if r2.stride(-1) != 1 or r2.stride(0) % 8 != 0:
+                r2 = r2.contiguous()
+        gemm(x2, w, bias=bias, out=y.view(-1, w.shape[0]), addend=r2)   # y = x W^T (+ b) (+ residual), one kernel
+        ctx.has_res = residual is not None
         ctx.save_for_backward(x2, w)
         # the engine's hand-off attributes (_tb_grad_view / _tb_grad_ready) live on the parameter OBJECT; under
         # non-reentrant activation checkpointing ctx.saved_tensors returns detached aliases without them
@@ -108,14 +128,17 @@ class _LinearFn(torch.autograd.Function):
                 dw = gemm(dy2, x2, a_mn_major=True, b_mn_major=True)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy2.float().sum(0).to(dy2.dtype)
-        return dx, dw, db
+        return dx, dw, db, (dy if ctx.has_res else None)
 
 
-def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Drop-in for ``F.linear`` (bf16 CUDA tensors go through the tcgen05 GEMM)."""
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+           residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Drop-in for ``F.linear`` (bf16 CUDA tensors go through the tcgen05 GEMM).  ``residual`` (same shape as the
+    result) is added inside the GEMM epilogue: ``x @ w.T + bias + residual`` without a separate elementwise pass."""
     if x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and nat.use_native(x, w):
-        return _LinearFn.apply(x, w, bias)
-    return F.linear(x, w, bias)
+        return _LinearFn.apply(x, w, bias, residual)
+    y = F.linear(x, w, bias)
+    return y if residual is None else y + residual
 
 
 class Linear(torch.nn.Linear):

@@ -23,7 +23,7 @@ def rmsnorm_ref(x, w, eps, residual=None):
 class _RMSNormFn(torch.autograd.Function):
 
     @staticmethod
-    def forward(ctx, x, w, residual, eps):
+    def forward(ctx, x, w, residual, eps, passthrough=False):
         H = x.shape[-1]
         x2 = x.contiguous().view(-1, H)
         r2 = residual.contiguous().view(-1, H) if residual is not None else None
@@ -39,9 +39,12 @@ class _RMSNormFn(torch.autograd.Function):
         nat.count_launch()
         ctx.save_for_backward(h.view(-1, H) if r2 is not None else h, w, rstd)
         ctx.has_res = r2 is not None
+        ctx.passthrough = bool(passthrough) and r2 is None
         ctx.shape = x.shape
         if r2 is not None:
             return y, h
+        if ctx.passthrough:
+            return y, x.view_as(x)      # identity branch: its gradient is added inside the backward kernel
         return y, None
 
     @staticmethod
@@ -50,7 +53,7 @@ class _RMSNormFn(torch.autograd.Function):
         H = h.shape[-1]
         rows = h.shape[0]
         dy2 = dy.contiguous().view(-1, H)
-        dres = dh.contiguous().view(-1, H) if (dh is not None and ctx.has_res) else None
+        dres = dh.contiguous().view(-1, H) if (dh is not None and (ctx.has_res or ctx.passthrough)) else None
         dx = torch.empty(ctx.shape, dtype=h.dtype, device=h.device)
         # one CTA per partial row: each writes its fp32 column sums (no atomics), summed below
         parts = max(1, min(rows, nat.num_sms() * 2))   # = resident CTAs (2 x 512 threads per SM): persistent rows loop
@@ -61,18 +64,20 @@ class _RMSNormFn(torch.autograd.Function):
                              dx.data_ptr(), dw_part.data_ptr(), parts, rows, H, nat.num_sms(), nat.stream()),
             "tb_rmsnorm_bwd")
         nat.count_launch()
-        return dx, dw_part.sum(0).to(w.dtype), (dx if ctx.has_res else None), None
+        return dx, dw_part.sum(0).to(w.dtype), (dx if ctx.has_res else None), None, None
 
 
-def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-6,
-            residual: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-6, residual: Optional[torch.Tensor] = None,
+            passthrough: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Returns ``(y, h)``: ``h = x + residual`` (the updated residual stream, ``None`` without residual) and
-    ``y = rmsnorm(h) * weight``."""
+    ``y = rmsnorm(h) * weight``.  With ``passthrough`` (and no residual) ``h`` is ``x`` itself routed through the
+    op, so a consumer of the skip branch sends its gradient into the fused backward kernel instead of a separate
+    autograd accumulation pass."""
     if x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and nat.use_native(x, weight) \
             and x.shape[-1] % 8 == 0 and x.shape[-1] <= 16384:
-        return _RMSNormFn.apply(x, weight, residual, eps)
+        return _RMSNormFn.apply(x, weight, residual, eps, passthrough)
     y, h = rmsnorm_ref(x, weight, eps, residual)
-    return y, (h if residual is not None else None)
+    return y, (h if residual is not None else (x if passthrough else None))
 
 
 class RMSNorm(torch.nn.Module):

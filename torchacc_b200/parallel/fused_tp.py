@@ -43,7 +43,7 @@ class FusedTP:
     def __init__(self, group, device: torch.device, comm_clusters: Optional[int] = None):
         if comm_clusters is None:
             import os
-            comm_clusters = int(os.environ.get("TORCHACC_B200_AG_CLUSTERS", "4"))
+            comm_clusters = int(os.environ.get("TORCHACC_B200_AG_CLUSTERS", "0"))   # 0 = per-shape heuristic
         self.domain = SymmDomain.get(group, device)
         self.device = device
         self.world, self.rank = self.domain.world, self.domain.rank
@@ -81,13 +81,17 @@ class FusedTP:
         y = torch.empty((self.world * rows, N), dtype=x_shard.dtype, device=x_shard.device)
         d = self.domain
         buf = d.find(full)
+        # copy clusters: a short GEMM (small N) has little math to hide the transfer behind -> more copy CTAs;
+        # a long one prefers the SMs for tensor work (measured at N=2: profiles/fused_tp_bench_*.txt)
+        cc = self.comm_clusters if self.comm_clusters > 0 else (8 if N <= 4096 else 4)
+        self.flag_total = getattr(self, "flag_total", 0) + cc * 2
         self.flag_calls += 1
         L = nat.require()
         nat.check(
             L.tb_ag_gemm_bf16(buf.peer_ptrs, d.pad_ptrs, full.data_ptr(), w.data_ptr(), y.data_ptr(), nat.ptr(bias), rows,
                               N, K, w.stride(0), y.stride(0), int(b_mn_major), self.rank, self.world,
-                              self.flags.data_ptr(), self.flag_calls * self.comm_clusters * 2,
-                              self.block_counter.data_ptr(), CH_AG_GEMM, d.next_epoch(CH_AG_GEMM), self.comm_clusters,
+                              self.flags.data_ptr(), self.flag_total,
+                              self.block_counter.data_ptr(), CH_AG_GEMM, d.next_epoch(CH_AG_GEMM), cc,
                               nat.num_sms(), nat.stream()), "tb_ag_gemm_bf16")
         nat.count_launch()
         return y, full
