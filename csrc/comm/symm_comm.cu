@@ -215,6 +215,28 @@ static int grid_for(size_t bytes, int num_sms) {
   return (int)blocks;
 }
 
+// The collectives run concurrently with persistent tcgen05 GEMM CTAs that need the maximum shared-memory carve-out
+// (~199 KB).  An SM cannot host CTAs of two kernels with different L1/shared carve-outs: with the default (L1-heavy)
+// configuration every SM holding a collective CTA was closed to the GEMM until the collective finished, and GEMMs
+// overlapping a collective ran 3.3x slower (profiles/step_timeline_n2_run15.txt).  Asking for the max-shared
+// carve-out makes both kernels co-resident.
+template <typename K>
+static void prefer_max_smem_carveout(K kernel) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+static void configure_kernels_once() {
+  static bool done = [] {
+    prefer_max_smem_carveout(all_gather_kernel);
+    prefer_max_smem_carveout(all_to_all_kernel);
+    prefer_max_smem_carveout(reduce_scatter_kernel<__nv_bfloat16, float>);
+    prefer_max_smem_carveout(reduce_scatter_kernel<__nv_bfloat16, __nv_bfloat16>);
+    prefer_max_smem_carveout(reduce_scatter_kernel<float, float>);
+    prefer_max_smem_carveout(reduce_scatter_kernel<float, __nv_bfloat16>);
+    return true;
+  }();
+  (void)done;
+}
+
 static void fill(Peers& p, Pads& q, const uint64_t* peer_ptrs, const uint64_t* pad_ptrs, int world, size_t off_bytes) {
   for (int i = 0; i < kMaxWorld; ++i) {
     p.ptr[i] = i < world ? reinterpret_cast<void*>(peer_ptrs[i] + off_bytes) : nullptr;
@@ -227,6 +249,7 @@ cudaError_t symm_all_gather(const uint64_t* peer_ptrs, const uint64_t* pad_ptrs,
                             int num_sms, cudaStream_t stream) {
   if (world > kMaxWorld || bytes % 16 != 0 || channel >= kPadChannels) return cudaErrorInvalidValue;
   Peers p; Pads q;
+  configure_kernels_once();
   fill(p, q, peer_ptrs, pad_ptrs, world, src_off_bytes);
   all_gather_kernel<<<grid_for(bytes * world, num_sms), 512, 0, stream>>>(p, q, (uint8_t*)out, bytes, rank, world,
                                                                           channel, epoch, block_counter);
@@ -239,6 +262,7 @@ cudaError_t symm_reduce_scatter(const uint64_t* peer_ptrs, const uint64_t* pad_p
   if (world > kMaxWorld || channel >= kPadChannels) return cudaErrorInvalidValue;
   if (n % (in_bf16 ? 8 : 4) != 0) return cudaErrorInvalidValue;
   Peers p; Pads q;
+  configure_kernels_once();
   fill(p, q, peer_ptrs, pad_ptrs, world, src_off_bytes);
   const int grid = grid_for(n * (in_bf16 ? 2 : 4) * world, num_sms);
 #define TB_RS(IN, OUT)                                                                                          \
@@ -257,6 +281,7 @@ cudaError_t symm_all_to_all(const uint64_t* peer_ptrs, const uint64_t* pad_ptrs,
                             uint32_t* block_counter, int num_sms, cudaStream_t stream) {
   if (world > kMaxWorld || chunk_bytes % 16 != 0 || channel >= kPadChannels) return cudaErrorInvalidValue;
   Peers p; Pads q;
+  configure_kernels_once();
   fill(p, q, peer_ptrs, pad_ptrs, world, src_off_bytes);
   all_to_all_kernel<<<grid_for(chunk_bytes * world, num_sms), 512, 0, stream>>>(p, q, (uint8_t*)out, chunk_bytes, rank,
                                                                                 world, channel, epoch, block_counter);

@@ -106,6 +106,8 @@ def use_native(*tensors) -> bool:
     """Decide between the sm_100a kernels and the PyTorch reference path for these tensors."""
     if not tensors or not all(t.is_cuda for t in tensors if isinstance(t, torch.Tensor)):
         return False
+    if os.environ.get("TORCHACC_B200_DISABLE_NATIVE", "0") == "1":   # accuracy baselines: plain PyTorch ops on the GPU
+        return False
     if lib() is None:
         if allow_fallback():
             return False

@@ -68,15 +68,10 @@ def accelerate(model: nn.Module, dataloader=None, config: Optional[Config] = Non
     orig_sig = inspect.signature(model.forward)
     _materialize_meta(model, device)
 
-    needs_wrapper = config.is_distributed_parallel() or config.compute.dtype != torch.float32
-    if needs_wrapper:
-        model = DistributedParallel(model, config, orig_forward_sig=orig_sig)
-        model.to(device)
-    else:
-        if config.memory.gc and config.memory.gc_cls:
-            from .utils.checkpoint import gradient_checkpoint
-            model = gradient_checkpoint(model, config.memory.gc_cls, config.memory.gc_cnt)
-        model = model.to(device)
+    # always the same wrapper type (reference accelerate.py:127-131): training scripts call model.clip_grad_norm_ /
+    # *_optim_state_dict regardless of the world size; with one rank the engine simply has no collectives
+    model = DistributedParallel(model, config, orig_forward_sig=orig_sig)
+    model.to(device)
     if not isinstance(getattr(type(model), "device", None), property):   # HF models expose a read-only property
         try:
             model.device = device

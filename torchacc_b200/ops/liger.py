@@ -96,13 +96,22 @@ def patch_linears(model: nn.Module) -> int:
 
 
 def apply_liger_kernel(model: Optional[nn.Module] = None) -> None:
-    """Best-effort patching used by ``accelerate()`` (reference liger.py:133-153)."""
+    """Best-effort patching used by ``accelerate()`` (reference liger.py:133-153).  With a model, only the HF
+    families that actually occur in it are patched (class-level patches are process-global; a native model must not
+    change how unrelated HF models behave); without one, every supported family is patched like the reference."""
     try:
         import transformers  # noqa: F401
     except Exception:
         transformers = None
     if transformers is not None:
-        for fn in (apply_liger_kernel_to_llama, apply_liger_kernel_to_qwen2):
+        families = {"transformers.models.llama.": apply_liger_kernel_to_llama,
+                    "transformers.models.qwen2.": apply_liger_kernel_to_qwen2}
+        if model is None:
+            wanted = list(families.values())
+        else:
+            mods = {type(m).__module__ for m in model.modules()}
+            wanted = [fn for prefix, fn in families.items() if any(x.startswith(prefix) for x in mods)]
+        for fn in wanted:
             try:
                 fn()
             except Exception as e:  # pragma: no cover - depends on the installed transformers
