@@ -38,6 +38,7 @@ TB_API int tb_gemm_bf16(uint64_t A, uint64_t B, uint64_t D, uint64_t bias, int M
                             S(stream));
 }
 
+TB_API int tb_gemm_sched_mode(int mode) { return tb::gemm_sched_mode(mode); }
 TB_API int tb_gemm_bf16_ex(uint64_t A, uint64_t B, uint64_t D, uint64_t bias, uint64_t C, int M, int N, int K,
                            long long lda, long long ldb, long long ldd, long long ldc, int a_mn_major, int b_mn_major,
                            int out_fp32, int cluster, int num_sms, uint64_t stream) {

@@ -93,22 +93,26 @@ TB_DEVICE void barrier_exit(const Pads& pads, int rank, int world, int ch, uint3
 // ----------------------------------------------------------------------------------------------------------
 // all-gather (bytes): out + r*bytes <- peer[r] (+ src_off)
 // ----------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512)
-all_gather_kernel(Peers src, Pads pads, uint8_t* __restrict__ out, size_t bytes, int rank, int world, int ch,
-                  uint32_t epoch, uint32_t* block_counter) {
+// Register budget matters here: these kernels run NEXT TO persistent tcgen05 GEMM CTAs (256 threads x 96 registers).
+// At 32 registers x 512 threads a collective CTA takes a quarter of an SM's register file and co-resides with the
+// GEMM; the first version (128 registers: the whole file) kept every SM it touched closed to the GEMM, which then
+// finished only after the collective (profiles/step_timeline_n2_run15.txt: overlapped GEMMs 3.3x slower).
+__global__ void __launch_bounds__(512, 4)
+all_gather_kernel(const __grid_constant__ Peers src, const __grid_constant__ Pads pads, uint8_t* __restrict__ out,
+                  size_t bytes, int rank, int world, int ch, uint32_t epoch, uint32_t* block_counter) {
   barrier_enter(pads, rank, world, ch, epoch);
-  const size_t nvec = bytes >> 4;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nvec = (uint32_t)(bytes >> 4);                 // < 2^31 vectors (32 GB) per shard
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   for (int step = 0; step < world; ++step) {
     const int r = (rank + step) % world;  // start with the local shard, then walk the ring so peers are hit evenly
     const uint4* s = reinterpret_cast<const uint4*>(src.ptr[r]);
     uint4* d = reinterpret_cast<uint4*>(out + (size_t)r * bytes);
     if (r == rank && (const void*)s == (const void*)d) continue;  // shard already lives inside the output buffer
-    size_t i = tid;
+    uint32_t i = tid;
     for (; i + 3 * stride < nvec; i += 4 * stride) {
-      uint4 a = ld_peer_v4(s + i), b = ld_peer_v4(s + i + stride), c = ld_peer_v4(s + i + 2 * stride),
-            e = ld_peer_v4(s + i + 3 * stride);
+      const uint4 a = ld_peer_v4(s + i), b = ld_peer_v4(s + i + stride), c = ld_peer_v4(s + i + 2 * stride),
+                  e = ld_peer_v4(s + i + 3 * stride);
       d[i] = a; d[i + stride] = b; d[i + 2 * stride] = c; d[i + 3 * stride] = e;
     }
     for (; i < nvec; i += stride) d[i] = ld_peer_v4(s + i);
@@ -120,8 +124,8 @@ all_gather_kernel(Peers src, Pads pads, uint8_t* __restrict__ out, size_t bytes,
 // reduce-scatter: out[i] = scale * sum_r peer_r[rank*n + i], fp32 accumulation.  In: bf16 or fp32.  Out: fp32/bf16.
 // ----------------------------------------------------------------------------------------------------------
 template <typename InT, typename OutT>
-__global__ void __launch_bounds__(512)
-reduce_scatter_kernel(Peers src, Pads pads, OutT* __restrict__ out, size_t n, float scale, int rank, int world, int ch,
+__global__ void __launch_bounds__(512, 3)
+reduce_scatter_kernel(const __grid_constant__ Peers src, const __grid_constant__ Pads pads, OutT* __restrict__ out, size_t n, float scale, int rank, int world, int ch,
                       uint32_t epoch, uint32_t* block_counter) {
   barrier_enter(pads, rank, world, ch, epoch);
   constexpr int kPer = 16 / sizeof(InT);  // elements per 16-byte load: 8 (bf16) or 4 (fp32)
@@ -131,25 +135,29 @@ reduce_scatter_kernel(Peers src, Pads pads, OutT* __restrict__ out, size_t n, fl
     float acc[kPer];
 #pragma unroll
     for (int j = 0; j < kPer; ++j) acc[j] = 0.f;
-    uint4 v[kMaxWorld];
+    // four peers per batch: 4 loads in flight, 16 data registers (the kernel must stay small enough to share an SM
+    // with a GEMM CTA and an all-gather CTA)
+    for (int base = 0; base < world; base += 4) {
+      uint4 v[4];
 #pragma unroll
-    for (int step = 0; step < kMaxWorld; ++step) {
-      if (step < world) {
-        const int r = (rank + step) % world;
-        v[step] = ld_peer_v4(reinterpret_cast<const uint4*>(reinterpret_cast<const InT*>(src.ptr[r]) + (size_t)rank * n) + i);
+      for (int j = 0; j < 4; ++j) {
+        if (base + j < world) {
+          const int r = (rank + base + j) % world;
+          v[j] = ld_peer_v4(reinterpret_cast<const uint4*>(reinterpret_cast<const InT*>(src.ptr[r]) + (size_t)rank * n) + i);
+        }
       }
-    }
 #pragma unroll
-    for (int step = 0; step < kMaxWorld; ++step) {
-      if (step < world) {
-        if constexpr (sizeof(InT) == 2) {
-          float2 a = unpack_bf16x2(v[step].x), b = unpack_bf16x2(v[step].y), c = unpack_bf16x2(v[step].z),
-                 d = unpack_bf16x2(v[step].w);
-          acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
-          acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
-        } else {
-          acc[0] += __uint_as_float(v[step].x); acc[1] += __uint_as_float(v[step].y);
-          acc[2] += __uint_as_float(v[step].z); acc[3] += __uint_as_float(v[step].w);
+      for (int j = 0; j < 4; ++j) {
+        if (base + j < world) {
+          if constexpr (sizeof(InT) == 2) {
+            float2 a = unpack_bf16x2(v[j].x), b = unpack_bf16x2(v[j].y), c = unpack_bf16x2(v[j].z),
+                   d = unpack_bf16x2(v[j].w);
+            acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+            acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+          } else {
+            acc[0] += __uint_as_float(v[j].x); acc[1] += __uint_as_float(v[j].y);
+            acc[2] += __uint_as_float(v[j].z); acc[3] += __uint_as_float(v[j].w);
+          }
         }
       }
     }
@@ -178,8 +186,8 @@ reduce_scatter_kernel(Peers src, Pads pads, OutT* __restrict__ out, size_t n, fl
 // ----------------------------------------------------------------------------------------------------------
 // all-to-all (bytes): out + r*chunk <- peer[r] + rank*chunk
 // ----------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512)
-all_to_all_kernel(Peers src, Pads pads, uint8_t* __restrict__ out, size_t chunk_bytes, int rank, int world, int ch,
+__global__ void __launch_bounds__(512, 4)
+all_to_all_kernel(const __grid_constant__ Peers src, const __grid_constant__ Pads pads, uint8_t* __restrict__ out, size_t chunk_bytes, int rank, int world, int ch,
                   uint32_t epoch, uint32_t* block_counter) {
   barrier_enter(pads, rank, world, ch, epoch);
   const size_t nvec = chunk_bytes >> 4;

@@ -204,6 +204,45 @@ TB_DEVICE void tma_store_wait() {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Cluster launch control (sm_100): a running cluster cancels a not-yet-launched cluster of the same grid and
+// receives its coordinates -- hardware work stealing for "persistent" kernels launched with one cluster per tile.
+// The 16-byte response lands in shared memory (of every CTA of the cluster with .multicast) and completes 16
+// transaction bytes on the mbarrier at the same offset.
+// ----------------------------------------------------------------------------------------------
+template <bool kMulticast>
+TB_DEVICE void clc_try_cancel(uint32_t resp_smem, uint32_t bar) {
+  if constexpr (kMulticast) {
+    asm volatile(
+        "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 "
+        "[%0], [%1];" ::"r"(resp_smem), "r"(bar)
+        : "memory");
+  } else {
+    asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];"
+                 ::"r"(resp_smem), "r"(bar)
+                 : "memory");
+  }
+}
+// Returns true and the x coordinate of the first CTA of the cancelled cluster, or false if nothing was left to cancel.
+TB_DEVICE bool clc_query(uint32_t resp_smem, uint32_t& first_ctaid_x) {
+  uint32_t valid, x;
+  asm volatile(
+      "{\n"
+      ".reg .pred p1;\n"
+      ".reg .b128 r;\n"
+      "ld.shared.b128 r, [%2];\n"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n"
+      "selp.u32 %1, 1, 0, p1;\n"
+      "mov.u32 %0, 0;\n"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid::x.b32.b128 %0, r;\n"
+      "}\n"
+      : "=r"(x), "=r"(valid)
+      : "r"(resp_smem)
+      : "memory");
+  first_ctaid_x = x;
+  return valid != 0;
+}
+
+// ----------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, ld/st, fences
 // ----------------------------------------------------------------------------------------------
 template <int kCtaGroup>

@@ -16,6 +16,10 @@ cudaError_t gemm_bf16(const void* A, const void* B, void* D, const void* bias, i
                       long long ldb, long long ldd, bool a_mn_major, bool b_mn_major, bool out_fp32, bool accumulate,
                       int cluster, int num_sms, cudaStream_t stream);
 
+// Tile scheduling of the unfused GEMM: 1 = dynamic (one cluster per tile, claimed with cluster launch control; robust
+// against SMs that are busy with a concurrent kernel), 0 = static striping over a persistent grid.  mode < 0 queries.
+int gemm_sched_mode(int mode);
+
 // Same with a separate addend: D = A_op * B_op^T (+ bias) + C, C with D's dtype and row pitch ldc (C may alias D).
 // Used to fuse the transformer residual add into the down-projection epilogue.
 cudaError_t gemm_bf16_ex(const void* A, const void* B, void* D, const void* bias, const void* C, int M, int N, int K,

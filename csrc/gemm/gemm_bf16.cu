@@ -20,6 +20,7 @@
 // Reference parity: replaces the cuBLAS GEMMs the reference reaches through nn.Linear
 // (reference torchacc/__init__.py:97-98 forces XLA onto cuBLAS; eager path uses cuBLASLt).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../common/ptx.cuh"
@@ -69,6 +70,7 @@ struct GemmArgs {
   long long ldc;   // a different C fuses a residual add into the epilogue (h + x W^T).
   int out_fp32;
   int num_m_tiles, num_n_tiles;
+  int dynamic;     // 1: grid = one cluster per tile, tiles are claimed with cluster-launch-control (see kernel comment)
   FuseArgs fuse;
 };
 
@@ -231,6 +233,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  // dynamic tile scheduler (cluster launch control): 16-byte responses + full/empty barriers
+  constexpr int kSched = 4;
+  auto clc_full = [&](int s) { return bar_base + 8u * (2 * kStages + 6 + s); };
+  auto clc_empty = [&](int s) { return bar_base + 8u * (2 * kStages + 6 + kSched + s); };
+  auto clc_resp = [&](int s) { return bar_base + 512u + 16u * s; };
+  constexpr uint32_t kSchedConsumers = 5 * kCluster + 1;   // per CTA: TMA warp + 4 epilogue warps; + the MMA warp
   auto smem_a = [&](int s) { return smem_base + s * S::kStageBytes; };
   auto smem_b = [&](int s) { return smem_base + s * S::kStageBytes + S::kABytes; };
 
@@ -278,6 +286,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 4 * kCluster);  // one arrive per epilogue warp (of both CTAs)
     }
+    for (int s = 0; s < kSched; ++s) {
+      mbar_init(clc_full(s), 1);
+      mbar_init(clc_empty(s), kSchedConsumers);
+    }
     fence_mbar_init();
   }
   if (warp_idx == 2) tmem_alloc<kCluster>(tmem_slot, 512);
@@ -287,11 +299,54 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  // ---- tile iteration ----
+  // static : tile = cluster_id, += num_clusters (one resident cluster per SM pair for the whole kernel)
+  // dynamic: the grid has one cluster per tile.  A launched cluster starts with the tile of its own index and then
+  //          claims not-yet-launched clusters through cluster launch control until none is left.  SMs that are busy
+  //          with another kernel (a collective on a side stream) simply join late or never: the remaining clusters
+  //          absorb their tiles instead of the whole GEMM waiting for stragglers.
+  const bool dynamic = (kFuse == 0) && args.dynamic != 0;
+  int sched_it = 0;   // per role thread: position in the response pipeline
+  auto advance = [&](int& tile, bool do_arrive) -> bool {
+    if (!dynamic) {
+      tile += num_clusters;
+      return tile < num_tiles;
+    }
+    const int s = sched_it % kSched;
+    mbar_wait(clc_full(s), (sched_it / kSched) & 1);
+    uint32_t x;
+    const bool valid = clc_query(clc_resp(s), x);
+    fence_proxy_async_smem();   // our read of the response precedes the next asynchronous write of this slot
+    if (do_arrive) {
+      if constexpr (kCluster == 2) mbar_arrive_cluster(mapa_shared(clc_empty(s), 0));
+      else mbar_arrive(clc_empty(s));
+    }
+    ++sched_it;
+    tile = (int)(x / kCluster);
+    return valid;
+  };
+  if (dynamic && warp_idx == 3 && lane == 0) {
+    // ================================ Tile scheduler ================================
+    for (int it = 0;; ++it) {
+      const int s = it % kSched;
+      if (is_leader && it >= kSched) {   // every consumer (of both CTAs) has read the previous response in this slot
+        if constexpr (kCluster == 2) mbar_wait_cluster(clc_empty(s), ((it / kSched) - 1) & 1);
+        else mbar_wait(clc_empty(s), ((it / kSched) - 1) & 1);
+      }
+      mbar_arrive_expect_tx(clc_full(s), 16);       // each CTA arms its own barrier; the response is multicast
+      if (is_leader) clc_try_cancel<kCluster == 2>(clc_resp(s), clc_full(s));
+      mbar_wait(clc_full(s), (it / kSched) & 1);
+      uint32_t x;
+      if (!clc_query(clc_resp(s), x)) break;
+    }
+  }
+
   if (warp_idx == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
       int it = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      int t = cluster_id;
+      for (bool more = t < num_tiles; more; more = advance(t, true)) {
         int tm, tn, shard;
         coords(t, tm, tn, shard);
         const int m0 = tm * (int)kUmmaM + (int)cta_rank * kBlockMCta;
@@ -332,7 +387,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ================================ MMA issuer ================================
     if (is_leader && lane == 0) {
       int it = 0, lt = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++lt) {
+      int t = cluster_id;
+      for (bool more = t < num_tiles; more; more = advance(t, true), ++lt) {
         const int as = lt & 1;
         const uint32_t aph = (lt >> 1) & 1;
         if constexpr (kCluster == 2) mbar_wait_cluster(tempty_bar(as), aph ^ 1);
@@ -385,7 +441,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     };
-    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++lt) {
+    int t = cluster_id;
+    for (bool more = t < num_tiles; more; more = advance(t, lane == 0), ++lt) {
       int tm, tn, shard;
       coords(t, tm, tn, shard);
       const int as = lt & 1;
@@ -551,6 +608,7 @@ static cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb_, con
   if (clusters > num_tiles) clusters = num_tiles;
   if (clusters < 1) clusters = 1;
   if (kFuse == 1) clusters += args.fuse.comm_clusters;
+  if (kFuse == 0 && args.dynamic) clusters = num_tiles;   // one cluster per tile; extra ones are cancelled on device
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * kCluster);
   cfg.blockDim = dim3(kNumThreads);
@@ -566,6 +624,18 @@ static cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb_, con
   return cudaLaunchKernelEx(&cfg, kern, ta, tb_, args);
 }
 
+// 1 = dynamic (cluster-launch-control) tile scheduling, 0 = static striping.  mode < 0 only queries.
+int gemm_sched_mode(int mode) {
+  // default static: ~1-3 % faster when the GEMM owns the GPU (profiles/gemm_sched_ab_run21.txt); the sharding engine
+  // switches to dynamic when collectives run next to the GEMMs.  TORCHACC_B200_GEMM_SCHED=static|dynamic pins it.
+  static int current = [] {
+    const char* e = getenv("TORCHACC_B200_GEMM_SCHED");
+    return (e && e[0] == 'd') ? 1 : 0;
+  }();
+  if (mode >= 0) current = mode ? 1 : 0;
+  return current;
+}
+
 static bool fill_common(GemmArgs& args, void* D, const void* bias, int M, int N, int K, long long ldd, bool out_fp32,
                         const void* C, long long ldc, int cluster) {
   args.D = D;
@@ -577,6 +647,7 @@ static bool fill_common(GemmArgs& args, void* D, const void* bias, int M, int N,
   const int tile_m = kBlockMCta * cluster;
   args.num_m_tiles = (M + tile_m - 1) / tile_m;
   args.num_n_tiles = (N + kBlockN - 1) / kBlockN;
+  args.dynamic = gemm_sched_mode(-1);
   memset(&args.fuse, 0, sizeof(args.fuse));
   return true;
 }

@@ -114,14 +114,17 @@ static void perf_case(cublasHandle_t h, const char* name, int M, int N, int K, i
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   double flops = 2.0 * M * N * K;
   float alpha = 1.f, beta = 0.f;
-  for (int mode = 0; mode < 3; ++mode) {  // 0: ours cluster1, 1: ours cluster2, 2: cuBLAS
+  for (int mode = 0; mode < 4; ++mode) {  // 0: ours cluster1, 1: ours cluster2 (dynamic), 2: cuBLAS, 3: cluster2 static
     if (mode < 2 && !(cl_mask & (1 << mode))) continue;
+    if (mode == 3 && !(cl_mask & 2)) continue;
+    tb::gemm_sched_mode(mode == 3 ? 0 : 1);
     float best = 1e30f, total = 0;
     for (int i = 0; i < iters + 3; ++i) {
       CK(cudaMemsetAsync(flush, i, flush_bytes, 0));  // flush L2 (126 MB) between timed iterations
       cudaEventRecord(e0, 0);
-      if (mode < 2) {
-        cudaError_t e = tb::gemm_bf16(A, B, D, nullptr, M, N, K, lda, ldb, N, a_mn, b_mn, false, false, mode + 1, num_sms, 0);
+      if (mode != 2) {
+        cudaError_t e = tb::gemm_bf16(A, B, D, nullptr, M, N, K, lda, ldb, N, a_mn, b_mn, false, false,
+                                      mode == 0 ? 1 : 2, num_sms, 0);
         if (e != cudaSuccess) { printf("launch failed %s\n", cudaGetErrorString(e)); exit(2); }
       } else {
         // row-major D[M,N] = A_op B_op^T  <=> column-major D^T[N,M] = B_op(cm) * A_op(cm)
@@ -137,10 +140,11 @@ static void perf_case(cublasHandle_t h, const char* name, int M, int N, int K, i
       cudaEventElapsedTime(&ms, e0, e1);
       if (i >= 3) { total += ms; if (ms < best) best = ms; }
     }
-    const char* mn = mode == 0 ? "tb cluster1" : mode == 1 ? "tb cluster2" : "cuBLAS     ";
+    const char* mn = mode == 0 ? "tb cluster1" : mode == 1 ? "tb cl2 dyn " : mode == 2 ? "cuBLAS     " : "tb cl2 stat";
     printf("  %-10s %s M=%d N=%d K=%d : best %.3f ms (%.1f TFLOP/s)  mean %.3f ms (%.1f TFLOP/s)\n", name, mn, M, N, K,
            best, flops / best * 1e-9, total / iters, flops / (total / iters) * 1e-9);
   }
+  tb::gemm_sched_mode(1);
   cudaFree(A); cudaFree(B); cudaFree(D); cudaFree(flush);
 }
 

@@ -23,6 +23,7 @@ _SIGS = {
     "tb_abi_version": ([], i32),
     "tb_device_info": ([i32, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i64)], i32),
     "tb_gemm_bf16": ([u64, u64, u64, u64, i32, i32, i32, i64, i64, i64, i32, i32, i32, i32, i32, i32, u64], i32),
+    "tb_gemm_sched_mode": ([i32], i32),
     "tb_gemm_bf16_ex": ([u64, u64, u64, u64, u64, i32, i32, i32, i64, i64, i64, i64, i32, i32, i32, i32, i32, u64], i32),
     "tb_rmsnorm_fwd": ([u64, u64, u64, u64, u64, u64, i32, i32, f32, i32, u64], i32),
     "tb_rmsnorm_bwd": ([u64, u64, u64, u64, u64, u64, u64, i32, i32, i32, i32, u64], i32),
@@ -135,6 +136,17 @@ def num_sms() -> int:
 
 def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def set_gemm_scheduler(dynamic: bool) -> None:
+    """Tile scheduling of the tcgen05 GEMM: static striping (fastest when the GEMM owns the GPU) or dynamic
+    cluster-launch-control claiming (robust when collective kernels occupy some SMs on side streams).  The env
+    var ``TORCHACC_B200_GEMM_SCHED=static|dynamic`` pins the mode."""
+    if os.environ.get("TORCHACC_B200_GEMM_SCHED", "auto") not in ("auto", ""):
+        return
+    L = lib()
+    if L is not None and hasattr(L, "tb_gemm_sched_mode"):
+        L.tb_gemm_sched_mode(1 if dynamic else 0)
 
 
 def ptr(t: Optional[torch.Tensor]) -> int:

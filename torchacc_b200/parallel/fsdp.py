@@ -466,6 +466,11 @@ class ShardingEngine:
         self.grad_pool = _BufferPool(device, depth=2, allocator=(self.shard_coll.alloc if symm_grad else None))
         self._empty = torch.empty(0, dtype=compute_dtype, device=device)
         cuda = device.type == "cuda"
+        if cuda and self.world_data > 1:
+            # collectives will run on side streams next to the GEMMs: claim GEMM tiles dynamically so SMs that are
+            # busy with a collective CTA do not stall a whole GEMM (see csrc/gemm/gemm_bf16.cu, "tile iteration")
+            from .. import _native as nat
+            nat.set_gemm_scheduler(True)
         self.gather_stream = torch.cuda.Stream(device) if (cuda and self.shard_world > 1) else None
         self.reduce_stream = torch.cuda.Stream(device) if (cuda and self.world_data > 1) else None
         self.fwd_order: List[int] = []
