@@ -471,8 +471,8 @@ class ShardingEngine:
             # busy with a collective CTA do not stall a whole GEMM (see csrc/gemm/gemm_bf16.cu, "tile iteration")
             from .. import _native as nat
             nat.set_gemm_scheduler(True)
-        self.gather_stream = torch.cuda.Stream(device) if (cuda and self.shard_world > 1) else None
-        self.reduce_stream = torch.cuda.Stream(device) if (cuda and self.world_data > 1) else None
+        self.gather_stream = torch.cuda.Stream(device, priority=-1) if (cuda and self.shard_world > 1) else None
+        self.reduce_stream = torch.cuda.Stream(device, priority=-1) if (cuda and self.world_data > 1) else None
         self.fwd_order: List[int] = []
         self._fwd_recorded = False
         self._final_units: List[FlatParamUnit] = []
