@@ -246,14 +246,15 @@ struct CopyList {            // for each source rank r: copy `bytes` from src[r]
   uint8_t* dst[kMaxWorld];
 };
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(32)
 multi_copy_tma_kernel(const __grid_constant__ CopyList cl, const __grid_constant__ Pads pads, size_t bytes, int rank,
-                      int world, int ch, uint32_t epoch, uint32_t* block_counter) {
+                      int world, uint32_t kTmaChunk, uint32_t kTmaStages, int ch, uint32_t epoch,
+                      uint32_t* block_counter) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
   const uint32_t bar = base + kTmaStages * kTmaChunk;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTmaStages; ++s) mbar_init(bar + 8u * s, 1);
+    for (uint32_t s = 0; s < kTmaStages; ++s) mbar_init(bar + 8u * s, 1);
     fence_mbar_init();
   }
   barrier_enter(pads, rank, world, ch, epoch);   // (ends with __syncthreads)
@@ -283,7 +284,7 @@ multi_copy_tma_kernel(const __grid_constant__ CopyList cl, const __grid_constant
       bulk_load(base + st * kTmaChunk, sp, len, bar + 8u * st);
     };
     uint32_t issued = 0;
-    for (; issued < (uint32_t)kTmaStages - 1 && issued < total; ++issued) issue(issued);
+    for (; issued < kTmaStages - 1 && issued < total; ++issued) issue(issued);
     for (uint32_t i = 0; i < total; ++i) {
       const uint32_t st = i % kTmaStages;
       mbar_wait(bar + 8u * st, (i / kTmaStages) & 1);
@@ -449,14 +450,34 @@ static int tma_min_bytes() {
   }();
   return v;
 }
-static int tma_ctas() {
-  static int v = [] {
-    const char* e = getenv("TORCHACC_B200_COMM_TMA_CTAS");
-    const int n = e ? atoi(e) : 16;
-    return n > 0 ? n : 16;
-  }();
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  const int n = e ? atoi(e) : dflt;
+  return n > 0 ? n : dflt;
+}
+// reduce-scatter: CTAs with a 192 KB staging ring (they own their SM; the GEMM's dynamic scheduler skips them)
+static int rs_ctas() {
+  static int v = env_int("TORCHACC_B200_COMM_RS_CTAS", 16);
   return v;
 }
+// copy kernels (all-gather / all-to-all): many one-warp CTAs with a SMALL ring (3 x 8 KB) that fits next to a GEMM
+// CTA (199 KB) on the same SM.  A CTA's bulk copies from peer memory do not pipeline deeper than ~32 KB, so
+// bandwidth comes from the number of SMs driving TMA, not from ring depth.  Measured at 2 GPUs
+// (profiles/overlap_geometry_n2_run27.txt): 120 x (3 x 8 KB) -> 457 GB/s with the GEMM 1.08x slower;
+// 16 x (6 x 32 KB) -> 336 GB/s / 1.10x; 32 x (6 x 32 KB) -> 425 GB/s / 1.24x.
+static int tma_ctas() {
+  static int v = env_int("TORCHACC_B200_COMM_TMA_CTAS", 120);
+  return v;
+}
+static uint32_t copy_chunk() {
+  static int v = env_int("TORCHACC_B200_COMM_TMA_CHUNK", 8192) & ~15;
+  return (uint32_t)v;
+}
+static uint32_t copy_stages() {
+  static int v = env_int("TORCHACC_B200_COMM_TMA_STAGES", 3);
+  return (uint32_t)(v < 2 ? 2 : v);
+}
+static int copy_smem() { return (int)(copy_chunk() * copy_stages()) + 128 + 256; }
 template <typename K>
 static cudaError_t allow_smem(K kernel, int bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -477,16 +498,17 @@ cudaError_t symm_all_gather(const uint64_t* peer_ptrs, const uint64_t* pad_ptrs,
   configure_kernels_once();
   fill(p, q, peer_ptrs, pad_ptrs, world, src_off_bytes);
   if (tma_min_bytes() > 0 && bytes >= (size_t)tma_min_bytes()) {
-    static cudaError_t cfg = allow_smem(multi_copy_tma_kernel, kTmaSmem);
+    static cudaError_t cfg = allow_smem(multi_copy_tma_kernel, copy_smem());
     if (cfg != cudaSuccess) return cfg;
     CopyList cl;
     for (int r = 0; r < kMaxWorld; ++r) {
       cl.src[r] = r < world ? (const uint8_t*)p.ptr[r] : nullptr;
       cl.dst[r] = r < world ? (uint8_t*)out + (size_t)r * bytes : nullptr;
     }
-    const size_t chunks = (bytes + kTmaChunk - 1) / kTmaChunk;
+    const size_t chunks = (bytes + copy_chunk() - 1) / copy_chunk();
     const int grid = (int)(chunks < (size_t)tma_ctas() ? chunks : (size_t)tma_ctas());
-    multi_copy_tma_kernel<<<grid, 128, kTmaSmem, stream>>>(cl, q, bytes, rank, world, channel, epoch, block_counter);
+    multi_copy_tma_kernel<<<grid, 32, copy_smem(), stream>>>(cl, q, bytes, rank, world, copy_chunk(), copy_stages(),
+                                                             channel, epoch, block_counter);
     return cudaGetLastError();
   }
   all_gather_kernel<<<grid_for(bytes * world, num_sms), 512, 0, stream>>>(p, q, (uint8_t*)out, bytes, rank, world,
@@ -508,7 +530,7 @@ cudaError_t symm_reduce_scatter(const uint64_t* peer_ptrs, const uint64_t* pad_p
     const int stages = kTmaStages;
     const int smem = stages * (int)sub * world + 1024 + 256;
     const size_t chunks = (slice_bytes + sub - 1) / sub;
-    const int grid = (int)(chunks < (size_t)tma_ctas() ? chunks : (size_t)tma_ctas());
+    const int grid = (int)(chunks < (size_t)rs_ctas() ? chunks : (size_t)rs_ctas());
 #define TB_RS_TMA(IN, OUT)                                                                                         \
   do {                                                                                                             \
     static cudaError_t cfg = allow_smem(reduce_scatter_tma_kernel<IN, OUT>, kTmaSmem);                             \
@@ -543,17 +565,17 @@ cudaError_t symm_all_to_all(const uint64_t* peer_ptrs, const uint64_t* pad_ptrs,
   configure_kernels_once();
   fill(p, q, peer_ptrs, pad_ptrs, world, src_off_bytes);
   if (tma_min_bytes() > 0 && chunk_bytes >= (size_t)tma_min_bytes()) {
-    static cudaError_t cfg = allow_smem(multi_copy_tma_kernel, kTmaSmem);
+    static cudaError_t cfg = allow_smem(multi_copy_tma_kernel, copy_smem());
     if (cfg != cudaSuccess) return cfg;
     CopyList cl;
     for (int r = 0; r < kMaxWorld; ++r) {
       cl.src[r] = r < world ? (const uint8_t*)p.ptr[r] + (size_t)rank * chunk_bytes : nullptr;
       cl.dst[r] = r < world ? (uint8_t*)out + (size_t)r * chunk_bytes : nullptr;
     }
-    const size_t chunks = (chunk_bytes + kTmaChunk - 1) / kTmaChunk;
+    const size_t chunks = (chunk_bytes + copy_chunk() - 1) / copy_chunk();
     const int grid = (int)(chunks < (size_t)tma_ctas() ? chunks : (size_t)tma_ctas());
-    multi_copy_tma_kernel<<<grid, 128, kTmaSmem, stream>>>(cl, q, chunk_bytes, rank, world, channel, epoch,
-                                                          block_counter);
+    multi_copy_tma_kernel<<<grid, 32, copy_smem(), stream>>>(cl, q, chunk_bytes, rank, world, copy_chunk(),
+                                                             copy_stages(), channel, epoch, block_counter);
     return cudaGetLastError();
   }
   all_to_all_kernel<<<grid_for(chunk_bytes * world, num_sms), 512, 0, stream>>>(p, q, (uint8_t*)out, chunk_bytes, rank,

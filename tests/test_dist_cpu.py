@@ -82,7 +82,7 @@ def test_default_config_is_data_parallel():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def _fsdp_worker(rank, world, hybrid, sp=1):
+def _fsdp_worker(rank, world, hybrid, sp=1, check=None):
     import torchacc_b200 as ta
     ids = _data()
     model = _tiny()
@@ -113,6 +113,8 @@ def _fsdp_worker(rank, world, hybrid, sp=1):
     full = model._inner_engine_module().full_state_dict(rank0_only=False)
     for n, p in ref.named_parameters():
         assert torch.allclose(full[n], p.detach(), atol=1e-4, rtol=1e-3), (n, float((full[n] - p).abs().max()))
+    if check is not None:
+        check(model.engine)
 
 
 def test_fsdp_matches_single_process():
@@ -121,6 +123,22 @@ def test_fsdp_matches_single_process():
 
 def test_hsdp_matches_single_process():
     run_distributed(_fsdp_worker, 4, args=(True,))
+
+
+def _fsdp_windows_worker(rank, world):
+    os.environ["TORCHACC_B200_COMM_WINDOWS"] = "force"
+
+    def check(eng):
+        # 2 layers x 3 steps: forward windows start the next layer's gather, recomputation windows start the previous
+        # layer's gather and the reduce-scatter of the layer that just finished its backward
+        assert eng.stats.get("window_gathers", 0) >= 3 and eng.stats.get("window_reduces", 0) >= 3, eng.stats
+    _fsdp_worker(rank, world, False, check=check)
+
+
+def test_fsdp_deferred_collectives_match_single_process():
+    """Communication windows: prefetch all-gathers / gradient reduce-scatters are deferred to the MLP of the running
+    (or recomputed) layer; parameters after 3 SGD steps must still equal the single-process run."""
+    run_distributed(_fsdp_windows_worker, 2)
 
 
 def test_fsdp_with_context_parallel_matches_single_process():

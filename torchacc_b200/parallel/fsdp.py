@@ -295,6 +295,12 @@ class FlatParamUnit:
         """Turn this unit's flat gradient buffer into the optimizer-visible gradient shard:
         single device -> the buffer itself; otherwise reduce-scatter over the shard group with fp32 accumulation
         (+ all-reduce over replicas for HSDP / DP), overlapped with the rest of backward on the reduce stream."""
+        if self.stage_reduce():
+            self.launch_reduce()
+
+    def stage_reduce(self) -> bool:
+        """First half of ``reduce_grads``: finish the flat buffer on the compute stream and record the event the
+        collective has to wait for.  Returns False when there is nothing to communicate (single device)."""
         eng = self.engine
         self.collect_autograd_grads()
         fp = self.flat_param
@@ -308,36 +314,44 @@ class FlatParamUnit:
                 else:
                     fp.grad.add_(self.grad_full)
             self.grad_full = None
-            return
+            return False
+        self._reduce_ready = None
+        if eng.device.type == "cuda":
+            self._reduce_ready = torch.cuda.Event()
+            self._reduce_ready.record()
+        self._reduce_src, self.grad_full = self.grad_full, None
+        return True
+
+    def launch_reduce(self) -> None:
+        """Second half: the collective itself, on the reduce stream (may run long after ``stage_reduce``)."""
+        eng = self.engine
+        fp = self.flat_param
+        src, self._reduce_src = self._reduce_src, None
         first = not self.grad_accumulated
         if getattr(self, "_grad_shard", None) is None:
             self._grad_shard = torch.empty(self.shard_numel, dtype=eng.grad_shard_dtype, device=eng.device)
         out = self._grad_shard if first else torch.empty_like(self._grad_shard)
-        done = None
-        if eng.device.type == "cuda":
-            done = torch.cuda.Event()
-            done.record()
         scale = 1.0 / eng.world_data
-        with eng.on_reduce_stream(done):
+        with eng.on_reduce_stream(self._reduce_ready):
             if eng.shard_world > 1:
-                eng.shard_coll.reduce_scatter(self.grad_full, out, scale)
+                eng.shard_coll.reduce_scatter(src, out, scale)
             else:
-                out.copy_(self.grad_full)
+                out.copy_(src)
                 out.mul_(scale)
             if eng.replica_world > 1:
                 eng.replica_coll.all_reduce(out)
             if not first:
                 self._grad_shard.add_(out)
             if eng.device.type == "cuda":
-                eng.grad_pool.release(self.grad_full, torch.cuda.current_stream())
+                eng.grad_pool.release(src, torch.cuda.current_stream())
                 out.record_stream(torch.cuda.current_stream())
             eng.note_reduce_done()
+        self._reduce_ready = None
         self.grad_accumulated = True
         if eng.grad_mode == "fused" or self._grad_shard.dtype != fp.dtype:
             fp._tb_grad = self._grad_shard
         else:
             fp.grad = self._grad_shard
-        self.grad_full = None
 
 
 class _PostBackward(torch.autograd.Function):
@@ -354,6 +368,15 @@ class _PostBackward(torch.autograd.Function):
         return (None, *grads)
 
 
+def _find_window_module(module: nn.Module) -> Optional[nn.Module]:
+    """The sub-module of a transformer block whose start marks the "GEMM-only" part of the layer (the MLP)."""
+    for name in ("mlp", "feed_forward", "ffn", "block_sparse_moe"):
+        m = getattr(module, name, None)
+        if isinstance(m, nn.Module):
+            return m
+    return None
+
+
 class ShardedUnit(nn.Module):
     """Wrapper installed in place of each unit module: gather -> (checkpointed) forward -> reshard, plus the
     autograd hooks that drive backward prefetch and gradient reduction."""
@@ -364,6 +387,15 @@ class ShardedUnit(nn.Module):
         self.module = module
         self.__dict__["_unit"] = unit
         self.use_gc = use_gc
+        unit.recomputes = bool(use_gc)
+        unit.window_module = None
+        if engine.comm_windows:
+            win = _find_window_module(module)
+            if win is not None:
+                # fires in the forward AND in the checkpoint recomputation: the point after attention, where only
+                # GEMM-bound work (MLP) follows -- the engine starts deferred collectives here (see comm_window)
+                win.register_forward_pre_hook(lambda _m, _a, _e=engine, _u=unit: _e.comm_window(_u))
+                unit.window_module = win
 
     @property
     def unit(self) -> FlatParamUnit:
@@ -471,6 +503,16 @@ class ShardingEngine:
             # busy with a collective CTA do not stall a whole GEMM (see csrc/gemm/gemm_bf16.cu, "tile iteration")
             from .. import _native as nat
             nat.set_gemm_scheduler(True)
+        # communication windows: on a GPU the flash-attention CTAs need whole SMs (224 KB smem) and small GEMMs are
+        # the most sensitive to a concurrent collective, so prefetch all-gathers and gradient reduce-scatters are
+        # not started at unit boundaries but at the next "window" = the start of an MLP, where ~2-5 ms of large GEMMs
+        # follow (measured: profiles/step_timeline_n8_run26.txt).  TORCHACC_B200_COMM_WINDOWS=0 restores the old timing.
+        import os as _os
+        _cw = _os.environ.get("TORCHACC_B200_COMM_WINDOWS", "1")           # "0" off, "force" also on CPU (tests)
+        self.comm_windows = bool(self.world_data > 1 and (_cw == "force" or (cuda and _cw != "0")))
+        self._deferred_prefetch: Optional[FlatParamUnit] = None
+        self._deferred_reduces: List[FlatParamUnit] = []
+        self._bwd_unit: Optional[FlatParamUnit] = None
         self.gather_stream = torch.cuda.Stream(device, priority=-1) if (cuda and self.shard_world > 1) else None
         self.reduce_stream = torch.cuda.Stream(device, priority=-1) if (cuda and self.world_data > 1) else None
         self.fwd_order: List[int] = []
@@ -545,7 +587,27 @@ class ShardingEngine:
         for k in range(1, self.prefetch + 1):
             nxt = self._neighbor(unit, k)
             if nxt is not None:
-                nxt.gather(prefetch=True)
+                if k == 1 and self.comm_windows and getattr(unit, "window_module", None) is not None:
+                    self._deferred_prefetch = nxt          # started by comm_window(unit)
+                else:
+                    nxt.gather(prefetch=True)
+
+    def comm_window(self, unit: FlatParamUnit):
+        """Start the collectives that were deferred to this unit's GEMM-only phase."""
+        if self._deferred_reduces:
+            pending, self._deferred_reduces = self._deferred_reduces, []
+            for u in pending:
+                u.launch_reduce()
+            if unit is not None:
+                self.stats["window_reduces"] = self.stats.get("window_reduces", 0) + len(pending)
+        nxt, self._deferred_prefetch = self._deferred_prefetch, None
+        if nxt is not None:
+            nxt.gather(prefetch=True)
+            if unit is not None:
+                self.stats["window_gathers"] = self.stats.get("window_gathers", 0) + 1
+
+    def flush_deferred(self):
+        self.comm_window(None)
 
     def post_forward(self, unit: FlatParamUnit):
         if self.reshard and unit is not self.root_unit and not self._is_last_forward_unit(unit):
@@ -558,19 +620,35 @@ class ShardingEngine:
     def pre_backward(self, unit: FlatParamUnit):
         if not self._fwd_recorded and self.fwd_order:
             self._fwd_recorded = True
+        if self._deferred_prefetch is not None:      # a forward window never came (e.g. last forward unit)
+            nxt, self._deferred_prefetch = self._deferred_prefetch, None
+            if nxt is not unit:
+                nxt.gather(prefetch=True)
         unit.gather()
         unit.wait_gather()
         unit.prepare_grad_buffer()
+        # with activation checkpointing the unit's forward is recomputed now and its window hook fires again
+        windowed = self.comm_windows and getattr(unit, "window_module", None) is not None and \
+            getattr(unit, "recomputes", False)
+        if not windowed and self._deferred_reduces:
+            self.flush_deferred()
         for k in range(1, self.prefetch + 1):
             prv = self._neighbor(unit, -k)
             if prv is not None:
-                prv.gather(prefetch=True)
+                if k == 1 and windowed:
+                    self._deferred_prefetch = prv
+                else:
+                    prv.gather(prefetch=True)
         self._queue_final_callback()
 
     def post_backward(self, unit: FlatParamUnit):
         if unit.grad_full is None:
             unit.prepare_grad_buffer()
-        unit.reduce_grads()
+        if self.comm_windows:
+            if unit.stage_reduce():                  # collect + "gradients complete" event now, collective later
+                self._deferred_reduces.append(unit)
+        else:
+            unit.reduce_grads()
         if self.reshard:
             unit.reshard()
 
@@ -586,6 +664,7 @@ class ShardingEngine:
 
     def _final_callback(self):
         self._callback_queued = False
+        self.flush_deferred()
         for unit in self._final_units:
             # units whose inputs carry no gradient (embedding/root): reduce now, after the whole backward.
             # The list persists across backward passes (1F1B runs several forwards before the first backward).
