@@ -332,6 +332,11 @@ class FlatParamUnit:
             self._grad_shard = torch.empty(self.shard_numel, dtype=eng.grad_shard_dtype, device=eng.device)
         out = self._grad_shard if first else torch.empty_like(self._grad_shard)
         scale = 1.0 / eng.world_data
+        if eng.device.type == "cuda":
+            # start no earlier than the point the compute stream has reached NOW (the communication window this is
+            # launched from), not merely when the gradients were complete: the host runs far ahead of the device
+            self._reduce_ready = torch.cuda.Event()
+            self._reduce_ready.record()
         with eng.on_reduce_stream(self._reduce_ready):
             if eng.shard_world > 1:
                 eng.shard_coll.reduce_scatter(src, out, scale)
