@@ -12,7 +12,8 @@ import gzip
 import json
 from collections import defaultdict
 
-COMM = ("all_gather_kernel", "reduce_scatter_kernel", "all_to_all_kernel", "nccl", "rs_reduce")
+COMM = ("all_gather_kernel", "reduce_scatter_kernel", "all_to_all_kernel", "multi_copy_tma_kernel",
+        "reduce_scatter_tma_kernel", "nccl", "rs_reduce")
 
 
 def family(name: str) -> str:
@@ -20,7 +21,8 @@ def family(name: str) -> str:
     for key, fam in (("gemm_bf16_kernel", "gemm (tcgen05)"), ("flash_fwd", "attention fwd"), ("flash_bwd", "attention bwd"),
                      ("attn_bwd_pre", "attention bwd pre/post"), ("convert", "attention bwd pre/post"),
                      ("adamw", "adamw"), ("rmsnorm", "rmsnorm"), ("rope", "rope"), ("swiglu", "swiglu"),
-                     ("cross_entropy", "cross-entropy"), ("sqnorm", "grad-norm"), ("all_gather_kernel", "symm all-gather"),
+                     ("cross_entropy", "cross-entropy"), ("sqnorm", "grad-norm"), ("multi_copy_tma_kernel", "symm all-gather / all-to-all (TMA)"),
+                     ("reduce_scatter_tma_kernel", "symm reduce-scatter (TMA)"), ("all_gather_kernel", "symm all-gather"),
                      ("reduce_scatter_kernel", "symm reduce-scatter"), ("all_to_all_kernel", "symm all-to-all"),
                      ("nccl", "nccl"), ("Memcpy", "memcpy"), ("Memset", "memset")):
         if key in n:
