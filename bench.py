@@ -302,7 +302,17 @@ def run_reference(a):
         model = ref_ta.accelerate(model, config=cfg)
         opt = torch.optim.AdamW(model.parameters(), lr=1e-5, betas=(0.9, 0.95), weight_decay=0.1, fused=True)
     except Exception as e:  # noqa: BLE001
-        unavailable(f"setup failed: {type(e).__name__}: {e}"[:300])
+        msg = f"setup failed: {type(e).__name__}: {e}"
+        if world > 1 and "should be lazy" in str(e):
+            # stock behaviour of the unmodified reference without torch_xla: accelerate() initialises the 'nccl'
+            # process group for the eager backend (torchacc/dist/__init__.py:45-51) and Config.get_mesh() then
+            # insists on the XLA 'lazy' backend (torchacc/config.py:396-398) -> no multi-rank eager run is possible
+            msg = ("reference eager backend cannot run on >1 rank: Config.get_mesh() asserts the XLA 'lazy' "
+                   "process-group backend (torchacc/config.py:396-398) after accelerate() initialised 'nccl' "
+                   "(dist/__init__.py:45-51); the lazy backend needs torch_xla, which cannot be installed offline")
+        if world > 1 and dist.is_initialized():
+            dist.destroy_process_group()
+        unavailable(msg[:400])
 
     g = torch.Generator().manual_seed(rank)
     host = torch.randint(0, 128256, (a.mbs, a.seq_len), generator=g).pin_memory()
