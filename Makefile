@@ -22,4 +22,12 @@ bench: build
 sass:
 	cuobjdump -sass torchacc_b200/_C.so | grep -oE "UTC[A-Z0-9.]*MMA[A-Z0-9.]*|UTMA[A-Z0-9.]*|LDTM[A-Z0-9.]*|STTM[A-Z0-9.]*|UTMARED[A-Z0-9.]*" | sort | uniq -c
 
-.PHONY: build test test-gpu test-multigpu smoke bench sass
+# compute-sanitizer over the hand-written kernels (the reference has no sanitizer hooks at all):
+# memcheck + synccheck on the stand-alone GEMM harness (every descriptor / TMA / TMEM path, static and dynamic tile
+# scheduling) and memcheck on the op-level numerics tests.
+sanitize: build
+	compute-sanitizer --tool memcheck --error-exitcode 1 build/gemm_test 3 0 1
+	compute-sanitizer --tool synccheck --error-exitcode 1 build/gemm_test 2 0 1
+	compute-sanitizer --tool memcheck --error-exitcode 1 $(PY) -m pytest tests/test_ops_gpu.py -q -m gpu -k "rmsnorm or swiglu or rope or cross_entropy or adamw"
+
+.PHONY: build test test-gpu test-multigpu smoke bench sass sanitize
