@@ -58,6 +58,10 @@ def accelerate(model: nn.Module, dataloader=None, config: Optional[Config] = Non
                              num_buckets=dl.num_buckets, pad_value_dict=dl.pad_value_dict, prefetch=dl.prefetch,
                              pin_memory=dl.pin_memory)
 
+    if getattr(config.compute, "fp8", False):
+        from .utils.logger import logger
+        logger.warning("compute.fp8: the block-scaled fp8 tcgen05 GEMM is not available in this build; linear layers "
+                       "run the bf16 tcgen05 GEMM")
     if config.compute.acc_scaled_dot_attn:
         from .ops.sdpa import patch_sdpa
         patch_sdpa()

@@ -11,9 +11,13 @@ dist/dp.py:20-89 (torch DDP).  This is our own runtime, not a wrapper:
 * gradients: the wgrad GEMM epilogue writes straight into the unit's flat bf16 gradient buffer
   (``ops.linear`` + ``_tb_grad_view``); after the unit's backward the buffer is reduce-scattered with fp32
   accumulation into the fp32 gradient shard (bf16 on the wire, half the reference's fp32 reduce traffic);
-* schedule: all-gathers are prefetched one unit ahead on a communication stream, reduce-scatters run on a second
-  stream behind the backward; gather / gradient buffers come from small rotating pools so memory stays at
-  ``2 units`` regardless of depth (sized for 180 GB HBM: Llama-3-8B on one GPU keeps everything resident);
+* schedule: all-gathers are prefetched one unit ahead on a high-priority communication stream, reduce-scatters run
+  on a second one behind the backward; on a GPU both are *queued* at unit boundaries and *started* at the next
+  communication window (the MLP of the running / recomputed layer, ``ShardingEngine.comm_window``) so they overlap
+  large GEMMs instead of flash-attention and the small projections; the tcgen05 GEMM switches to dynamic
+  (cluster-launch-control) tile claiming while collectives share the GPU.  Gather / gradient buffers come from small
+  rotating pools so memory stays at ``2 units`` regardless of depth (sized for 180 GB HBM: Llama-3-8B on one GPU keeps
+  everything resident);
 * strategies: ``FULL_SHARD`` (fsdp), ``HYBRID`` (fsdp x dp replicas), ``NO_SHARD`` (pure DP: units act as
   gradient all-reduce buckets overlapped with backward -- this is the DataParallel engine);
 * gradient checkpointing (``gc``) happens INSIDE the unit, so recomputation reuses the gathered parameters
