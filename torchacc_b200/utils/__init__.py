@@ -1,5 +1,8 @@
 """Utilities (reference torchacc/utils/)."""
-from . import checkpoint, cpu_offload, decompose, import_utils, logger as _logger_mod, patch, trace, utils
+from . import checkpoint, cpu_offload, decompose, import_utils, logger as _logger_mod, metrics, patch, trace, utils
 from .logger import logger
 
-__all__ = ["checkpoint", "cpu_offload", "decompose", "import_utils", "logger", "patch", "trace", "utils"]
+from .metrics import ThroughputMeter, memory_stats
+
+__all__ = ["checkpoint", "cpu_offload", "decompose", "import_utils", "logger", "metrics", "patch", "trace", "utils",
+           "ThroughputMeter", "memory_stats"]
