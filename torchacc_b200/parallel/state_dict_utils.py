@@ -249,6 +249,52 @@ def save_checkpoints(state_dicts: List[Dict[str, Any]], shard_metadatas: List[Di
         list(ex.map(write, zip(state_dicts, shard_metadatas, save_paths)))
 
 
+def _engine_module(model):
+    return model._inner_engine_module() if hasattr(model, "_inner_engine_module") else model
+
+
+def save_sharded_checkpoint(model, optimizer=None, ckpt_dir: str = ".", extra: Optional[Dict[str, Any]] = None) -> None:
+    """The reference's documented FSDP recipe (docs/source/dist/fsdp.md:126-156) as one call: every rank writes
+    ``rank{R}-of-{W}-model.pth`` (its fp32 flat shards + ``shard_metadata``) and, with an optimizer,
+    ``rank{R}-of-{W}-optimizer.pth``; ``extra`` (step counter, LR-scheduler state, ...) goes into the model file.
+    The files are what ``consolidate_and_reshard_fsdp_ckpts`` consumes."""
+    m = _engine_module(model)
+    meta = m.get_shard_metadata()
+    r, w = meta["rank"], meta["world_size"]
+    os.makedirs(ckpt_dir, exist_ok=True)
+    payload = {"model": {k: v.detach().cpu() for k, v in m.sharded_state_dict().items()}, "shard_metadata": meta}
+    if extra:
+        payload["extra"] = extra
+    torch.save(payload, os.path.join(ckpt_dir, f"rank{r}-of-{w}-model.pth"))
+    if optimizer is not None:
+        torch.save(m.sharded_optim_state_dict(optimizer),          # {'optimizer': state_dict, 'shard_metadata': meta}
+                   os.path.join(ckpt_dir, f"rank{r}-of-{w}-optimizer.pth"))
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+
+
+def load_sharded_checkpoint(model, optimizer=None, ckpt_dir: str = ".") -> Dict[str, Any]:
+    """Resume from ``save_sharded_checkpoint`` files written by the SAME world size (use the consolidate / reshard
+    CLI for a different one; a mismatch raises like the reference, dist/fsdp.py:518-526).  Returns ``extra``."""
+    m = _engine_module(model)
+    meta = m.get_shard_metadata()
+    r, w = meta["rank"], meta["world_size"]
+    path = os.path.join(ckpt_dir, f"rank{r}-of-{w}-model.pth")
+    if not os.path.exists(path):
+        found = sorted(glob.glob(os.path.join(ckpt_dir, "rank*-of-*-model.pth")))
+        raise FileNotFoundError(f"{path} not found (checkpoint world size differs? files: {found[:4]}); "
+                                "reshard with `python -m torchacc_b200.utils.consolidate_and_reshard_ckpts`")
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    if ck["shard_metadata"]["world_size"] != w:
+        raise ValueError(f"checkpoint was written by {ck['shard_metadata']['world_size']} ranks, this job has {w}")
+    m.load_sharded_state_dict(ck["model"])
+    if optimizer is not None:
+        opath = os.path.join(ckpt_dir, f"rank{r}-of-{w}-optimizer.pth")
+        osd = torch.load(opath, map_location="cpu", weights_only=False)["optimizer"]
+        optimizer.load_state_dict(osd)
+    return ck.get("extra", {})
+
+
 def consolidate_sharded_model_checkpoints(ckpts: List[Dict[str, Any]]) -> "OrderedDict[str, torch.Tensor]":
     meta = ckpts[0]["shard_metadata"]
     out = OrderedDict()
