@@ -166,6 +166,16 @@ class Mesh:
                 g = dist.new_group(ranks=ranks)
                 if self.global_rank in ranks:
                     self._groups[name] = g
+        # second, independent communicator along the pp axis for gradients flowing backwards.  NCCL executes the p2p
+        # operations between two ranks of ONE communicator in issue order; with early-posted receives a stage's
+        # pending irecv(activation i+1) would sit in front of its isend(grad i) while the neighbour's
+        # isend(activation i+1) sits behind its irecv(grad i) -- a cyclic wait (observed: 2-stage 1F1B hang on GPUs).
+        lists = self._rank_groups["pp"]
+        if len(lists[0]) > 1:
+            for ranks in lists:
+                g = dist.new_group(ranks=ranks)
+                if self.global_rank in ranks:
+                    self._groups["pp_bwd"] = g
 
     def _my_ranks(self, name: str) -> List[int]:
         for ranks in self._rank_groups[name]:
@@ -198,6 +208,7 @@ class Mesh:
     def get_pp_rank(self): return self.coord["pp"]
     def get_pp_num(self): return self.sizes["pp"]
     def get_pp_proc_group(self): return self.get_proc_group("pp")
+    def get_pp_bwd_proc_group(self): return self.get_proc_group("pp_bwd") or self.get_proc_group("pp")
     def get_pp_rank_groups(self): return self._rank_groups["pp"]
     def get_stage_id(self): return self.coord["pp"]
     def is_first_stage(self): return self.coord["pp"] == 0

@@ -1,9 +1,10 @@
 """Point-to-point transport between adjacent pipeline stages (reference torchacc/dist/pp/p2p.py:7-37 and the
 metadata handshake of pp/executor.py:475-570).
 
-* asynchronous ``isend`` / ``irecv`` on the pipeline process group; receives are *posted early* and waited for
-  right before use, so transfers overlap the neighbouring micro-batch's compute (the reference blocks on every
-  ``dist.send/recv``);
+* asynchronous ``isend`` / ``irecv``; receives are *posted early* and waited for right before use, so transfers
+  overlap the neighbouring micro-batch's compute (the reference blocks on every ``dist.send/recv``).  Activations and
+  gradients use two separate process groups: NCCL runs the p2p operations of one communicator in issue order, so an
+  early-posted receive in one direction must never queue in front of a send in the other;
 * tensor metadata (dtype, shape, requires_grad) travels ONCE per shape epoch as a single fixed-size int64 header
   -- one host sync per epoch on the receiver instead of five ``.item()`` syncs per tensor (executor.py:528-561).
 """
@@ -57,7 +58,9 @@ class StageLink:
 
     def __init__(self, mesh, device: torch.device):
         self.mesh, self.device = mesh, device
-        self.group = mesh.get_pp_proc_group()
+        self.group = mesh.get_pp_proc_group()                  # activations (and their headers): stage i -> i+1
+        self.bwd_group = mesh.get_pp_bwd_proc_group() if hasattr(mesh, "get_pp_bwd_proc_group") else self.group
+        # gradients travel on their own communicator (see Mesh._create_groups: NCCL p2p ordering)
         self.stage, self.stages = mesh.get_stage_id(), mesh.get_pp_num()
         self.prev = mesh.stage_to_global(self.stage - 1) if self.stage > 0 else None
         self.next = mesh.stage_to_global(self.stage + 1) if self.stage < self.stages - 1 else None
@@ -97,7 +100,7 @@ class StageLink:
                 continue
             if g is None:
                 g = torch.zeros_like(t)
-            works.append(dist.isend(g.contiguous(), self.prev, group=self.group))
+            works.append(dist.isend(g.contiguous(), self.prev, group=self.bwd_group))
         self._pending += works
 
     def post_recv_grads(self) -> Tuple[List[Optional[torch.Tensor]], List]:
@@ -105,7 +108,7 @@ class StageLink:
         for m in self.sent_meta:
             if m.requires_grad:
                 b = torch.empty(m.shape, dtype=m.dtype, device=self.device)
-                works.append(dist.irecv(b, self.next, group=self.group))
+                works.append(dist.irecv(b, self.next, group=self.bwd_group))
                 bufs.append(b)
             else:
                 bufs.append(None)
