@@ -141,6 +141,24 @@ def test_fsdp_deferred_collectives_match_single_process():
     run_distributed(_fsdp_windows_worker, 2)
 
 
+def _fsdp_split_head_worker(rank, world):
+    os.environ["TORCHACC_B200_SPLIT_HEAD"] = "1"
+    os.environ["TORCHACC_B200_COMM_WINDOWS"] = "force"
+
+    def check(eng):
+        assert eng.head_unit is not None
+        names = sorted(i.fqn for i in eng.head_unit.infos)
+        assert names == ["lm_head.weight", "model.norm.weight"], names
+        assert all(i.fqn not in ("lm_head.weight", "model.norm.weight") for i in eng.root_unit.infos)
+    _fsdp_worker(rank, world, False, check=check)
+
+
+def test_fsdp_head_unit_split_matches_single_process():
+    """TORCHACC_B200_SPLIT_HEAD=1: final norm + lm_head form their own unit whose reduce-scatter starts after the first
+    layer's backward; parameters after 3 SGD steps equal the single-process run, checkpoints keep full names."""
+    run_distributed(_fsdp_split_head_worker, 2)
+
+
 def test_fsdp_with_context_parallel_matches_single_process():
     """fsdp=2 x sp=2: context-parallel peers replicate each parameter shard (HYBRID over the dp x sp group)."""
     run_distributed(_fsdp_worker, 4, args=(False, 2))

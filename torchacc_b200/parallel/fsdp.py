@@ -91,7 +91,7 @@ class FlatParamUnit:
     """All parameters of one wrapped module as a single flat, padded, sharded vector."""
 
     def __init__(self, engine: "ShardingEngine", module: nn.Module, prefix: str, index: int,
-                 exclude: Optional[Set[int]] = None):
+                 exclude: Optional[Set[int]] = None, include: Optional[Set[int]] = None):
         self.engine = engine
         self.module = module
         self.prefix = prefix
@@ -103,7 +103,7 @@ class FlatParamUnit:
         off = 0
         for mname, sub in module.named_modules():
             for pname, p in list(sub._parameters.items()):
-                if p is None or (exclude and id(p) in exclude):
+                if p is None or (exclude and id(p) in exclude) or (include is not None and id(p) not in include):
                     continue
                 if id(p) in seen:
                     self.shared.append((sub, pname, seen[id(p)]))
@@ -519,6 +519,12 @@ class ShardingEngine:
         import os as _os
         _cw = _os.environ.get("TORCHACC_B200_COMM_WINDOWS", "1")           # "0" off, "force" also on CPU (tests)
         self.comm_windows = bool(self.world_data > 1 and (_cw == "force" or (cuda and _cw != "0")))
+        # optional "head" unit (final norm + lm_head split off the root unit, TORCHACC_B200_SPLIT_HEAD=1): its
+        # gradients are complete right after the loss backward, so its reduce-scatter hides behind the whole
+        # backward pass instead of sitting exposed before the optimizer with the embedding's
+        self.split_head = _os.environ.get("TORCHACC_B200_SPLIT_HEAD", "0") == "1"
+        self.head_unit: Optional[FlatParamUnit] = None
+        self._head_staged = False
         self._deferred_prefetch: Optional[FlatParamUnit] = None
         self._deferred_reduces: List[FlatParamUnit] = []
         self._bwd_unit: Optional[FlatParamUnit] = None
@@ -591,6 +597,11 @@ class ShardingEngine:
             self.fwd_order.append(unit.index)
         unit.gather()
         unit.wait_gather()
+        if unit is self.root_unit and self.head_unit is not None:
+            self.head_unit.gather()
+            self.head_unit.wait_gather()
+            if torch.is_grad_enabled():
+                self.head_unit.prepare_grad_buffer()
         if unit is self.root_unit and torch.is_grad_enabled():
             unit.prepare_grad_buffer()   # the fused linear+CE writes lm_head's wgrad during the forward pass
         for k in range(1, self.prefetch + 1):
@@ -651,6 +662,16 @@ class ShardingEngine:
         self._queue_final_callback()
 
     def post_backward(self, unit: FlatParamUnit):
+        head = self.head_unit
+        if head is not None and not self._head_staged and head.grad_full is not None:
+            # the first wrapped unit has finished its backward: the loss / final-norm backward (and their
+            # AccumulateGrad nodes) ran long ago, the head's gradients are final
+            self._head_staged = True
+            if self.comm_windows:
+                if head.stage_reduce():
+                    self._deferred_reduces.append(head)
+            else:
+                head.reduce_grads()
         if unit.grad_full is None:
             unit.prepare_grad_buffer()
         if self.comm_windows:
@@ -673,6 +694,14 @@ class ShardingEngine:
 
     def _final_callback(self):
         self._callback_queued = False
+        head = self.head_unit
+        if head is not None:
+            if not self._head_staged and (head.grad_full is not None or
+                                          any(i.tensor.grad is not None for i in head.infos)):
+                if head.grad_full is None:
+                    head.prepare_grad_buffer()
+                head.reduce_grads()              # no wrapped unit ran a backward: reduce with the root
+            self._head_staged = False
         self.flush_deferred()
         for unit in self._final_units:
             # units whose inputs carry no gradient (embedding/root): reduce now, after the whole backward.
@@ -750,6 +779,41 @@ def _resolve_classes(model: nn.Module, names: Iterable[str]):
     return tuple(found.values())
 
 
+_HEAD_NAMES = ("lm_head", "norm", "ln_f", "final_layernorm", "final_norm")
+
+
+def _head_param_ids(model: nn.Module, claimed: Set[int]) -> Set[int]:
+    """Parameters of the modules that run AFTER the last wrapped unit (final norm, lm_head), found by name at the top
+    levels of the model (``model.lm_head``, ``model.model.norm``, ``model.transformer.ln_f`` ...).  A parameter that is
+    also used by another module (tied embeddings) stays in the root unit."""
+    cands: Dict[int, nn.Parameter] = {}
+    for holder in (model, getattr(model, "model", None), getattr(model, "transformer", None)):
+        if not isinstance(holder, nn.Module):
+            continue
+        for name in _HEAD_NAMES:
+            m = holder._modules.get(name)
+            if isinstance(m, nn.Module) and not isinstance(m, ShardedUnit):
+                for p in m.parameters():
+                    if id(p) not in claimed:
+                        cands[id(p)] = p
+    if not cands:
+        return set()
+    head_mods = set()
+    for holder in (model, getattr(model, "model", None), getattr(model, "transformer", None)):
+        if isinstance(holder, nn.Module):
+            for name in _HEAD_NAMES:
+                m = holder._modules.get(name)
+                if isinstance(m, nn.Module):
+                    head_mods |= {id(x) for x in m.modules()}
+    for sub in model.modules():
+        if id(sub) in head_mods:
+            continue
+        for p in sub._parameters.values():
+            if p is not None and id(p) in cands:
+                del cands[id(p)]                       # shared with a non-head module (e.g. tied embedding)
+    return set(cands)
+
+
 def shard_model(model: nn.Module, engine: ShardingEngine, wrap_classes: Sequence[type] = (),
                 gc_classes: Sequence[type] = (), gc_cnt: Optional[int] = None) -> nn.Module:
     """Wrap every instance of ``wrap_classes`` as its own unit and the remaining parameters as the root unit.
@@ -784,6 +848,14 @@ def shard_model(model: nn.Module, engine: ShardingEngine, wrap_classes: Sequence
     for b in model.buffers():
         if not b.is_meta:
             b.data = b.data.to(dev)
+    if engine.split_head and engine.world_data > 1:
+        head_ids = _head_param_ids(model, claimed)
+        if head_ids:
+            head = FlatParamUnit(engine, model, "", idx, exclude=claimed, include=head_ids)
+            idx += 1
+            engine.units.append(head)
+            engine.head_unit = head
+            claimed |= head.param_ids
     root_unit = FlatParamUnit(engine, model, "", idx, exclude=claimed)
     engine.units.append(root_unit)
     engine.root_unit = root_unit
