@@ -197,3 +197,10 @@ def create_scheduler(algo, training: bool, micro_batches: int, stages: int, stag
     if algo in (Algo.GPipe, "gpipe"):
         return GPipeTrain(micro_batches, stages, stage_id)
     raise ValueError(f"unknown pipeline schedule {algo!r}")
+
+
+# names used by the reference (torchacc/dist/pp/schedule.py:122-392) for code that imports them directly
+PipeDreamFlushTrain = OneFOneBTrain
+PipeDreamFlushInfer = ForwardOnly
+PipeInstruction = Instr
+BufferOpInstruction = Instr
