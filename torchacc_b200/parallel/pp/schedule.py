@@ -199,8 +199,6 @@ def create_scheduler(algo, training: bool, micro_batches: int, stages: int, stag
     raise ValueError(f"unknown pipeline schedule {algo!r}")
 
 
-# names used by the reference (torchacc/dist/pp/schedule.py:122-392) for code that imports them directly
-PipeDreamFlushTrain = OneFOneBTrain
-PipeDreamFlushInfer = ForwardOnly
+# instruction base-class names of the reference (torchacc/dist/pp/schedule.py:230,278)
 PipeInstruction = Instr
 BufferOpInstruction = Instr
