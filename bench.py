@@ -39,6 +39,8 @@ def parse():
     p.add_argument("--attn", default=None, help="attention backend override (native|sdpa)")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--trace", default=None, help="write a kernel timeline (chrome trace) of one extra, untimed step")
+    p.add_argument("--no-comm-trace", action="store_true",
+                   help="skip the extra profiled step that measures exposed communication when N > 1")
     return p.parse_args()
 
 
@@ -207,17 +209,28 @@ def run_ours(a):
                "h2d_bytes_per_step": int(2 * a.mbs * a.seq_len * 8), "d2h_bytes_per_step": 4,
                "last_loss": loss_val}
 
-    if a.trace:
-        # one extra step under the CUPTI-based torch profiler, AFTER every timed region (never part of a number);
-        # tools/trace_summary.py turns the trace into stream-utilisation / overlap tables for profiles/
-        from torch.profiler import ProfilerActivity, profile
-        torch.cuda.synchronize(device)
-        with profile(activities=[ProfilerActivity.CUDA]) as prof:
-            step()
+    comm = None
+    if a.trace or (world > 1 and not a.no_comm_trace):
+        # one extra step under the CUPTI-based torch profiler, AFTER every timed region (never part of a number):
+        # gives the exposed-communication figure of BASELINE.json's metric (communication-kernel time not hidden
+        # behind compute kernels, rank 0's timeline).  tools/trace_summary.py prints the full tables for profiles/.
+        try:
+            from torch.profiler import ProfilerActivity, profile
             torch.cuda.synchronize(device)
-        if rank == 0:
-            os.makedirs(os.path.dirname(os.path.abspath(a.trace)), exist_ok=True)
-            prof.export_chrome_trace(a.trace)
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                step()
+                torch.cuda.synchronize(device)
+            if rank == 0:
+                path = a.trace or os.path.join("/tmp", f"tb_bench_trace_{os.getpid()}.json")
+                os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+                prof.export_chrome_trace(path)
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                from trace_summary import comm_exposure
+                comm = {k: round(v, 3) for k, v in comm_exposure(path).items()}
+                if not a.trace:
+                    os.remove(path)
+        except Exception as e:  # noqa: BLE001  -- diagnostics must never break the benchmark line
+            comm = {"error": f"{type(e).__name__}: {e}"[:200]}
 
     if rank == 0:
         res = {
@@ -230,7 +243,7 @@ def run_ours(a):
                        "parallelism": f"fsdp{world}" + ("" if a.no_gc else "+gc"), "layers": mcfg.num_hidden_layers,
                        "optimizer": "FusedAdamW + clip_grad_norm(1.0)", "attention": ta.ops.get_attention_backend(),
                        "l2": "no explicit flush: each step streams >16 GB of weights/activations (>> 126 MB L2)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "comm": comm,
             "mfu_model_flops": mcfg.flops_per_token(a.seq_len) * value / world / 1e12,
             "loss": float(last["loss"]),
         }

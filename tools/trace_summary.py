@@ -65,6 +65,30 @@ def overlap(a_merged, b_merged):
     return tot
 
 
+def comm_exposure(trace_path: str) -> dict:
+    """{'step_ms', 'comm_busy_ms', 'comm_overlapped_ms', 'exposed_comm_ms'} of one traced step (bench.py uses this)."""
+    op = gzip.open if trace_path.endswith(".gz") else open
+    with op(trace_path, "rt") as f:
+        ev = json.load(f)["traceEvents"]
+    ks = [e for e in ev if e.get("ph") == "X" and e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
+    if not ks:
+        return {}
+    # the step proper starts with the first compute kernel (a collective may spin in its entry barrier before that
+    # while the slowest rank starts profiling)
+    comp = [(e["ts"], e["ts"] + e["dur"]) for e in ks if not any(c in e["name"] for c in COMM)]
+    comm = [(e["ts"], e["ts"] + e["dur"]) for e in ks if any(c in e["name"] for c in COMM)]
+    if not comp:
+        return {}
+    t0 = min(s for s, _ in comp)
+    t1 = max(e for _, e in comp + comm)
+    comm = [(max(s, t0), e) for s, e in comm if e > t0]
+    ct, cm = union(comm)
+    _, pm = union(comp)
+    ov = overlap(cm, pm)
+    return {"step_ms": (t1 - t0) / 1e3, "comm_busy_ms": ct / 1e3, "comm_overlapped_ms": ov / 1e3,
+            "exposed_comm_ms": (ct - ov) / 1e3}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("trace")
