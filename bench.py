@@ -214,23 +214,32 @@ def run_ours(a):
         # one extra step under the CUPTI-based torch profiler, AFTER every timed region (never part of a number):
         # gives the exposed-communication figure of BASELINE.json's metric (communication-kernel time not hidden
         # behind compute kernels, rank 0's timeline).  tools/trace_summary.py prints the full tables for profiles/.
+        # every rank runs exactly one more step whatever happens to the profiler (a rank that skipped it would
+        # leave its peers waiting inside the collectives)
+        prof = None
         try:
             from torch.profiler import ProfilerActivity, profile
             torch.cuda.synchronize(device)
-            with profile(activities=[ProfilerActivity.CUDA]) as prof:
-                step()
-                torch.cuda.synchronize(device)
-            if rank == 0:
-                path = a.trace or os.path.join("/tmp", f"tb_bench_trace_{os.getpid()}.json")
-                os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-                prof.export_chrome_trace(path)
-                sys.path.insert(0, os.path.join(ROOT, "tools"))
-                from trace_summary import comm_exposure
-                comm = {k: round(v, 3) for k, v in comm_exposure(path).items()}
-                if not a.trace:
-                    os.remove(path)
-        except Exception as e:  # noqa: BLE001  -- diagnostics must never break the benchmark line
-            comm = {"error": f"{type(e).__name__}: {e}"[:200]}
+            prof = profile(activities=[ProfilerActivity.CUDA])
+            prof.__enter__()
+        except Exception as e:  # noqa: BLE001
+            prof, comm = None, {"error": f"profiler unavailable: {type(e).__name__}: {e}"[:200]}
+        step()
+        torch.cuda.synchronize(device)
+        if prof is not None:
+            try:
+                prof.__exit__(None, None, None)
+                if rank == 0:
+                    path = a.trace or os.path.join("/tmp", f"tb_bench_trace_{os.getpid()}.json")
+                    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+                    prof.export_chrome_trace(path)
+                    sys.path.insert(0, os.path.join(ROOT, "tools"))
+                    from trace_summary import comm_exposure
+                    comm = {k: round(v, 3) for k, v in comm_exposure(path).items()}
+                    if not a.trace:
+                        os.remove(path)
+            except Exception as e:  # noqa: BLE001  -- diagnostics must never break the benchmark line
+                comm = {"error": f"{type(e).__name__}: {e}"[:200]}
 
     if rank == 0:
         res = {
