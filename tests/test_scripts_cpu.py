@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+from dist_utils import _free_port
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -23,7 +25,7 @@ def _torchrun(n, port, *args):
 
 
 def test_benchmark_transformer_dp2_gloo():
-    out = _run(_torchrun(2, 29751, "benchmarks/transformer.py", "--model_name", "gpt2-tiny", "--max_seq_length", "64",
+    out = _run(_torchrun(2, _free_port(), "benchmarks/transformer.py", "--model_name", "gpt2-tiny", "--max_seq_length", "64",
                          "--batch_size", "2", "--num_train_steps", "6", "--log_interval", "3", "--dp_size", "2"))
     recs = [json.loads(l) for l in out.splitlines() if l.startswith("{") and "samples_per_s" in l]
     assert len(recs) == 2 and recs[-1]["step"] == 6 and recs[-1]["samples_per_s"] > 0
@@ -31,8 +33,8 @@ def test_benchmark_transformer_dp2_gloo():
 
 
 def test_example_parallelism_tour_pp_and_ring():
-    for mode, port in (("pp", 29752), ("ring", 29753)):
-        out = _run(_torchrun(2, port, "examples/parallelism_tour.py", "--mode", mode))
+    for mode in ("pp", "ring"):
+        out = _run(_torchrun(2, _free_port(), "examples/parallelism_tour.py", "--mode", mode))
         losses = [float(l.split("loss")[1]) for l in out.splitlines() if l.startswith(f"[{mode}]")]
         assert len(losses) == 10 and losses[-1] < losses[0], (mode, losses)
 
