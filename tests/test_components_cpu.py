@@ -354,3 +354,33 @@ def test_trace_summary_tool(tmp_path):
                          text=True, check=True).stdout
     assert "step span 2.50 ms" in out and "GPU busy (any stream) 2.00 ms" in out, out
     assert "communication kernels busy 1.00 ms, of which 0.50 ms" in out, out
+
+
+def test_sliding_window_model_matches_masked_reference():
+    """Mistral-style local attention in the native model == explicit banded causal mask."""
+    from torchacc_b200.models import build_llama, llama_config
+    assert llama_config("mistral-7b").sliding_window == 4096
+    torch.manual_seed(0)
+    kw = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=1, num_attention_heads=4, num_key_value_heads=2,
+              head_dim=16, vocab_size=97, max_position_embeddings=64)
+    m_win = build_llama("tiny", sliding_window=8, **kw)
+    m_full = build_llama("tiny", **kw)
+    m_full.load_state_dict(m_win.state_dict())
+    ids = torch.randint(0, 97, (2, 32))
+    a = m_win(ids, return_logits=True)["logits"]
+    b = m_full(ids, return_logits=True)["logits"]
+    # the first `window` positions see the same keys in both models, later ones do not
+    assert torch.allclose(a[:, :8], b[:, :8], atol=1e-5)
+    assert not torch.allclose(a[:, 16:], b[:, 16:], atol=1e-4)
+    # and the windowed output equals attention with an explicit band mask
+    from torchacc_b200.ops.attention import attention_reference
+    q = torch.randn(1, 32, 4, 16)
+    k = torch.randn(1, 32, 2, 16)
+    v = torch.randn(1, 32, 2, 16)
+    out, _ = attention_reference(q, k, v, 16 ** -0.5, True, (7, 0))
+    kk, vv = k.repeat_interleave(2, 2), v.repeat_interleave(2, 2)
+    i = torch.arange(32)
+    band = (i[None, :] <= i[:, None]) & (i[None, :] >= i[:, None] - 7)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2), kk.transpose(1, 2), vv.transpose(1, 2),
+                                                           attn_mask=band).transpose(1, 2)
+    assert torch.allclose(out, ref, atol=1e-5)

@@ -84,6 +84,12 @@ PRESETS = {
     "qwen2-7b": dict(vocab_size=152064, hidden_size=3584, intermediate_size=18944, num_hidden_layers=28,
                      num_attention_heads=28, num_key_value_heads=4, rope_theta=1000000.0, attention_bias=True,
                      rms_norm_eps=1e-6, model_type="qwen2", max_position_embeddings=32768),
+    "mistral-7b": dict(vocab_size=32000, intermediate_size=14336, num_key_value_heads=8, rope_theta=10000.0,
+                       sliding_window=4096, max_position_embeddings=32768, model_type="mistral"),
+    "qwen2.5-0.5b": dict(vocab_size=151936, hidden_size=896, intermediate_size=4864, num_hidden_layers=24,
+                         num_attention_heads=14, num_key_value_heads=2, head_dim=64, rope_theta=1000000.0,
+                         attention_bias=True, rms_norm_eps=1e-6, tie_word_embeddings=True, model_type="qwen2",
+                         max_position_embeddings=32768),
     "tiny": dict(vocab_size=512, hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
                  num_key_value_heads=2, head_dim=64, max_position_embeddings=512),
 }
