@@ -90,6 +90,25 @@ def main():
         err = float((of.float() - out.float()).abs().max())
         res.append(dict(op="gemm_rs", layer=name, M=T, N=H, K=K, fused_ms=t_f, unfused_ms=t_u, gemm_only_ms=t_g,
                         speedup=t_u / t_f, tflops_fused=2.0 * T * H * K / t_f / 1e9, max_abs_err=err))
+    # roofline per the profiling recipe: target time = the slower of FLOPs / measured GEMM peak and the bytes that must
+    # cross NVLink / measured link bandwidth (770 GB/s per direction per GPU)
+    peak_tf, link_gbs = 1689.8, 770.0
+    try:
+        mp = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+        peak_tf = float(mp.get("bf16_tflops", peak_tf))
+    except Exception:
+        pass
+    for r in res:
+        flops = 2.0 * r["M"] * r["N"] * r["K"]
+        if r["op"] == "ag_gemm":      # remote rows of the gathered activation
+            nv_bytes = r["M"] * r["K"] * 2 * (world - 1) / world
+        else:                          # partial output tiles pushed to their owners
+            nv_bytes = r["M"] * r["N"] * 2 * (world - 1) / world
+        t_c, t_n = flops / (peak_tf * 1e12) * 1e3, nv_bytes / (link_gbs * 1e9) * 1e3
+        r["roofline_ms"] = max(t_c, t_n)
+        r["roofline_bound"] = "compute" if t_c >= t_n else "nvlink"
+        r["roofline_frac_fused"] = r["roofline_ms"] / r["fused_ms"]
+        r["roofline_frac_unfused"] = r["roofline_ms"] / r["unfused_ms"]
     if dist.get_rank() == 0:
         for r in res:
             print(json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} | {"world": world}))
