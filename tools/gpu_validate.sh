@@ -12,7 +12,8 @@ run() {   # run <name> <timeout_s> <cmd...>
   ( timeout "$t" "$@" > "$OUT/$name.log" 2>&1; echo "exit $?" >> "$OUT/$name.log" )
   printf "%-28s %s\n" "$name" "$(grep -E 'passed|failed|^\{|exit' "$OUT/$name.log" | tail -2 | tr '\n' ' ' | cut -c1-260)"
 }
-trun() { PORT=$((PORT+1)); echo python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port $PORT; }
+T=""   # torchrun prefix with a fresh rendezvous port (set by `nextport`; must run in THIS shell, not in $(...))
+nextport() { PORT=$((PORT+1)); T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $PORT"; }
 
 if [ "$N" -eq 1 ]; then
   run gpu_tests      600 python -m pytest tests -q -m gpu
@@ -20,12 +21,12 @@ if [ "$N" -eq 1 ]; then
   run gemm_ab        200 build/gemm_test 2 1 1
   run bench_n1       300 python bench.py --steps 5 --warmup 3
 else
-  run multigpu_tests 400 $(trun) -m pytest tests/test_multigpu.py -m multigpu -q
-  run pp_tour        120 $(trun) examples/parallelism_tour.py --mode pp
-  run fused_tp       200 $(trun) benchmarks/fused_tp_bench.py
-  run overlap        200 $(trun) benchmarks/overlap_bench.py
-  run bench          300 $(trun) bench.py --gpus "$N" --steps 5 --warmup 3 --trace "$OUT/trace_n$N.json"
-  TORCHACC_B200_SPLIT_HEAD=1 run bench_split_head 300 $(trun) bench.py --gpus "$N" --steps 5 --warmup 3 --no-e2e
+  nextport; run multigpu_tests 400 $T -m pytest tests/test_multigpu.py -m multigpu -q
+  nextport; run pp_tour        120 $T examples/parallelism_tour.py --mode pp
+  nextport; run fused_tp       200 $T benchmarks/fused_tp_bench.py
+  nextport; run overlap        200 $T benchmarks/overlap_bench.py
+  nextport; run bench          300 $T bench.py --gpus "$N" --steps 5 --warmup 3 --trace "$OUT/trace_n$N.json"
+  nextport; TORCHACC_B200_SPLIT_HEAD=1 run bench_split_head 300 $T bench.py --gpus "$N" --steps 5 --warmup 3 --no-e2e
   gzip -f "$OUT"/trace_*.json 2>/dev/null
 fi
 echo "logs: $OUT/"
