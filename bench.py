@@ -292,6 +292,26 @@ def run_reference(a):
 
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
+    LAZY_MSG = ("reference eager backend cannot run on >1 rank: Config.get_mesh() asserts the XLA 'lazy' "
+                "process-group backend (torchacc/config.py:396-398) after accelerate() initialised 'nccl' "
+                "(dist/__init__.py:45-51); the lazy backend needs torch_xla, which cannot be installed offline")
+    if world > 1:
+        # the first two things reference accelerate() does for a distributed config (accelerate.py:69-71 and
+        # dist/parallel_module.py -> config.get_mesh()), run BEFORE paying for an 8B-parameter model on every rank
+        try:
+            probe = ref_ta.Config()
+            probe.backend = "eager"
+            probe.dist.fsdp.size = world
+            ref_ta.dist.init_process_group(probe)
+            probe.get_mesh()
+        except AssertionError as e:
+            if dist.is_initialized():
+                dist.destroy_process_group()
+            unavailable(LAZY_MSG if "should be lazy" in str(e) else f"setup failed: AssertionError: {e}"[:400])
+        except Exception as e:  # noqa: BLE001
+            if dist.is_initialized():
+                dist.destroy_process_group()
+            unavailable(f"setup failed: {type(e).__name__}: {e}"[:400])
     hf = LlamaConfig(vocab_size=128256, hidden_size=4096, intermediate_size=14336,
                      num_hidden_layers=a.layers or 32, num_attention_heads=32, num_key_value_heads=8,
                      max_position_embeddings=max(a.seq_len, 8192), rope_theta=500000.0, rms_norm_eps=1e-5,
@@ -329,9 +349,7 @@ def run_reference(a):
             # stock behaviour of the unmodified reference without torch_xla: accelerate() initialises the 'nccl'
             # process group for the eager backend (torchacc/dist/__init__.py:45-51) and Config.get_mesh() then
             # insists on the XLA 'lazy' backend (torchacc/config.py:396-398) -> no multi-rank eager run is possible
-            msg = ("reference eager backend cannot run on >1 rank: Config.get_mesh() asserts the XLA 'lazy' "
-                   "process-group backend (torchacc/config.py:396-398) after accelerate() initialised 'nccl' "
-                   "(dist/__init__.py:45-51); the lazy backend needs torch_xla, which cannot be installed offline")
+            msg = LAZY_MSG
         if world > 1 and dist.is_initialized():
             dist.destroy_process_group()
         unavailable(msg[:400])
