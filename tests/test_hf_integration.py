@@ -145,3 +145,23 @@ def test_accelerate_hf_model_fsdp_two_ranks():
     """An unmodified HuggingFace model through accelerate(): class patches + FSDP engine + GC == single process."""
     from dist_utils import run_distributed
     run_distributed(_hf_fsdp_worker, 2)
+
+
+def test_native_gpt2_matches_hf_gpt2():
+    """Second native family: same weights -> same loss / logits as HuggingFace GPT-2 (vocabulary 131 is padded to 256 in
+    our embedding; the padding rows must not take part in the softmax)."""
+    from transformers import GPT2Config as HFConfig, GPT2LMHeadModel as HFGPT2
+    from torchacc_b200.models import build_gpt2
+    torch.manual_seed(0)
+    hf = HFGPT2(HFConfig(vocab_size=131, n_positions=64, n_embd=64, n_layer=2, n_head=4, attn_pdrop=0.0, embd_pdrop=0.0,
+                         resid_pdrop=0.0)).eval()
+    ours = build_gpt2("gpt2-tiny", vocab_size=131, n_positions=64, n_embd=64, n_layer=2, n_head=4)
+    assert ours.config.padded_vocab == 256
+    ours.load_hf_state_dict(hf.state_dict())
+    with torch.no_grad():
+        ours.wte.weight[131:].normal_(0, 1.0)         # garbage in the padding rows must not matter
+    ids = torch.randint(0, 131, (2, 24), generator=torch.Generator().manual_seed(4))
+    a = hf(input_ids=ids, labels=ids)
+    b = ours(ids, labels=ids, return_logits=True)
+    assert torch.allclose(a.logits, b["logits"], atol=2e-4), float((a.logits - b["logits"]).abs().max())
+    assert abs(float(a.loss) - float(b["loss"])) < 1e-4, (float(a.loss), float(b["loss"]))

@@ -93,6 +93,14 @@ class GPT2LMHeadModel(nn.Module):
             else:
                 p.normal_(0.0, self.config.initializer_range)
 
+    @torch.no_grad()
+    def load_hf_state_dict(self, sd: dict, strict: bool = True):
+        """Load a HuggingFace ``GPT2LMHeadModel`` / ``GPT2Model`` state dict."""
+        own = _hf_gpt2_to_native(sd, self.config)
+        tgt = self.state_dict()
+        own = {k: v.to(tgt[k].dtype) for k, v in own.items()}
+        return self.load_state_dict(own, strict=strict)
+
     def forward(self, input_ids, labels=None, attention_mask=None, return_logits=None, **_unused):
         B, S = input_ids.shape
         pos = torch.arange(S, device=input_ids.device).repeat(B)
@@ -104,10 +112,32 @@ class GPT2LMHeadModel(nn.Module):
         if labels is not None:
             lab = torch.full_like(labels, -100)
             lab[:, :-1] = labels[:, 1:]
-            out["loss"] = fused_linear_cross_entropy(h, self.wte.weight, lab.reshape(-1))
+            out["loss"] = fused_linear_cross_entropy(h, self.wte.weight, lab.reshape(-1),
+                                                     valid_vocab=self.config.vocab_size)
         if return_logits or (labels is None and return_logits is None):
             out["logits"] = linear(h, self.wte.weight).view(B, S, -1)[..., :self.config.vocab_size]
         return out
+
+
+def _hf_gpt2_to_native(sd: dict, cfg: GPT2Config) -> dict:
+    """HuggingFace GPT-2 state dict -> ours.  HF stores the projections as Conv1D ([in, out]): transpose them;
+    the tied embedding is padded with zero rows up to the aligned vocabulary."""
+    out = {}
+    g = lambda k: sd[k] if k in sd else sd["transformer." + k]
+    wte = g("wte.weight")
+    pad = cfg.padded_vocab - wte.shape[0]
+    out["wte.weight"] = torch.cat([wte, wte.new_zeros(pad, wte.shape[1])], 0) if pad > 0 else wte
+    out["wpe.weight"] = g("wpe.weight")
+    out["ln_f.weight"], out["ln_f.bias"] = g("ln_f.weight"), g("ln_f.bias")
+    for i in range(cfg.n_layer):
+        p, q = f"h.{i}.", f"h.{i}."
+        for ln in ("ln_1", "ln_2"):
+            out[q + ln + ".weight"], out[q + ln + ".bias"] = g(p + ln + ".weight"), g(p + ln + ".bias")
+        for ours, theirs in (("c_attn", "attn.c_attn"), ("c_proj", "attn.c_proj"), ("c_fc", "mlp.c_fc"),
+                             ("c_proj2", "mlp.c_proj")):
+            out[q + ours + ".weight"] = g(p + theirs + ".weight").t().contiguous()
+            out[q + ours + ".bias"] = g(p + theirs + ".bias")
+    return out
 
 
 def build_gpt2(name_or_cfg="gpt2", device=None, dtype=None, **overrides) -> GPT2LMHeadModel:

@@ -68,7 +68,7 @@ def cross_entropy(logits: torch.Tensor, labels: torch.Tensor, ignore_index: int 
 class _FusedLinearCEFn(torch.autograd.Function):
 
     @staticmethod
-    def forward(ctx, hidden, weight, labels, ignore_index, chunk_tokens, n_valid_total):
+    def forward(ctx, hidden, weight, labels, ignore_index, chunk_tokens, n_valid_total, valid_vocab=None):
         H = hidden.shape[-1]
         h2 = hidden.reshape(-1, H)
         if not h2.is_contiguous():
@@ -101,6 +101,8 @@ class _FusedLinearCEFn(torch.autograd.Function):
             e = min(T, s + chunk_tokens)
             lg = logits[:e - s]
             gemm(h2[s:e], weight, out=lg)                                   # logits chunk
+            if valid_vocab is not None and valid_vocab < V:
+                lg[:, valid_vocab:] = -1.0e4     # padding rows of the embedding: probability (and gradient) exactly 0
             rows = _ce_native(lg, lab[s:e], ignore_index, scale, want_grad)  # lg <- dlogits (already / n_valid)
             total += rows.sum()
             if not want_grad:
@@ -132,18 +134,23 @@ class _FusedLinearCEFn(torch.autograd.Function):
             ctx.weight._tb_grad_ready = True
         elif ctx.mode == "own":
             out_dw = dw * dloss.to(dw.dtype)
-        return dh.view(ctx.shape), out_dw, None, None, None, None
+        return dh.view(ctx.shape), out_dw, None, None, None, None, None
 
 
 def fused_linear_cross_entropy(hidden: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor,
                                ignore_index: int = -100, chunk_tokens: int = 4096,
-                               n_valid_total: Optional[torch.Tensor] = None) -> torch.Tensor:
+                               n_valid_total: Optional[torch.Tensor] = None,
+                               valid_vocab: Optional[int] = None) -> torch.Tensor:
     """Mean cross-entropy of ``hidden @ weight.T`` against ``labels`` without materialising all logits.
-    ``n_valid_total`` overrides the normaliser (e.g. the global valid-token count under data parallelism)."""
+    ``n_valid_total`` overrides the normaliser (e.g. the global valid-token count under data parallelism);
+    ``valid_vocab`` < ``weight.shape[0]`` excludes the trailing padding rows of a vocabulary that was padded for
+    alignment (GPT-2: 50257 -> 50304) from the softmax."""
     if hidden.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and nat.use_native(hidden, weight) \
             and weight.shape[0] % 8 == 0:
-        return _FusedLinearCEFn.apply(hidden, weight, labels, ignore_index, chunk_tokens, n_valid_total)
+        return _FusedLinearCEFn.apply(hidden, weight, labels, ignore_index, chunk_tokens, n_valid_total, valid_vocab)
     logits = F.linear(hidden, weight).float()
+    if valid_vocab is not None and valid_vocab < logits.shape[-1]:
+        logits = logits[..., :valid_vocab]
     loss = F.cross_entropy(logits.reshape(-1, logits.shape[-1]), labels.reshape(-1), ignore_index=ignore_index,
                            reduction="sum")
     if n_valid_total is None:
