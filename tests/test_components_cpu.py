@@ -184,6 +184,32 @@ def test_optimizer_state_load_roundtrip():
         assert torch.equal(a["exp_avg"], b["exp_avg"]) and torch.equal(a["exp_avg_sq"], c["exp_avg_sq"])
 
 
+@pytest.mark.parametrize("optimizer", ["fused", "torch"])
+def test_optimizer_zero_grad_equals_model_zero_grad(optimizer):
+    """reference loop (benchmarks/transformer.py:162-184): only ``optimizer.zero_grad()`` is called.  The engine must
+    not carry gradient state past it (round-1 advisor finding: stale gradients were summed into the next step)."""
+    import torchacc_b200 as ta
+    ids = torch.randint(0, 64, (2, 16), generator=torch.Generator().manual_seed(3))
+
+    def run(use_opt_zero):
+        model, _ = _engine_model()
+        opt = ta.optim.FusedAdamW(model.parameters(), lr=1e-2) if optimizer == "fused" \
+            else torch.optim.AdamW(model.parameters(), lr=1e-2)
+        norms = []
+        for _ in range(3):
+            model(ids, labels=ids)["loss"].backward()
+            norms.append(float(model.clip_grad_norm_(1e9)))
+            opt.step()
+            (opt if use_opt_zero else model).zero_grad()
+        return norms, [p.detach().clone() for p in model.parameters()]
+
+    n_a, p_a = run(True)
+    n_b, p_b = run(False)
+    assert n_a == pytest.approx(n_b, rel=1e-6), (n_a, n_b)
+    for a, b in zip(p_a, p_b):
+        assert torch.equal(a, b)
+
+
 def test_load_checkpoints_validates_every_shard(tmp_path):
     from torchacc_b200.parallel import state_dict_utils as U
     meta = {"world_size": 2, "rank": 0, "units": [], "pad_multiple": 128}

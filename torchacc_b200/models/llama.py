@@ -410,6 +410,9 @@ class LlamaPipelineStage(nn.Module):
     def forward(self, input_ids=None, hidden=None, labels=None, position_ids=None, cu_seqlens=None,
                 return_logits=None, **_unused):
         core = self._owner[0]
+        pctx = core.pctx
+        if pctx.cp_mesh is not None:
+            raise NotImplementedError("pipeline x context parallelism: shard the sequence outside the pipeline")
         if self.first:
             B, S = input_ids.shape
             h = self.embed_tokens(input_ids.reshape(-1))
@@ -418,19 +421,43 @@ class LlamaPipelineStage(nn.Module):
             h = hidden.reshape(B * S, hidden.shape[-1])
         rope = core.rope(h.device)
         pos = position_ids.reshape(-1).to(torch.int32) if position_ids is not None else None
+        # tensor parallelism inside a stage: the boundary tensor is the full (tp-replicated) hidden state; with
+        # sequence parallelism the residual stream is token-sharded between scatter (stage entry) and gather (exit)
+        tp = pctx.tp
+        sp = tp is not None and tp.sequence_parallel
+        if sp:
+            from ..parallel.tp import gather_tokens, scatter_tokens, tp_replicated
+            h = scatter_tokens(h, tp)
         for layer in self.layers:
-            h = layer(h, rope, B, S, pos, cu_seqlens, core.pctx)
+            h = layer(h, rope, B, S, pos, cu_seqlens, pctx)
         if not self.last:
+            if sp:
+                from ..parallel.tp import gather_tokens_replicated_grad
+                h = gather_tokens_replicated_grad(h, tp)
             return {"hidden": h.view(B, S, -1)}
-        y, _ = rmsnorm(h, self.norm.weight, self.norm.eps)
+        wn = tp_replicated(self.norm.weight, tp) if sp else self.norm.weight
+        y, _ = rmsnorm(h, wn, self.norm.eps)
         out = CausalLMOutput()
         if labels is not None:
             lab = torch.full_like(labels, -100)
             lab[:, :-1] = labels[:, 1:]
-            out["loss"] = fused_linear_cross_entropy(y, self.lm_head.weight, lab.reshape(-1),
-                                                     chunk_tokens=self.config.loss_chunk_tokens)
+            if tp is not None:      # lm_head is vocab-sharded: labels outside the local slice must never index it
+                from ..parallel.tp import gather_tokens, vocab_parallel_cross_entropy
+                hid = gather_tokens(y, tp) if sp else y
+                out["loss"] = vocab_parallel_cross_entropy(hid, self.lm_head.weight, lab.reshape(-1), tp)
+            else:
+                out["loss"] = fused_linear_cross_entropy(y, self.lm_head.weight, lab.reshape(-1),
+                                                         chunk_tokens=self.config.loss_chunk_tokens)
         if return_logits or (labels is None and return_logits is None):
-            out["logits"] = linear(y, self.lm_head.weight).view(B, S, -1)
+            if tp is not None:
+                from ..parallel.tp import gather_tokens
+                hid = gather_tokens(y, tp) if sp else y
+                local = linear(hid, self.lm_head.weight)
+                parts = [torch.empty_like(local) for _ in range(tp.size)]
+                torch.distributed.all_gather(parts, local.contiguous(), group=tp.group)
+                out["logits"] = torch.cat(parts, -1).view(B, S, -1)
+            else:
+                out["logits"] = linear(y, self.lm_head.weight).view(B, S, -1)
         return out
 
 
@@ -451,6 +478,11 @@ def _llama_pipeline_stages(self: LlamaForCausalLM, split_names):
         raise ValueError("split points must be listed in execution order")
     bounds = [0] + cuts + [L]
     n = len(bounds) - 1
+    if n > 1 and self.config.tie_word_embeddings:
+        # the first-stage embedding and the last-stage lm_head would become independent copies whose gradients are
+        # never combined (the reference's ReduceTiedGrads is dead code too, executor.py:140-144): refuse loudly
+        raise ValueError("pipeline parallelism with tie_word_embeddings=True is not supported: the tied weight would "
+                         "live on two stages without gradient synchronisation; untie it (copy into lm_head) first")
     specs = []
     for i in range(n):
         st = LlamaPipelineStage(self, bounds[i], bounds[i + 1], i == 0, i == n - 1)

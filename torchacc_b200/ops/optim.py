@@ -77,6 +77,15 @@ class FusedAdamW(torch.optim.Optimizer):
                     engines.add(id(unit.engine))
                     unit.engine.use_fused_optimizer(self)
 
+    def zero_grad(self, set_to_none: bool = True):
+        """Also drops the engine-side gradient hand-off (``_tb_grad``) of flat shards, so the reference's canonical
+        ``optimizer.zero_grad()`` loop behaves exactly like ``model.zero_grad()``."""
+        super().zero_grad(set_to_none)
+        for group in self.param_groups:
+            for p in group["params"]:
+                if getattr(p, "_tb_grad", None) is not None:
+                    p._tb_grad = None
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None

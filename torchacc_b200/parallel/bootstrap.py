@@ -45,6 +45,8 @@ def current_device() -> torch.device:
 
 def init_process_group(config=None, timeout_s: int = 1800) -> None:
     """Idempotent ``torch.distributed`` initialisation from the torchrun environment."""
+    from ..utils import watchdog
+    watchdog.arm_from_env()            # TORCHACC_B200_HANG_DUMP=<s>: dump every thread's Python stack on a hang
     if not dist.is_available() or dist.is_initialized():
         return
     if world_size() == 1 and "MASTER_ADDR" not in os.environ:

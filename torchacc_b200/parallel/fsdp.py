@@ -129,7 +129,15 @@ class FlatParamUnit:
         self.gather_event = None
         self.lp_version = -1
         self.needs_post_backward = False
-        self.grad_accumulated = False
+
+    @property
+    def grad_accumulated(self) -> bool:
+        """True while the optimizer-visible gradient of this unit holds earlier micro-batches.  Derived from the
+        gradient tensors themselves (not a sticky flag), so ``optimizer.zero_grad()`` -- the reference's canonical
+        loop, docs/quick_start.md / benchmarks/transformer.py:170 -- starts a fresh accumulation exactly like
+        ``model.zero_grad()`` does."""
+        fp = self.flat_param
+        return fp.grad is not None or getattr(fp, "_tb_grad", None) is not None
 
     # ---- construction ---------------------------------------------------------------------------------
     @torch.no_grad()
@@ -311,7 +319,6 @@ class FlatParamUnit:
         if eng.world_data == 1:
             if eng.grad_mode == "fused":
                 fp._tb_grad = self.grad_full        # persistent per-unit buffer, accumulates across micro-batches
-                self.grad_accumulated = True
             else:
                 if fp.grad is None:
                     fp.grad = self.grad_full.to(torch.float32, copy=True)   # never alias the reusable flat buffer
@@ -356,7 +363,6 @@ class FlatParamUnit:
                 out.record_stream(torch.cuda.current_stream())
             eng.note_reduce_done()
         self._reduce_ready = None
-        self.grad_accumulated = True
         if eng.grad_mode == "fused" or self._grad_shard.dtype != fp.dtype:
             fp._tb_grad = self._grad_shard
         else:
@@ -728,7 +734,6 @@ class ShardingEngine:
         for u in self.units:
             u.flat_param.grad = None
             u.flat_param._tb_grad = None
-            u.grad_accumulated = False
 
     def grads(self) -> List[torch.Tensor]:
         out = []

@@ -253,22 +253,57 @@ def _engine_module(model):
     return model._inner_engine_module() if hasattr(model, "_inner_engine_module") else model
 
 
+def _partition_coords() -> Dict[str, int]:
+    """Where this rank sits on the axes that hold DIFFERENT parameters (tp slice, pp stage) or identical copies
+    (replica = dp x sp) -- taken from the mesh ``accelerate()`` built; all zeros / ones without one."""
+    out = {"tp": 0, "tp_num": 1, "pp": 0, "pp_num": 1, "replica": 0}
+    try:
+        from .. import get_global_context
+        mesh = get_global_context().mesh
+    except Exception:
+        mesh = None
+    if mesh is not None:
+        out.update(tp=mesh.get_tp_rank(), tp_num=mesh.get_tp_num(), pp=mesh.get_pp_rank(), pp_num=mesh.get_pp_num())
+        rep = mesh.get_group_ranks("replica") if mesh.get_replica_num() > 1 else None
+        out["replica"] = rep.index(mesh.get_global_rank()) if rep else 0
+    return out
+
+
+def checkpoint_partition_dir(ckpt_dir: str, coords: Optional[Dict[str, int]] = None) -> str:
+    """Directory holding the FSDP shard files of ONE (tp slice, pp stage): ``ckpt_dir`` itself for plain FSDP/DP,
+    ``ckpt_dir/tp{t}-of-{T}_pp{p}-of-{P}`` under tensor / pipeline parallelism, where ranks with equal FSDP coordinates
+    hold different parameters (round-1 advisor finding: they used to overwrite each other's files).  The
+    consolidate / reshard CLI is run once per such directory."""
+    c = coords or _partition_coords()
+    if c["tp_num"] == 1 and c["pp_num"] == 1:
+        return ckpt_dir
+    return os.path.join(ckpt_dir, f"tp{c['tp']}-of-{c['tp_num']}_pp{c['pp']}-of-{c['pp_num']}")
+
+
 def save_sharded_checkpoint(model, optimizer=None, ckpt_dir: str = ".", extra: Optional[Dict[str, Any]] = None) -> None:
     """The reference's documented FSDP recipe (docs/source/dist/fsdp.md:126-156) as one call: every rank writes
     ``rank{R}-of-{W}-model.pth`` (its fp32 flat shards + ``shard_metadata``) and, with an optimizer,
-    ``rank{R}-of-{W}-optimizer.pth``; ``extra`` (step counter, LR-scheduler state, ...) goes into the model file.
-    The files are what ``consolidate_and_reshard_fsdp_ckpts`` consumes."""
+    ``rank{R}-of-{W}-optim.pth``; ``extra`` (step counter, LR-scheduler state, ...) goes into the model file.
+    The files are what ``consolidate_and_reshard_fsdp_ckpts`` consumes (its default patterns match).
+
+    R / W are FSDP shard coordinates.  Ranks that only replicate a shard (HSDP / DP / sequence-parallel peers) do not
+    write; tensor- and pipeline-parallel partitions go to their own sub-directory (``checkpoint_partition_dir``)."""
     m = _engine_module(model)
     meta = m.get_shard_metadata()
+    coords = _partition_coords()
+    meta = dict(meta, partition={k: coords[k] for k in ("tp", "tp_num", "pp", "pp_num")})
     r, w = meta["rank"], meta["world_size"]
-    os.makedirs(ckpt_dir, exist_ok=True)
-    payload = {"model": {k: v.detach().cpu() for k, v in m.sharded_state_dict().items()}, "shard_metadata": meta}
-    if extra:
-        payload["extra"] = extra
-    torch.save(payload, os.path.join(ckpt_dir, f"rank{r}-of-{w}-model.pth"))
-    if optimizer is not None:
-        torch.save(m.sharded_optim_state_dict(optimizer),          # {'optimizer': state_dict, 'shard_metadata': meta}
-                   os.path.join(ckpt_dir, f"rank{r}-of-{w}-optimizer.pth"))
+    d = checkpoint_partition_dir(ckpt_dir, coords)
+    if coords["replica"] == 0:
+        os.makedirs(d, exist_ok=True)
+        payload = {"model": {k: v.detach().cpu() for k, v in m.sharded_state_dict().items()}, "shard_metadata": meta}
+        if extra:
+            payload["extra"] = extra
+        torch.save(payload, os.path.join(d, f"rank{r}-of-{w}-model.pth"))
+        if optimizer is not None:
+            osd = m.sharded_optim_state_dict(optimizer)      # {'optimizer': state_dict, 'shard_metadata': meta}
+            osd["shard_metadata"] = meta
+            torch.save(osd, os.path.join(d, f"rank{r}-of-{w}-optim.pth"))
     if dist.is_available() and dist.is_initialized():
         dist.barrier()
 
@@ -279,9 +314,10 @@ def load_sharded_checkpoint(model, optimizer=None, ckpt_dir: str = ".") -> Dict[
     m = _engine_module(model)
     meta = m.get_shard_metadata()
     r, w = meta["rank"], meta["world_size"]
-    path = os.path.join(ckpt_dir, f"rank{r}-of-{w}-model.pth")
+    d = checkpoint_partition_dir(ckpt_dir)
+    path = os.path.join(d, f"rank{r}-of-{w}-model.pth")
     if not os.path.exists(path):
-        found = sorted(glob.glob(os.path.join(ckpt_dir, "rank*-of-*-model.pth")))
+        found = sorted(glob.glob(os.path.join(d, "rank*-of-*-model.pth")))
         raise FileNotFoundError(f"{path} not found (checkpoint world size differs? files: {found[:4]}); "
                                 "reshard with `python -m torchacc_b200.utils.consolidate_and_reshard_ckpts`")
     ck = torch.load(path, map_location="cpu", weights_only=False)
@@ -289,7 +325,9 @@ def load_sharded_checkpoint(model, optimizer=None, ckpt_dir: str = ".") -> Dict[
         raise ValueError(f"checkpoint was written by {ck['shard_metadata']['world_size']} ranks, this job has {w}")
     m.load_sharded_state_dict(ck["model"])
     if optimizer is not None:
-        opath = os.path.join(ckpt_dir, f"rank{r}-of-{w}-optimizer.pth")
+        opath = os.path.join(d, f"rank{r}-of-{w}-optim.pth")
+        if not os.path.exists(opath) and os.path.exists(opath.replace("-optim.pth", "-optimizer.pth")):
+            opath = opath.replace("-optim.pth", "-optimizer.pth")      # files written by round-1 builds
         osd = torch.load(opath, map_location="cpu", weights_only=False)["optimizer"]
         optimizer.load_state_dict(osd)
     return ck.get("extra", {})

@@ -181,6 +181,23 @@ class _GatherTokens(torch.autograd.Function):
         return _reduce_scatter_rows(g.contiguous(), ctx.tp), None
 
 
+class _GatherTokensReplicatedGrad(torch.autograd.Function):
+    """all-gather rows forward; backward keeps this rank's row block of an upstream gradient that is already COMPLETE
+    and identical on every tp rank (a pipeline-stage boundary: each tp peer of the next stage returns the full
+    gradient), where ``_GatherTokens``' reduce-scatter would count it tp times."""
+
+    @staticmethod
+    def forward(ctx, x, tp: TPContext):
+        ctx.tp = tp
+        return _all_gather_rows(x, tp)
+
+    @staticmethod
+    def backward(ctx, g):
+        tp = ctx.tp
+        n = g.shape[0] // tp.size
+        return g[tp.rank * n:(tp.rank + 1) * n].contiguous(), None
+
+
 class _ScatterTokens(torch.autograd.Function):
     """take this rank's row block forward, all-gather backward."""
 
@@ -211,6 +228,10 @@ def gather_tokens(x, tp: TPContext):
     return _GatherTokens.apply(x, tp)
 
 
+def gather_tokens_replicated_grad(x, tp: TPContext):
+    return _GatherTokensReplicatedGrad.apply(x, tp)
+
+
 def scatter_tokens(x, tp: TPContext):
     return _ScatterTokens.apply(x, tp)
 
@@ -233,8 +254,12 @@ class _VocabParallelCE(torch.autograd.Function):
         dh = torch.zeros_like(hidden)
         want_w = ctx.needs_input_grad[1]
         view = getattr(w_local, "_tb_grad_view", None)
-        dw = view if (want_w and view is not None) else (torch.zeros_like(w_local) if want_w else None)
-        first = not (view is not None and getattr(w_local, "_tb_grad_ready", False))
+        # The weight gradient is produced here for d(loss) = 1 and rescaled in backward (same contract as
+        # ops.cross_entropy._FusedLinearCEFn): write straight into the engine's flat gradient slice only when that
+        # slice holds nothing yet, otherwise keep a private buffer that backward adds with the incoming scale.
+        direct = want_w and view is not None and not bool(getattr(w_local, "_tb_grad_ready", False))
+        dw = (view if direct else torch.zeros_like(w_local)) if want_w else None
+        first = True
         total = torch.zeros((), dtype=torch.float32, device=hidden.device)
         for s in range(0, T, chunk):
             e = min(T, s + chunk)
@@ -260,22 +285,31 @@ class _VocabParallelCE(torch.autograd.Function):
             if want_w:
                 _mm(g, hidden[s:e], a_mn_major=True, b_mn_major=True, out=dw, accumulate=not first)
                 first = False
-        if want_w and view is not None:
+        if direct:
             w_local._tb_grad_ready = True
         # Each rank holds the part of dh that flows through ITS vocab slice.  With sequence parallelism the caller
         # gathered the tokens (gather_tokens) and that op's backward reduce-scatters these partials; without it the
         # hidden states are replicated and the full gradient is needed on every rank.
         if not tp.sequence_parallel:
             tp.coll.all_reduce(dh)
-        ctx.save_for_backward(dh, dw if (want_w and view is None) else None)
-        ctx.own_dw = want_w and view is None
+        ctx.save_for_backward(dh, dw if (want_w and not direct) else None)
+        ctx.mode = "direct" if direct else ("view" if (want_w and view is not None) else ("own" if want_w else "none"))
+        ctx.view = view if want_w else None
+        ctx.weight = w_local if (want_w and view is not None) else None   # the parameter OBJECT (attributes survive)
         return total / n_valid
 
     @staticmethod
     def backward(ctx, dloss):
         dh, dw = ctx.saved_tensors
-        return (dh * dloss.to(dh.dtype), (dw * dloss.to(dw.dtype) if ctx.own_dw else None), None, None, None, None,
-                None)
+        out_dw = None
+        if ctx.mode == "direct":
+            ctx.view.mul_(dloss.to(ctx.view.dtype))
+        elif ctx.mode == "view":
+            ctx.view.add_(dw * dloss.to(dw.dtype))
+            ctx.weight._tb_grad_ready = True
+        elif ctx.mode == "own":
+            out_dw = dw * dloss.to(dw.dtype)
+        return (dh * dloss.to(dh.dtype), out_dw, None, None, None, None, None)
 
 
 def vocab_parallel_cross_entropy(hidden, w_local, labels, tp: TPContext, ignore_index: int = -100,
