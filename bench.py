@@ -30,7 +30,13 @@ def parse():
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=5)
     p.add_argument("--warmup", type=int, default=3)
-    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_fsdp"],
+                   help="ours | reference (UNMODIFIED reference, stock path) | torch_fsdp (NOT the reference: the stack "
+                        "the reference's eager FSDP path would build -- torch FSDP1 + its kernel patches -- so that "
+                        "N > 1 has a same-box competitor; see DESIGN.md section 4)")
+    p.add_argument("--hf", action="store_true",
+                   help="ours: run the SAME HuggingFace LlamaForCausalLM object as the reference arm through "
+                        "ta.accelerate (kernel patches + FSDP engine) instead of the native model definition")
     p.add_argument("--model", default="llama3-8b")
     p.add_argument("--seq-len", type=int, default=4096)
     p.add_argument("--mbs", type=int, default=2, help="sequences per GPU per step")
@@ -77,6 +83,39 @@ class ClockSampler:
         reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(self.rows)}
+
+
+def bench_config(a, world, layers):
+    """The ``config`` object of the JSON line: identical in every arm (the driver compares them)."""
+    return {"model": a.model, "global_batch": a.mbs * world, "seq_len": a.seq_len,
+            "parallelism": f"fsdp{world}" + ("" if a.no_gc else "+gc"), "layers": layers,
+            "l2": "no explicit flush: each step streams >16 GB of weights/activations (>> 126 MB L2)"}
+
+
+METRIC = "Llama-3-8B FSDP bf16 training throughput (whole job, device-timed, max over ranks)"
+
+
+def hf_llama(a, torch, device, world):
+    """HuggingFace Llama-3-8B (random init, same distributions as the native arm) -- the model object the reference
+    arm, the torch_fsdp arm and ``--hf`` all run."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+    hf = LlamaConfig(vocab_size=128256, hidden_size=4096, intermediate_size=14336,
+                     num_hidden_layers=a.layers or 32, num_attention_heads=32, num_key_value_heads=8,
+                     max_position_embeddings=max(a.seq_len, 8192), rope_theta=500000.0, rms_norm_eps=1e-5,
+                     tie_word_embeddings=False, attn_implementation="flash_attention_2", use_cache=False)
+    torch.manual_seed(1234)
+    with torch.device("meta"):
+        model = LlamaForCausalLM(hf)
+    if world == 1:
+        torch.set_default_dtype(torch.float32)
+    model = model.to_empty(device="cpu" if world > 1 else device)
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() == 1:
+                p.fill_(1.0)            # RMSNorm weights (same initialisation as our arm)
+            else:
+                p.normal_(0, 0.02)
+    return model, hf
 
 
 def dist_env():
@@ -129,8 +168,14 @@ def run_ours(a):
         over["num_hidden_layers"] = a.layers
     mcfg = llama_config(a.model, max_position_embeddings=max(a.seq_len, 8192), **over)
     torch.manual_seed(1234)
-    with torch.device(device):
-        model = build_llama(mcfg, dtype=torch.bfloat16)
+    if a.hf:
+        if world > 1:
+            ta.dist.init_process_group()
+        model, _ = hf_llama(a, torch, device, 1)        # built on the device: 16 GB of bf16 per rank
+        model = model.to(torch.bfloat16)
+    else:
+        with torch.device(device):
+            model = build_llama(mcfg, dtype=torch.bfloat16)
 
     cfg = ta.Config()
     cfg.compute.bf16 = True
@@ -243,15 +288,16 @@ def run_ours(a):
 
     if rank == 0:
         res = {
-            "metric": "Llama-3-8B FSDP bf16 training throughput (whole job, device-timed, max over ranks)",
+            "metric": METRIC,
             "value": value, "unit": "tokens/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": value / (A100_TOKENS_PER_S_PER_GPU * world), "dtype": "bf16", "data": "synthetic",
             "impl": "ours",
-            "config": {"model": a.model, "global_batch": a.mbs * world, "seq_len": a.seq_len,
-                       "parallelism": f"fsdp{world}" + ("" if a.no_gc else "+gc"), "layers": mcfg.num_hidden_layers,
+            "config": bench_config(a, world, mcfg.num_hidden_layers),
+            "detail": {"model_code": "HF LlamaForCausalLM through ta.accelerate" if a.hf else "native build_llama",
                        "optimizer": "FusedAdamW + clip_grad_norm(1.0)", "attention": ta.ops.get_attention_backend(),
-                       "l2": "no explicit flush: each step streams >16 GB of weights/activations (>> 126 MB L2)"},
+                       "stack": "torchacc_b200: own FSDP engine + tcgen05 GEMM/attention + symmetric-memory collectives",
+                       "engine_stats": dict(getattr(getattr(model, "engine", None), "stats", {}) or {})},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "comm": comm,
             "mfu_model_flops": mcfg.flops_per_token(a.seq_len) * value / world / 1e12,
             "loss": float(last["loss"]),
@@ -312,21 +358,8 @@ def run_reference(a):
             if dist.is_initialized():
                 dist.destroy_process_group()
             unavailable(f"setup failed: {type(e).__name__}: {e}"[:400])
-    hf = LlamaConfig(vocab_size=128256, hidden_size=4096, intermediate_size=14336,
-                     num_hidden_layers=a.layers or 32, num_attention_heads=32, num_key_value_heads=8,
-                     max_position_embeddings=max(a.seq_len, 8192), rope_theta=500000.0, rms_norm_eps=1e-5,
-                     tie_word_embeddings=False, attn_implementation="flash_attention_2", use_cache=False)
-    torch.manual_seed(1234)
     try:
-        with torch.device("meta"):
-            model = LlamaForCausalLM(hf)
-        model = model.to_empty(device="cpu" if world > 1 else device)
-        with torch.no_grad():
-            for p in model.parameters():
-                if p.dim() == 1:
-                    p.fill_(1.0)            # RMSNorm weights (same initialisation as our arm)
-                else:
-                    p.normal_(0, 0.02)
+        model, hf = hf_llama(a, torch, device, world)
         # transformers 5.x builds `SiLUActivation` objects; the reference's liger MLP patch only accepts `nn.SiLU`
         # (torchacc/ops/liger.py:21-24).  Swapping the activation OBJECT on the user's model keeps the reference's
         # kernel patches active (the alternative, config.compute.disable_kernel_patches, would slow the reference).
@@ -395,23 +428,130 @@ def run_reference(a):
                "h2d_bytes_per_step": int(a.mbs * a.seq_len * 8), "d2h_bytes_per_step": 4, "last_loss": loss_val}
     if rank == 0:
         print(json.dumps({
-            "metric": "Llama-3-8B FSDP bf16 training throughput (whole job, device-timed, max over ranks)",
+            "metric": METRIC,
             "value": value, "unit": "tokens/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": value / (A100_TOKENS_PER_S_PER_GPU * world), "dtype": "bf16", "data": "synthetic",
             "impl": "reference",
-            "config": {"model": a.model, "global_batch": a.mbs * world, "seq_len": a.seq_len,
-                       "parallelism": f"fsdp{world}" + ("" if a.no_gc else "+gc(hf)"),
+            "config": bench_config(a, world, hf.num_hidden_layers),
+            "detail": {"model_code": "HF LlamaForCausalLM", "gc": "HF gradient_checkpointing_enable()",
+                       "optimizer": "torch.optim.AdamW(fused=True) + clip_grad_norm(1.0)",
                        "stack": "torchacc eager: torch FSDP1 + cuBLAS + flash-attn2 + liger"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": 0, "loss": float(last["loss"])}), flush=True)
     if world > 1:
         dist.barrier(device_ids=[device.index])
         dist.destroy_process_group()
 
+# ----------------------------------------------------------------------------------------------------------------
+# context arm (NOT the reference): what reference fsdp.py:196-216 would build if its eager path could run on N > 1
+# ----------------------------------------------------------------------------------------------------------------
+def run_torch_fsdp(a):
+    """torch FSDP1 FULL_SHARD + MixedPrecision(bf16 params, fp32 reduce, fp32 buffers) + ModuleWrapPolicy over
+    LlamaDecoderLayer, the reference's own kernel patches (its liger + flash-attn-2 patches, applied by importing the
+    stock reference package and calling its ``apply_liger_kernel``), HF gradient checkpointing, fused torch AdamW.
+    This is a hand-assembled stand-in, printed with ``"impl": "torch_fsdp"`` -- it never goes through
+    ``--impl reference``, which stays the unmodified stock path (and is unavailable for N > 1)."""
+    rank, local_rank, world = dist_env()
+    import functools
+    import torch
+    import torch.distributed as dist
+    from transformers import LlamaForCausalLM  # noqa: F401  (before the reference import, see run_reference)
+    import transformers.models.llama.modeling_llama as ml
+    import transformers.modeling_flash_attention_utils  # noqa: F401
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    patches = "none (baseline/_ref missing)"
+    if os.path.isdir(os.path.join(ref_dir, "torchacc")):
+        sys.path.insert(0, ref_dir)
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "shims"))
+        try:
+            import torchacc as ref_ta          # import-time patch_fa (torchacc/__init__.py:135)
+            patches = "reference patch_fa"
+        except Exception as e:  # noqa: BLE001
+            ref_ta, patches = None, f"reference import failed: {type(e).__name__}"
+    else:
+        ref_ta = None
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+    model, hf = hf_llama(a, torch, device, world)
+    for m in model.modules():
+        if type(getattr(m, "act_fn", None)).__name__ == "SiLUActivation":
+            m.act_fn = torch.nn.SiLU()
+    if ref_ta is not None:
+        try:
+            ref_ta.ops.apply_liger_kernel()    # what reference accelerate() does on the eager backend (accelerate.py:95-96)
+            patches += " + reference apply_liger_kernel"
+        except Exception as e:  # noqa: BLE001
+            patches += f" (liger failed: {type(e).__name__}: {e})"[:120]
+    if not a.no_gc:
+        model.gradient_checkpointing_enable()
+    from torch.distributed.fsdp import FullyShardedDataParallel as FSDP, MixedPrecision, ShardingStrategy
+    from torch.distributed.fsdp.wrap import ModuleWrapPolicy
+    model = FSDP(model, sharding_strategy=ShardingStrategy.FULL_SHARD,
+                 auto_wrap_policy=ModuleWrapPolicy({ml.LlamaDecoderLayer}),
+                 mixed_precision=MixedPrecision(param_dtype=torch.bfloat16, reduce_dtype=torch.float32,
+                                                buffer_dtype=torch.float32),
+                 device_id=torch.cuda.current_device(), sync_module_states=False)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-5, betas=(0.9, 0.95), weight_decay=0.1, fused=True)
+    g = torch.Generator().manual_seed(rank)
+    host = torch.randint(0, 128256, (a.mbs, a.seq_len), generator=g).pin_memory()
+    ids = host.to(device)
+    last = {}
+
+    def step(x=ids):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = model(input_ids=x, labels=x)
+        loss = out.loss if hasattr(out, "loss") else out["loss"]
+        loss.backward()
+        model.clip_grad_norm_(1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        last["loss"] = loss
+        return loss
+
+    for _ in range(a.warmup):
+        step()
+    torch.cuda.synchronize(device)
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    ms = timed_loop(step, a.steps, 0, device, world)
+    clocks = sampler.stop() if sampler else None
+    tokens = a.mbs * a.seq_len * world * a.steps
+    value = tokens / (ms / 1e3)
+    e2e = None
+    if not a.no_e2e:
+        dist.barrier(device_ids=[device.index])
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            loss_val = float(step(host.to(device, non_blocking=True)))
+        torch.cuda.synchronize(device)
+        wall = torch.tensor([(time.perf_counter() - t0) * 1e3], device=device)
+        dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        e2e = {"value": tokens / (float(wall) / 1e3), "unit": "tokens/s",
+               "h2d_bytes_per_step": int(a.mbs * a.seq_len * 8), "d2h_bytes_per_step": 4, "last_loss": loss_val}
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": value / (A100_TOKENS_PER_S_PER_GPU * world), "dtype": "bf16", "data": "synthetic",
+            "impl": "torch_fsdp", "config": bench_config(a, world, hf.num_hidden_layers),
+            "detail": {"note": "NOT the reference arm: hand-assembled torch FSDP1 stack mirroring reference "
+                               "dist/fsdp.py:196-216 so that N > 1 has a same-box competitor",
+                       "model_code": "HF LlamaForCausalLM", "kernel_patches": patches,
+                       "optimizer": "torch.optim.AdamW(fused=True) + FSDP.clip_grad_norm_(1.0)",
+                       "stack": "torch FSDP1 FULL_SHARD + MixedPrecision(bf16/fp32 reduce) + cuBLAS + flash-attn2 + liger"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": 0, "loss": float(last["loss"])}), flush=True)
+    dist.barrier(device_ids=[device.index])
+    dist.destroy_process_group()
+
 
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch_fsdp":
+        run_torch_fsdp(args)
     else:
         run_ours(args)

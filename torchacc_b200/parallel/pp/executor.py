@@ -38,6 +38,13 @@ class PipeExecutor:
         self.link = StageLink(mesh, device)
         self.stage, self.stages = mesh.get_stage_id(), mesh.get_pp_num()
         self.is_first, self.is_last = mesh.is_first_stage(), mesh.is_last_stage()
+        # Receives are posted one micro-batch early so transfers overlap compute -- except during the FIRST schedule
+        # run: CUDA loads kernel modules lazily, a first-use load can wait for running kernels, and an early-posted NCCL
+        # receive is a kernel that runs until its peer sends.  The first run therefore posts each receive right before
+        # its wait (the reference's blocking order, executor.py:622-667); every kernel is resident afterwards.
+        import os as _os
+        self.early_post = _os.environ.get("TORCHACC_B200_PP_EARLY_POST", "1") != "0"
+        self._warm = False
         self._reset_state()
 
     def _reset_state(self):
@@ -67,9 +74,12 @@ class PipeExecutor:
                                    for k, v in kw.items() if k in self.spec.load_names}
 
     def _post_recv_act(self, ins):
-        self.recv_bufs[ins.buffer], self.recv_works[ins.buffer] = self.link.post_recv_activations()
+        if self._warm and self.early_post:
+            self.recv_bufs[ins.buffer], self.recv_works[ins.buffer] = self.link.post_recv_activations()
 
     def _wait_recv_act(self, ins):
+        if ins.buffer not in self.recv_bufs:      # just-in-time posting (first run / early_post off)
+            self.recv_bufs[ins.buffer], self.recv_works[ins.buffer] = self.link.post_recv_activations()
         StageLink.wait(self.recv_works.pop(ins.buffer, []))
         bufs = self.recv_bufs.pop(ins.buffer)
         for b, m in zip(bufs, self.link.recv_meta):
@@ -108,9 +118,12 @@ class PipeExecutor:
             self.outputs.pop(ins.buffer, None)
 
     def _post_recv_grad(self, ins):
-        self.grad_bufs[ins.buffer], self.grad_works[ins.buffer] = self.link.post_recv_grads()
+        if self._warm and self.early_post:
+            self.grad_bufs[ins.buffer], self.grad_works[ins.buffer] = self.link.post_recv_grads()
 
     def _wait_recv_grad(self, ins):
+        if ins.buffer not in self.grad_bufs:
+            self.grad_bufs[ins.buffer], self.grad_works[ins.buffer] = self.link.post_recv_grads()
         StageLink.wait(self.grad_works.pop(ins.buffer, []))
 
     def _backward(self, ins):
@@ -147,6 +160,8 @@ class PipeExecutor:
                     continue  # ReduceGrads / OptimizerStep happen outside (engine hooks / user loop)
                 h(self, ins)
         self.link.flush()
+        if torch.is_grad_enabled():
+            self._warm = True          # forward AND backward kernels are loaded now
 
     # ---- public ---------------------------------------------------------------------------------------------------
     def _prepare(self, kwargs: dict, output_fn, training: bool):

@@ -67,6 +67,32 @@ class StageLink:
         self.recv_meta: Optional[List[Meta]] = None          # activations coming from prev
         self.sent_meta: Optional[List[Meta]] = None
         self._pending: List = []
+        self.warm_up()
+
+    def warm_up(self):
+        """Create both communicators' p2p channels NOW, collectively (reference dist/__init__.py:68-81 warms its PP
+        send/recv for the same reason).  NCCL creates a communicator / p2p channel at its first use with a host-side
+        rendezvous of both peers; inside the 1F1B schedule the two stages reach their first gradient transfer at
+        different points, and the stage that arrives first blocks on the host while its neighbour's device sits in an
+        early-posted receive that only the blocked stage could satisfy (observed on 2 B200: profiles/pp_hang_r2.txt).
+        One tiny exchange per direction and communicator, in the same order on every stage, then a device sync."""
+        if self.stages <= 1 or not (dist.is_available() and dist.is_initialized()):
+            return
+        t = torch.zeros(1, device=self.device)
+        for group, down in ((self.group, True), (self.bwd_group, False)):
+            # activations flow prev -> next on `group`, gradients next -> prev on `bwd_group`; even stages talk to
+            # their successor first, odd stages to their predecessor, so every pair meets without a cyclic wait
+            for phase in (0, 1):
+                lower = self.stage if (self.stage % 2 == phase) else self.stage - 1     # pair (lower, lower + 1)
+                if lower < 0 or lower + 1 >= self.stages:
+                    continue
+                src, dst = (lower, lower + 1) if down else (lower + 1, lower)
+                if self.stage == src:
+                    dist.send(t, self.mesh.stage_to_global(dst), group=group)
+                else:
+                    dist.recv(t, self.mesh.stage_to_global(src), group=group)
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
 
     def reset_shapes(self):
         self.recv_meta = None
