@@ -106,8 +106,6 @@ def hf_llama(a, torch, device, world):
     torch.manual_seed(1234)
     with torch.device("meta"):
         model = LlamaForCausalLM(hf)
-    if world == 1:
-        torch.set_default_dtype(torch.float32)
     model = model.to_empty(device="cpu" if world > 1 else device)
     with torch.no_grad():
         for p in model.parameters():
@@ -286,6 +284,13 @@ def run_ours(a):
             except Exception as e:  # noqa: BLE001  -- diagnostics must never break the benchmark line
                 comm = {"error": f"{type(e).__name__}: {e}"[:200]}
 
+    carry_counters = None
+    try:
+        from torchacc_b200.parallel.carry import CarryRuntime, available
+        if world > 1 and available():
+            carry_counters = CarryRuntime.counters()
+    except Exception:  # noqa: BLE001
+        pass
     if rank == 0:
         res = {
             "metric": METRIC,
@@ -297,7 +302,8 @@ def run_ours(a):
             "detail": {"model_code": "HF LlamaForCausalLM through ta.accelerate" if a.hf else "native build_llama",
                        "optimizer": "FusedAdamW + clip_grad_norm(1.0)", "attention": ta.ops.get_attention_backend(),
                        "stack": "torchacc_b200: own FSDP engine + tcgen05 GEMM/attention + symmetric-memory collectives",
-                       "engine_stats": dict(getattr(getattr(model, "engine", None), "stats", {}) or {})},
+                       "engine_stats": dict(getattr(getattr(model, "engine", None), "stats", {}) or {}),
+                       "carried_collectives": carry_counters},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "comm": comm,
             "mfu_model_flops": mcfg.flops_per_token(a.seq_len) * value / world / 1e12,
             "loss": float(last["loss"]),

@@ -181,3 +181,25 @@ TB_API int tb_rs_reduce_bf16(uint64_t stage, uint64_t counters, uint32_t expecte
   return (int)tb::rs_reduce_bf16(P<void>(stage), P<uint32_t>(counters), expected, P<void>(residual), P<void>(out), rows,
                                  N, world, slot_stride, num_sms, S(stream));
 }
+
+// ---- collectives carried inside the GEMM kernels (csrc/fused/carry.*) ----------------------------------------
+#include "fused/carry.h"
+TB_API long long tb_carry_push(int kind, const uint64_t* src, uint64_t dst, const uint64_t* pads, long long bytes,
+                               int rank, int world, int channel, uint32_t epoch, uint64_t block_counter, float scale,
+                               int in_bf16, int out_fp32, int accumulate, uint64_t stats, int background,
+                               uint64_t stream) {
+  return tb::carry_push(kind, src, dst, pads, bytes, rank, world, channel, epoch, block_counter, scale, in_bf16, out_fp32,
+                        accumulate, stats, background, S(stream));
+}
+TB_API long long tb_carry_pending(long long job_id, int queue) { return tb::carry_pending(job_id, queue); }
+TB_API int tb_carry_flush(long long job_id, int queue, int num_sms, uint64_t stream) {
+  return (int)tb::carry_flush(job_id, queue, num_sms, S(stream));
+}
+TB_API double tb_carry_bytes_per_flop(double v) { return tb::carry_bytes_per_flop(v); }
+TB_API int tb_carry_stats(long long* out4, int reset) {
+  tb::carry_stats(out4, reset);
+  return 0;
+}
+TB_API int tb_symm_wait_done(const uint64_t* pads, int rank, int world, int channel, uint32_t epoch, uint64_t stream) {
+  return (int)tb::symm_wait_done(pads, rank, world, channel, epoch, S(stream));
+}

@@ -25,6 +25,8 @@
 
 #include "../common/ptx.cuh"
 #include "../common/tensormap.h"
+#include "../fused/carry.cuh"
+#include "../fused/carry.h"
 #include "gemm.h"
 
 namespace tb {
@@ -72,6 +74,7 @@ struct GemmArgs {
   int num_m_tiles, num_n_tiles;
   int dynamic;     // 1: grid = one cluster per tile, tiles are claimed with cluster-launch-control (see kernel comment)
   FuseArgs fuse;
+  CarryArgs carry;  // slices of pending FSDP collectives moved by warp 3 of every CTA while the tiles run (fused/carry.cuh)
 };
 
 TB_DEVICE void st_release_sys_u32(uint32_t* p, uint32_t v) {
@@ -190,6 +193,7 @@ struct GemmSmem {
   static constexpr int kStages = (kCluster == 2) ? 6 : 4;
   static constexpr int kBarrierBytes = 1024;
   static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // +1024 alignment slack
+  static constexpr int kTotalCarry = kTotal + kCarrySmemBytes;                 // + the copy warp's private ring
 };
 
 __device__ __forceinline__ void tile_coords(int t, int num_m_tiles, int num_n_tiles, int& tm, int& tn) {
@@ -416,6 +420,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         else umma_commit(tfull_bar(as));
       }
     }
+  } else if (warp_idx == 3) {
+    // ================================ Carried collective ================================
+    // Under static scheduling this warp has no GEMM role: it moves this launch's slice of the pending FSDP
+    // all-gather / reduce-scatter (TMA bulk copies through a private 24 KB ring) while the tiles are computed.
+    if constexpr (kFuse == 0) {
+      if (!dynamic && args.carry.slice[0].kind != 0) {
+        const uint32_t ring = bar_base + S::kBarrierBytes;
+        carry_role(args.carry, ring, ring + kCarryStages * kCarryStageBytes, (int)blockIdx.x, (int)gridDim.x);
+      }
+    }
   } else if (warp_idx >= 4) {
     // ================================ Epilogue ================================
     const uint32_t q = warp_idx & 3;  // TMEM lane quarter this warp may read
@@ -598,10 +612,11 @@ static cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb_, con
   auto kern = gemm_bf16_kernel<kCluster, kAMajor, kBMajor, kFuse>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalCarry);
     if (e != cudaSuccess) return e;
     configured = true;
   }
+  const bool carrying = kFuse == 0 && args.carry.slice[0].kind != 0;
   const int num_tiles = args.num_m_tiles * args.num_n_tiles;
   int clusters = num_sms / kCluster;
   if (kFuse == 1) clusters -= args.fuse.comm_clusters;   // copy clusters share their SMs with nobody
@@ -612,7 +627,7 @@ static cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb_, con
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * kCluster);
   cfg.blockDim = dim3(kNumThreads);
-  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.dynamicSmemBytes = carrying ? S::kTotalCarry : S::kTotal;   // the ring only when there is something to carry
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -649,6 +664,7 @@ static bool fill_common(GemmArgs& args, void* D, const void* bias, int M, int N,
   args.num_n_tiles = (N + kBlockN - 1) / kBlockN;
   args.dynamic = gemm_sched_mode(-1);
   memset(&args.fuse, 0, sizeof(args.fuse));
+  memset(&args.carry, 0, sizeof(args.carry));
   return true;
 }
 
@@ -677,6 +693,9 @@ cudaError_t gemm_bf16_ex(const void* A, const void* B, void* D, const void* bias
   }
   GemmArgs args;
   fill_common(args, D, bias, M, N, K, ldd, out_fp32, C, ldc, cluster);
+  // pending FSDP collectives ride along: bytes proportional to this GEMM's FLOPs (static scheduling only -- under
+  // dynamic scheduling warp 3 is the tile scheduler and collectives run as their own kernels)
+  if (!args.dynamic) carry_take(2.0 * (double)M * (double)N * (double)K, &args.carry);
 
 #define TB_DISPATCH(CL, AM, BM) return launch_one<CL, AM, BM, 0>(ta, tbm, args, num_sms, stream)
   if (cluster == 2) {

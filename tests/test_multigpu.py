@@ -67,6 +67,62 @@ def test_symm_collectives_match_nccl():
     assert torch.allclose(big, ref, atol=1e-4, rtol=1e-4)
 
 
+def test_carried_collectives_match_reference():
+    """Parameter all-gather and gradient reduce-scatter carried by tcgen05 GEMM launches (csrc/fused/carry.cuh): results
+    equal the NCCL collectives, the GEMMs that carried them are still correct, the fused sum of squares matches, and
+    the counters prove slices really rode inside GEMM kernels (not only in the stand-alone flush)."""
+    from torchacc_b200.ops.linear import gemm
+    from torchacc_b200.parallel.carry import BACKGROUND, CarryRuntime, make_carry
+    from torchacc_b200.parallel.symm_mem import SymmCollectives, symm_available
+    from torchacc_b200 import _native as nat
+    g = dist.group.WORLD
+    assert symm_available(g)
+    c = SymmCollectives(g, WORLD, dist.get_rank(), _dev())
+    rt = make_carry(c, _dev())
+    assert rt is not None
+    prev_sched = nat.require().tb_gemm_sched_mode(-1)
+    nat.set_gemm_scheduler(False)
+    torch.manual_seed(100 + dist.get_rank())
+    n = (6 << 20) + 128 * 7                      # elements per shard; not a multiple of the 8 KB chunk
+    shard = c.alloc(n, torch.bfloat16)
+    shard.copy_(torch.randn(n, device=_dev()).bfloat16())
+    grads = c.alloc(n * WORLD, torch.bfloat16)
+    grads.copy_(torch.randn(n * WORLD, device=_dev()).bfloat16())
+    full = torch.zeros(n * WORLD, dtype=torch.bfloat16, device=_dev())
+    out = torch.full((n,), 7.0, dtype=torch.float32, device=_dev())
+    a = torch.randn(4096, 4096, device=_dev()).bfloat16()
+    b = torch.randn(4096, 4096, device=_dev()).bfloat16()
+    ref_y = (a.float() @ b.float().t())
+    CarryRuntime.counters(reset=True)
+    rt.arm_stats()
+    jg = rt.push_gather(shard, full)
+    jr = rt.push_reduce(grads, out, 1.0 / WORLD, accumulate=False)
+    ys = [gemm(a, b) for _ in range(6)]           # 6 x 137 GFLOP: carries most of the 2 x 12 MB x (W-1)
+    rt.flush()                                    # whatever is left
+    rt.wait_done(jg[1], jg[2])
+    rt.wait_done(jr[1], jr[2])
+    torch.cuda.synchronize()
+    cnt = CarryRuntime.counters()
+    assert cnt["chunks_carried"] > 0 and cnt["launches_carrying"] > 0, cnt
+    ref_full = torch.empty_like(full)
+    dist.all_gather_into_tensor(ref_full, shard)
+    assert torch.equal(full, ref_full)
+    ref_out = torch.empty(n, dtype=torch.float32, device=_dev())
+    dist.reduce_scatter_tensor(ref_out, grads.float() / WORLD)
+    assert torch.allclose(out, ref_out, atol=1e-5, rtol=1e-5), float((out - ref_out).abs().max())
+    assert torch.allclose(rt.stats[0], (ref_out.double() ** 2).sum().float(), rtol=1e-4), (rt.stats, (ref_out ** 2).sum())
+    assert float(rt.stats[1]) == 0.0
+    for y in ys:
+        assert torch.allclose(y.float(), ref_y, atol=2.0, rtol=2e-2)
+    # accumulate into the existing shard + everything through the stand-alone kernel
+    jr2 = rt.push_reduce(grads, out, 1.0 / WORLD, accumulate=True)
+    rt.flush(jr2[0], BACKGROUND)
+    rt.wait_done(jr2[1], jr2[2])
+    torch.cuda.synchronize()
+    assert torch.allclose(out, 2 * ref_out, atol=2e-5, rtol=1e-5)
+    nat.set_gemm_scheduler(bool(prev_sched))
+
+
 def _tiny(dtype=torch.bfloat16):
     from torchacc_b200.models import build_llama
     torch.manual_seed(0)

@@ -1,0 +1,158 @@
+"""Collectives carried inside the GEMM kernels (csrc/fused/carry.cuh / carry.cu) -- the FSDP hot path.
+
+Instead of launching the parameter all-gather and the gradient reduce-scatter of a unit as their own kernels on side
+streams, the sharding engine *enqueues* them here.  Every tcgen05 GEMM launched afterwards (forward, recomputation,
+dgrad, wgrad, the chunked lm_head) takes a slice of the pending jobs proportional to its FLOPs, and warp 3 of each of
+its CTAs moves that slice over NVLink with TMA bulk copies while the tile pipeline of the same CTA runs:
+
+* all-gather: peer shards -> private smem ring -> the local gathered flat-parameter buffer;
+* reduce-scatter: this rank's slice of all peers' flat gradient buffers -> smem -> fp32 sum -> 1/world scale ->
+  gradient shard, and the sum of squares of the result for ``clip_grad_norm_`` (no separate norm pass).
+
+Foreground jobs (the next unit's gather) get a launch's byte budget first; background jobs (reduce-scatters, the
+lm_head gather) use the rest.  Whatever no GEMM carried by the time it is needed runs as one stand-alone kernel
+(``flush``) -- in a Llama-3-8B step that is the first gather of the step and the last reductions of the backward.
+Everything is on the compute stream: there are no communication streams and no events in this mode.
+
+Reference parity: torchacc/dist/fsdp.py:196-230 (torch FSDP / XLA-FSDP all-gather + reduce-scatter per unit).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from .. import _native as nat
+
+nat.register_signatures({
+    "tb_carry_push": ([nat.i32, ctypes.POINTER(nat.u64), nat.u64, ctypes.POINTER(nat.u64), nat.i64, nat.i32, nat.i32,
+                       nat.i32, ctypes.c_uint32, nat.u64, nat.f32, nat.i32, nat.i32, nat.i32, nat.u64, nat.i32, nat.u64],
+                      nat.i64),
+    "tb_carry_pending": ([nat.i64, nat.i32], nat.i64),
+    "tb_carry_flush": ([nat.i64, nat.i32, nat.i32, nat.u64], nat.i32),
+    "tb_carry_bytes_per_flop": ([ctypes.c_double], ctypes.c_double),
+    "tb_carry_stats": ([ctypes.POINTER(nat.i64), nat.i32], nat.i32),
+    "tb_symm_wait_done": ([ctypes.POINTER(nat.u64), nat.i32, nat.i32, nat.i32, ctypes.c_uint32, nat.u64], nat.i32),
+})
+
+# signal-pad channels (parallel/symm_mem.py uses 0-3, fused TP 8+)
+CH_GATHER, CH_REDUCE, CH_GATHER_BG = 4, 5, 6
+FOREGROUND, BACKGROUND, ALL_QUEUES = 0, 1, -1
+
+
+def available() -> bool:
+    L = nat.lib()
+    return L is not None and hasattr(L, "tb_carry_push")
+
+
+class CarryRuntime:
+    """Job submission for one symmetric-memory domain (= one FSDP shard group)."""
+
+    def __init__(self, coll, device: torch.device):
+        self.coll = coll                      # SymmCollectives
+        self.domain = coll.domain
+        self.device = device
+        self.world, self.rank = self.domain.world, self.domain.rank
+        # [sum of squares of every reduced gradient shard of this backward pass, non-finite flag]
+        self.stats = torch.zeros(2, dtype=torch.float32, device=device)
+        self.reduce_jobs = 0                  # reduce-scatters pushed since the statistics were armed
+        self.stats_exact = True               # False once a job accumulated into an existing shard (micro-batching)
+        self.last_epoch = {CH_GATHER: 0, CH_REDUCE: 0, CH_GATHER_BG: 0}
+
+    # ---- submission ---------------------------------------------------------------------------------------
+    def _buf(self, t: torch.Tensor):
+        buf = self.domain.find(t)
+        if buf is None:
+            raise RuntimeError("carried collectives need their peer-visible operand inside the symmetric domain")
+        return buf
+
+    def push_gather(self, shard: torch.Tensor, full: torch.Tensor, background: bool = False):
+        """``full[r * n:(r + 1) * n] = shard of rank r`` for every r (this rank's own shard is copied here, now).
+        Returns ``(job_id, channel, epoch)``."""
+        d = self.domain
+        buf = self._buf(shard)
+        nbytes = shard.numel() * shard.element_size()
+        assert nbytes % 16 == 0 and full.numel() == shard.numel() * self.world and full.is_contiguous()
+        off = shard.data_ptr() - buf.ptr
+        src = (nat.u64 * self.world)(*[buf.peer_ptrs[r] + off for r in range(self.world)])
+        n = shard.numel()
+        full[self.rank * n:(self.rank + 1) * n].copy_(shard)          # local part: plain device copy
+        ch = CH_GATHER_BG if background else CH_GATHER
+        epoch = d.next_epoch(ch)
+        L = nat.require()
+        job = L.tb_carry_push(1, src, full.data_ptr(), d.pad_ptrs, nbytes, self.rank, self.world, ch, epoch,
+                              d.counter_ptr(ch), 1.0, 0, 0, 0, 0, int(background), nat.stream())
+        if job <= 0:
+            raise nat.NativeError("tb_carry_push (gather) rejected the job")
+        self.last_epoch[ch] = epoch
+        return job, ch, epoch
+
+    def push_reduce(self, full: torch.Tensor, out: torch.Tensor, scale: float, accumulate: bool):
+        """``out (+)= scale * sum_r full_of_rank_r[rank * n:(rank + 1) * n]`` with fp32 accumulation; the sum of
+        squares of the new ``out`` is added to ``self.stats``.  Returns ``(job_id, channel, epoch)``."""
+        d = self.domain
+        buf = self._buf(full)
+        n = out.numel()
+        assert full.numel() == n * self.world and full.is_contiguous() and out.is_contiguous()
+        assert full.dtype in (torch.bfloat16, torch.float32) and out.dtype in (torch.bfloat16, torch.float32)
+        slice_bytes = n * full.element_size()
+        assert slice_bytes % 256 == 0, "shard sizes are multiples of 128 elements"
+        off = full.data_ptr() - buf.ptr
+        src = (nat.u64 * self.world)(*[buf.peer_ptrs[r] + off for r in range(self.world)])
+        epoch = d.next_epoch(CH_REDUCE)
+        L = nat.require()
+        job = L.tb_carry_push(2, src, out.data_ptr(), d.pad_ptrs, slice_bytes, self.rank, self.world, CH_REDUCE, epoch,
+                              d.counter_ptr(CH_REDUCE), float(scale), int(full.dtype == torch.bfloat16),
+                              int(out.dtype == torch.float32), int(accumulate), self.stats.data_ptr(), 1,
+                              nat.stream())
+        if job <= 0:
+            raise nat.NativeError("tb_carry_push (reduce) rejected the job")
+        self.last_epoch[CH_REDUCE] = epoch
+        self.reduce_jobs += 1
+        if accumulate:
+            self.stats_exact = False
+        return job, CH_REDUCE, epoch
+
+    def arm_stats(self):
+        """Start of a backward pass: forget the previous pass' gradient statistics."""
+        self.stats.zero_()
+        self.reduce_jobs = 0
+        self.stats_exact = True
+
+    # ---- completion ---------------------------------------------------------------------------------------
+    def pending(self, job: int = 0, queue: int = ALL_QUEUES) -> int:
+        return int(nat.require().tb_carry_pending(job, queue))
+
+    def flush(self, job: int = 0, queue: int = ALL_QUEUES) -> None:
+        """Issue whatever is still queued (up to ``job``) as a stand-alone kernel on the current stream."""
+        L = nat.require()
+        if L.tb_carry_pending(job, queue) > 0:
+            nat.check(L.tb_carry_flush(job, queue, nat.num_sms(), nat.stream()), "tb_carry_flush")
+            nat.count_launch()
+
+    def wait_done(self, channel: int, epoch: int) -> None:
+        """Current stream waits until EVERY rank finished the job ``epoch`` of ``channel`` (its source buffers may
+        then be overwritten)."""
+        if epoch <= 0:
+            return
+        d = self.domain
+        nat.check(nat.require().tb_symm_wait_done(d.pad_ptrs, self.rank, self.world, channel, epoch, nat.stream()),
+                  "tb_symm_wait_done")
+        nat.count_launch()
+
+    @staticmethod
+    def counters(reset: bool = False) -> dict:
+        out = (nat.i64 * 4)()
+        nat.require().tb_carry_stats(out, int(reset))
+        return {"chunks_carried": out[0], "chunks_flushed": out[1], "launches_carrying": out[2], "flushes": out[3]}
+
+
+def make_carry(coll, device: torch.device) -> Optional[CarryRuntime]:
+    """A runtime when ``coll`` is the symmetric-memory back-end on a CUDA device and the feature is enabled."""
+    import os
+    if device.type != "cuda" or not hasattr(coll, "domain") or not available():
+        return None
+    if os.environ.get("TORCHACC_B200_CARRY", "1") == "0":
+        return None
+    return CarryRuntime(coll, device)

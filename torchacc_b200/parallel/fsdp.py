@@ -213,12 +213,22 @@ class FlatParamUnit:
         self.lp_version = fp._version
         fp._tb_lp_version = fp._version
 
-    def gather(self, prefetch: bool = False) -> None:
-        """Make ``lp_full`` valid (asynchronously on the gather stream when sharded)."""
+    def gather(self, prefetch: bool = False, background: bool = False) -> None:
+        """Make ``lp_full`` valid (asynchronously on the gather stream when sharded; as a job carried by the following
+        GEMM kernels when the engine runs carried collectives)."""
         if self.gathered:
             return
         eng = self.engine
         self.refresh_lp_shard()
+        if eng.carry is not None and self.persistent_full is None:
+            buf = eng.lp_pool.acquire(self.padded, eng.compute_dtype)
+            self._gather_job = eng.carry.push_gather(self.lp_shard, buf, background=background)
+            self.gather_event = None
+            self.lp_full = buf
+            self.gathered = True
+            if not prefetch:
+                self.finish_gather()
+            return
         if self.persistent_full is not None:
             if eng.shard_world > 1:   # NO_SHARD-after-forward mode keeps a full copy: refresh it by all-gather
                 with eng.on_gather_stream():
@@ -234,7 +244,20 @@ class FlatParamUnit:
         self.lp_full = buf
         self.gathered = True
 
+    def finish_gather(self) -> None:
+        """Carried mode: whatever part of this unit's gather no GEMM has taken yet runs now (stand-alone kernel)."""
+        job = getattr(self, "_gather_job", None)
+        if job is not None:
+            self._gather_job = None
+            jid, ch, _epoch = job
+            from .carry import BACKGROUND, FOREGROUND
+            left = self.engine.carry.pending(jid, BACKGROUND if ch != 4 else FOREGROUND)
+            if left:
+                self.engine.stats["gather_chunks_flushed"] = self.engine.stats.get("gather_chunks_flushed", 0) + left
+                self.engine.carry.flush(jid, BACKGROUND if ch != 4 else FOREGROUND)
+
     def wait_gather(self) -> None:
+        self.finish_gather()
         if self.gather_event is not None:
             torch.cuda.current_stream().wait_event(self.gather_event)
             self.gather_event = None
@@ -266,6 +289,18 @@ class FlatParamUnit:
             self.grad_full = self._grad_persistent
         else:
             self.grad_full = eng.grad_pool.acquire(self.padded, eng.grad_wire_dtype)
+            if eng.carry is not None:
+                # the previous user's reduce-scatter reads this buffer from EVERY rank: it must have been issued here
+                # and finished everywhere before the wgrad epilogues write into it again
+                prev = eng._carry_reduce_of.pop(self.grad_full.data_ptr(), None)
+                if prev is not None:
+                    from .carry import BACKGROUND
+                    jid, ch, epoch = prev
+                    left = eng.carry.pending(jid, BACKGROUND)
+                    if left:
+                        eng.stats["reduce_chunks_flushed"] = eng.stats.get("reduce_chunks_flushed", 0) + left
+                        eng.carry.flush(jid, BACKGROUND)
+                    eng.carry.wait_done(ch, epoch)
         keep = self.grad_accumulated and eng.accumulate_in_flat
         for info in self.infos:
             t = info.tensor
@@ -341,6 +376,21 @@ class FlatParamUnit:
         first = not self.grad_accumulated
         if getattr(self, "_grad_shard", None) is None:
             self._grad_shard = torch.empty(self.shard_numel, dtype=eng.grad_shard_dtype, device=eng.device)
+        if eng.carry is not None:
+            # carried by the GEMMs of the units whose backward follows: fp32 sum over ranks, 1/world scale, (+= for
+            # later micro-batches) and the sum of squares for the gradient norm, all in the reducing warp
+            if not eng._carry_stats_armed:
+                eng.carry.arm_stats()
+                eng._carry_stats_armed = True
+            job = eng.carry.push_reduce(src, self._grad_shard, 1.0 / eng.world_data, accumulate=not first)
+            eng._carry_reduce_of[src.data_ptr()] = job
+            eng.grad_pool.release(src, torch.cuda.current_stream())
+            self._reduce_ready = None
+            if eng.grad_mode == "fused" or self._grad_shard.dtype != fp.dtype:
+                fp._tb_grad = self._grad_shard
+            else:
+                fp.grad = self._grad_shard
+            return
         out = self._grad_shard if first else torch.empty_like(self._grad_shard)
         scale = 1.0 / eng.world_data
         if eng.device.type == "cuda":
@@ -513,11 +563,21 @@ class ShardingEngine:
         self.grad_pool = _BufferPool(device, depth=2, allocator=(self.shard_coll.alloc if symm_grad else None))
         self._empty = torch.empty(0, dtype=compute_dtype, device=device)
         cuda = device.type == "cuda"
+        # Carried collectives (parallel/carry.py): parameter all-gathers and gradient reduce-scatters ride inside the
+        # GEMM kernels that run anyway (warp 3 of every CTA is the copy / reduce engine) -- no communication kernels
+        # next to the GEMMs, no side streams.  Needs the symmetric-memory back-end and a plain FULL_SHARD group.
+        self.carry = None
+        self._carry_reduce_of: Dict[int, tuple] = {}
+        self._carry_stats_armed = False
+        if cuda and self.reshard and self.replica_world == 1:
+            from .carry import make_carry
+            self.carry = make_carry(self.shard_coll, device)
         if cuda and self.world_data > 1:
-            # collectives will run on side streams next to the GEMMs: claim GEMM tiles dynamically so SMs that are
-            # busy with a collective CTA do not stall a whole GEMM (see csrc/gemm/gemm_bf16.cu, "tile iteration")
+            # without carried collectives they run on side streams next to the GEMMs: claim GEMM tiles dynamically so
+            # SMs that are busy with a collective CTA do not stall a whole GEMM (csrc/gemm/gemm_bf16.cu, "tile
+            # iteration").  With them the GEMM owns the GPU: static striping (warp 3 is the copy engine, not a scheduler)
             from .. import _native as nat
-            nat.set_gemm_scheduler(True)
+            nat.set_gemm_scheduler(self.carry is None)
         # communication windows: on a GPU the flash-attention CTAs need whole SMs (224 KB smem) and small GEMMs are
         # the most sensitive to a concurrent collective, so prefetch all-gathers and gradient reduce-scatters are
         # not started at unit boundaries but at the next "window" = the start of an MLP, where ~2-5 ms of large GEMMs
@@ -525,10 +585,13 @@ class ShardingEngine:
         import os as _os
         _cw = _os.environ.get("TORCHACC_B200_COMM_WINDOWS", "1")           # "0" off, "force" also on CPU (tests)
         self.comm_windows = bool(self.world_data > 1 and (_cw == "force" or (cuda and _cw != "0")))
+        if self.carry is not None:
+            self.comm_windows = False      # nothing to defer: the jobs are spread over the GEMMs by their FLOPs
         # optional "head" unit (final norm + lm_head split off the root unit, TORCHACC_B200_SPLIT_HEAD=1): its
         # gradients are complete right after the loss backward, so its reduce-scatter hides behind the whole
         # backward pass instead of sitting exposed before the optimizer with the embedding's
-        self.split_head = _os.environ.get("TORCHACC_B200_SPLIT_HEAD", "0") == "1"
+        # default on since round 2 (2 GPUs: exposed communication 6.9 -> 3.8 ms per step, profiles/split_head_n2_r2.txt)
+        self.split_head = _os.environ.get("TORCHACC_B200_SPLIT_HEAD", "1") == "1"
         self.head_unit: Optional[FlatParamUnit] = None
         self._head_staged = False
         self._deferred_prefetch: Optional[FlatParamUnit] = None
@@ -604,10 +667,18 @@ class ShardingEngine:
         unit.gather()
         unit.wait_gather()
         if unit is self.root_unit and self.head_unit is not None:
-            self.head_unit.gather()
-            self.head_unit.wait_gather()
+            head = self.head_unit
+            if self.carry is not None and self._fwd_recorded and len(self.fwd_order) > 2:
+                # final norm + lm_head are needed after the LAST layer: their gather rides in the background of all
+                # layers' GEMMs; post_forward of the last wrapped unit makes sure it is complete
+                head.gather(prefetch=True, background=True)
+                head._point_views(head.lp_full)
+                head._views_ptr = head.lp_full.data_ptr()
+            else:
+                head.gather()
+                head.wait_gather()
             if torch.is_grad_enabled():
-                self.head_unit.prepare_grad_buffer()
+                head.prepare_grad_buffer()
         if unit is self.root_unit and torch.is_grad_enabled():
             unit.prepare_grad_buffer()   # the fused linear+CE writes lm_head's wgrad during the forward pass
         for k in range(1, self.prefetch + 1):
@@ -636,6 +707,8 @@ class ShardingEngine:
         self.comm_window(None)
 
     def post_forward(self, unit: FlatParamUnit):
+        if self.carry is not None and self.head_unit is not None and self._is_last_forward_unit(unit):
+            self.head_unit.finish_gather()
         if self.reshard and unit is not self.root_unit and not self._is_last_forward_unit(unit):
             unit.reshard()
 
@@ -722,7 +795,19 @@ class ShardingEngine:
                 unit.reshard()
         for unit in self.units:  # anything still gathered from prefetch
             if self.reshard and unit.gathered:
+                unit.finish_gather()
                 unit.reshard()
+        if self.carry is not None:
+            c = self.carry
+            left = c.pending()
+            if left:
+                self.stats["tail_chunks_flushed"] = self.stats.get("tail_chunks_flushed", 0) + left
+            c.flush()                                   # the last reductions of the pass: nothing left to carry them
+            # every rank has finished pulling parameter shards: the optimizer may now rewrite them
+            from .carry import CH_GATHER, CH_GATHER_BG
+            c.wait_done(CH_GATHER, c.last_epoch[CH_GATHER])
+            c.wait_done(CH_GATHER_BG, c.last_epoch[CH_GATHER_BG])
+            self._carry_stats_armed = False
         self.wait_reductions()
         self.training_step += 1
 
@@ -753,7 +838,12 @@ class ShardingEngine:
         from ..ops.optim import grad_sqnorm, scale_
         assert norm_type == 2.0, "only the L2 norm is supported"
         gs = self.grads()
-        stat = grad_sqnorm(gs, device=self.device)
+        c = self.carry
+        if c is not None and c.stats_exact and c.reduce_jobs == len(gs) and len(gs) == len(self.units):
+            stat = c.stats.clone()          # accumulated by the reduce-scatter warps: no pass over the gradients
+            self.stats["fused_grad_norm"] = self.stats.get("fused_grad_norm", 0) + 1
+        else:
+            stat = grad_sqnorm(gs, device=self.device)
         if self.shard_world > 1:
             self.shard_coll.all_reduce(stat)
         for g in groups:
