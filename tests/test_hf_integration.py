@@ -165,3 +165,40 @@ def test_native_gpt2_matches_hf_gpt2():
     b = ours(ids, labels=ids, return_logits=True)
     assert torch.allclose(a.logits, b["logits"], atol=2e-4), float((a.logits - b["logits"]).abs().max())
     assert abs(float(a.loss) - float(b["loss"])) < 1e-4, (float(a.loss), float(b["loss"]))
+
+
+def test_accelerate_hf_trainer_patches_drive_ten_steps(restore_hf_classes):
+    """reference core/accelerate_hf_trainer.py:52-77.  `transformers.Trainer` cannot be constructed offline (it needs
+    the `accelerate` package), so the three patched Trainer methods are driven in the order Trainer's inner loop calls
+    them (trainer.py: _wrap_model -> create_optimizer -> per step: forward/backward, _clip_grad_norm, optimizer.step,
+    optimizer.zero_grad) on a stand-in that carries the attributes those methods read."""
+    import types
+    import torchacc_b200 as ta
+    from transformers import Trainer
+    assert ta.accelerate_hf_trainer(True)
+    try:
+        args = types.SimpleNamespace(bf16=False, fp16=False, gradient_checkpointing=True, fsdp="full_shard",
+                                     fsdp_config={"transformer_layer_cls_to_wrap": ["LlamaDecoderLayer"]},
+                                     learning_rate=1e-2, adam_beta1=0.9, adam_beta2=0.999, adam_epsilon=1e-8,
+                                     weight_decay=0.0, max_grad_norm=1.0)
+        me = types.SimpleNamespace(args=args, optimizer=None, model=_hf_llama(), model_wrapped=None)
+        model = Trainer._wrap_model(me, me.model)
+        assert getattr(model, "_tb_accelerated", False) and me.model_wrapped is model
+        assert Trainer._wrap_model(me, model) is model            # idempotent, like HF's own wrapper
+        opt = Trainer.create_optimizer(me)
+        assert type(opt).__name__ == "FusedAdamW" and Trainer.create_optimizer(me) is opt
+        ids = torch.randint(0, 160, (2, 24), generator=torch.Generator().manual_seed(3))
+        losses, norms = [], []
+        for _ in range(10):
+            loss = model(input_ids=ids, labels=ids).loss
+            loss.backward()
+            norms.append(float(Trainer._clip_grad_norm(me, model)))   # routed through the sharding engine
+            opt.step()
+            opt.zero_grad()
+            losses.append(float(loss))
+        assert losses[-1] < losses[0] - 0.5, losses
+        assert all(n > 0 for n in norms)
+        assert model.engine.last_clip_coef is not None             # the engine computed the coefficient
+    finally:
+        ta.accelerate_hf_trainer(False)
+    assert Trainer._clip_grad_norm.__qualname__.startswith("Trainer.")

@@ -68,11 +68,23 @@ def accelerate_hf_trainer(enable: bool = True) -> bool:
                                             eps=a.adam_epsilon, weight_decay=a.weight_decay)
             return self.optimizer
 
+        def _clip_grad_norm(self, model):
+            # transformers >= 4.5x calls this once per optimizer step (trainer.py: `grad_norm = self._clip_grad_norm(model)`)
+            m = model if getattr(model, "_tb_accelerated", False) else getattr(self, "model_wrapped", model)
+            if hasattr(m, "clip_grad_norm_") and getattr(m, "_tb_accelerated", False):
+                return m.clip_grad_norm_(self.args.max_grad_norm)     # sharded norm + device-side coefficient
+            return _ORIG["_clip_grad_norm"](self, model)
+
         Trainer._wrap_model = _wrap_model
         Trainer.create_optimizer = create_optimizer
+        if hasattr(Trainer, "_clip_grad_norm"):
+            _ORIG["_clip_grad_norm"] = Trainer._clip_grad_norm
+            Trainer._clip_grad_norm = _clip_grad_norm
         _ENABLED = True
     elif not enable and _ENABLED:
         Trainer._wrap_model = _ORIG.pop("_wrap_model")
         Trainer.create_optimizer = _ORIG.pop("create_optimizer")
+        if "_clip_grad_norm" in _ORIG:
+            Trainer._clip_grad_norm = _ORIG.pop("_clip_grad_norm")
         _ENABLED = False
     return True
