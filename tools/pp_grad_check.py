@@ -1,0 +1,96 @@
+#!/usr/bin/env python
+"""Diagnostic (2 GPUs): per-parameter gradients of one pipeline-parallel step (pp=2, M micro-batches) against the same
+batch on one GPU.  torchrun --nproc-per-node 2 tools/pp_grad_check.py [--mb 2] [--no-clip]"""
+import argparse
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torchacc_b200 as ta  # noqa: E402
+from torchacc_b200.models import LlamaDecoderLayer, build_llama  # noqa: E402
+from torchacc_b200.parallel.fsdp import ShardingEngine, shard_model  # noqa: E402
+
+
+def tiny(dev):
+    torch.manual_seed(0)
+    with torch.device(dev):
+        return build_llama("tiny", hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=8,
+                           num_key_value_heads=2, head_dim=64, vocab_size=2048, max_position_embeddings=512,
+                           dtype=torch.bfloat16)
+
+
+def grads_of(engine):
+    out = {}
+    for u in engine.units:
+        g = getattr(u.flat_param, "_tb_grad", None)
+        if g is None:
+            g = u.flat_param.grad
+        if g is None:
+            continue
+        for info in u.infos:
+            name = (u.prefix + "." if u.prefix else "") + info.fqn
+            out[name] = g[info.offset:info.offset + info.numel].float().clone()
+    return out
+
+
+def canon(name, layer_offset=0):
+    name = name.replace("model.", "")
+    parts = name.split(".")
+    if parts[0] == "layers":
+        parts[1] = str(int(parts[1]) + layer_offset)
+    return ".".join(parts)
+
+
+def main():
+    p = argparse.ArgumentParser()
+    p.add_argument("--mb", type=int, default=2)
+    a = p.parse_args()
+    rank = int(os.environ["LOCAL_RANK"])
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(0, 2048, (4, 128), generator=g).to(dev)
+    # single GPU
+    ref_model = tiny(dev)
+    eng = ShardingEngine(dev, compute_dtype=torch.bfloat16, strategy="NO_SHARD", grad_mode="compat")
+    root = shard_model(ref_model, eng, (LlamaDecoderLayer,), ())
+    opt = ta.optim.FusedAdamW(eng.flat_parameters(), lr=1e-3)
+    loss = root(input_ids=ids, labels=ids)["loss"]
+    loss.backward()
+    ref = {canon(k): v for k, v in grads_of(eng).items()}
+    ref_norm = float(eng.clip_grad_norm_(1.0))
+    # pipeline
+    model = tiny(dev)
+    cfg = ta.Config()
+    cfg.compute.bf16 = True
+    cfg.dist.pp.size = 2
+    cfg.dist.pp.num_micro_batches = a.mb
+    cfg.dist.pp.split_points = ["model.layers.1"]
+    model = ta.accelerate(model, config=cfg)
+    opt2 = ta.optim.FusedAdamW(model.parameters(), lr=1e-3)
+    pl = model.forward_backward(input_ids=ids, labels=ids, output_fn=lambda out: out["loss"])
+    got = {canon(k, layer_offset=rank): v for k, v in grads_of(model.engine).items()}
+    norm = float(model.clip_grad_norm_(1.0))
+    torch.cuda.synchronize()
+    for r in range(2):
+        dist.barrier()
+        if r != rank:
+            continue
+        print(f"--- rank {rank}: loss single {float(loss):.5f} pp {float(pl) if pl is not None else float('nan'):.5f}  "
+              f"grad norm single {ref_norm:.4f} pp {norm:.4f}", flush=True)
+        for k, v in got.items():
+            if k not in ref:
+                print(f"  {k}: no reference entry ({list(ref)[:3]}...)")
+                continue
+            rv = ref[k]
+            rel = float((v - rv).norm() / (rv.norm() + 1e-12))
+            ratio = float(v.norm() / (rv.norm() + 1e-12))
+            print(f"  {k:45s} |g| {float(v.norm()):.4e} ref {float(rv.norm()):.4e} ratio {ratio:.3f} relerr {rel:.3e}", flush=True)
+    dist.barrier()
+
+
+if __name__ == "__main__":
+    main()
