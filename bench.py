@@ -272,6 +272,8 @@ def run_ours(a):
         if prof is not None:
             try:
                 prof.__exit__(None, None, None)
+                if rank != 0 and a.trace and os.environ.get("TORCHACC_B200_TRACE_ALL", "0") == "1":
+                    prof.export_chrome_trace(a.trace.replace(".json", f".rank{rank}.json"))   # skew diagnostics
                 if rank == 0:
                     path = a.trace or os.path.join("/tmp", f"tb_bench_trace_{os.getpid()}.json")
                     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)

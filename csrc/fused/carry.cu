@@ -33,8 +33,8 @@ double g_bpf = -1.0;
 double bpf_locked() {
   if (g_bpf < 0) {
     const char* e = getenv("TORCHACC_B200_CARRY_BYTES_PER_FLOP");
-    g_bpf = e ? atof(e) : 2.0e-4;
-    if (!(g_bpf >= 0)) g_bpf = 2.0e-4;
+    g_bpf = e ? atof(e) : 1.2e-4;
+    if (!(g_bpf >= 0)) g_bpf = 1.2e-4;
   }
   return g_bpf;
 }
@@ -84,12 +84,12 @@ long long carry_push(int kind, const uint64_t* src, uint64_t dst, const uint64_t
   if (kind == 1) {
     p.chunk_bytes = kCarryStageBytes;
     const long long cps = (bytes + p.chunk_bytes - 1) / p.chunk_bytes;
-    j.total = (uint32_t)(cps * (world - 1));
+    j.total = (uint32_t)(cps * world);              // own shard included: no separate local copy
     j.bytes_per_chunk = (double)p.chunk_bytes;
   } else {
     p.chunk_bytes = (kCarryStageBytes / (uint32_t)world) & ~127u;        // one ring stage holds `world` sub-chunks
     j.total = (uint32_t)((bytes + p.chunk_bytes - 1) / p.chunk_bytes);
-    j.bytes_per_chunk = (double)p.chunk_bytes * (world - 1);
+    j.bytes_per_chunk = (double)p.chunk_bytes * world;      // every source passes through the reducing warp
   }
   j.next = 0;
   // The entry flag ("my source buffer is final") is published HERE, stream-ordered after the kernels that produced the

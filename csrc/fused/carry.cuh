@@ -14,8 +14,10 @@
 //                              squares of the result is accumulated for the global gradient norm (no separate pass)
 //
 // Cross-rank protocol (epoch e of a channel on the symmetric signal pad, see comm/symm_comm.cu for the layout):
-//   entry : the FIRST slice of a job publishes e into slot [ch][rank] of every peer ("my source buffer is final");
-//           every slice waits until all peers have published >= e before touching peer memory.
+//   entry : when a job is ENQUEUED (carry_push, a one-warp kernel ordered after the producers of the source buffer) the
+//           rank publishes e into slot [ch][rank] of every peer ("my source buffer is final"); every slice waits until
+//           all peers have published >= e before touching peer memory.  (Tying the flag to the enqueue point instead
+//           of the first slice keeps ranks whose byte budgets differ from waiting on each other's scheduling.)
 //   exit  : the LAST slice, once every CTA of this rank has finished, publishes e into slot [ch][8 + rank] of every
 //           peer ("I am done reading your buffer") and does NOT wait; whoever is about to overwrite a source buffer
 //           waits for those flags first (symm_wait_done, a one-warp kernel).
@@ -106,7 +108,7 @@ TB_DEVICE void carry_run_slice(const CarrySlice& s, uint32_t ring, uint32_t bars
       const uint32_t cps = (uint32_t)((s.bytes + s.chunk_bytes - 1) / s.chunk_bytes);   // chunks per source shard
       auto locate = [&](uint32_t j, const uint8_t*& sp, uint8_t*& dp, uint32_t& len) {
         const uint32_t c = s.chunk_begin + cta + j * num_ctas;
-        const int r = (s.rank + 1 + (int)(c / cps)) % s.world;
+        const int r = (s.rank + (int)(c / cps)) % s.world;      // own shard first (local copy), then the ring
         const long long off = (long long)(c % cps) * s.chunk_bytes;
         sp = s.src[r] + off;
         dp = s.dst + (long long)r * s.bytes + off;

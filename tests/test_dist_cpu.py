@@ -82,7 +82,7 @@ def test_default_config_is_data_parallel():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def _fsdp_worker(rank, world, hybrid, sp=1, check=None, opt_zero=False):
+def _fsdp_worker(rank, world, hybrid, sp=1, check=None, opt_zero=False, reshard=None):
     import torchacc_b200 as ta
     ids = _data()
     model = _tiny()
@@ -94,8 +94,10 @@ def _fsdp_worker(rank, world, hybrid, sp=1, check=None, opt_zero=False):
         cfg.dist.sp.size = sp
         cfg.dist.sp.mode = "ring"
     cfg.dist.fsdp.wrap_layer_cls = {"LlamaDecoderLayer"}
+    cfg.dist.fsdp.reshard_after_forward = reshard          # None: auto (tiny model -> gathered copies are kept)
     cfg.memory.gc = True
     model = ta.accelerate(model, config=cfg)
+    assert model.engine.keep_gathered == (reshard is not True)
     opt = torch.optim.SGD(model.parameters(), lr=0.1)      # plain torch optimizer on the flat shards
     nrep = world // sp
     local = ids.chunk(nrep)[rank // sp]       # sp is the faster axis: sp peers share one batch shard
@@ -126,6 +128,11 @@ def test_fsdp_matches_single_process():
 
 def test_fsdp_optimizer_zero_grad_starts_fresh_accumulation():
     run_distributed(_fsdp_worker, 2, args=(False, 1, None, True))
+
+
+def test_fsdp_reshard_after_forward_matches_single_process():
+    """classic ZeRO-3: free the gathered parameters after the forward and gather them again for the backward"""
+    run_distributed(_fsdp_worker, 2, args=(False, 1, None, False, True))
 
 
 def test_hsdp_matches_single_process():

@@ -58,6 +58,13 @@ def main():
     eng = ShardingEngine(dev, compute_dtype=torch.bfloat16, strategy="NO_SHARD", grad_mode="compat")
     root = shard_model(ref_model, eng, (LlamaDecoderLayer,), ())
     opt = ta.optim.FusedAdamW(eng.flat_parameters(), lr=1e-3)
+    ref_hidden = []
+    hk = ref_model.model.layers[0].register_forward_hook(lambda m, i, o: ref_hidden.append(o.detach().float().clone()))
+    for part in ids.chunk(a.mb):        # per-micro-batch activations after layer 0 (no grads kept)
+        with torch.no_grad():
+            root(input_ids=part, labels=part)
+    hk.remove()
+    ref_hidden = ref_hidden[:a.mb]
     loss = root(input_ids=ids, labels=ids)["loss"]
     loss.backward()
     ref = {canon(k): v for k, v in grads_of(eng).items()}
@@ -71,7 +78,21 @@ def main():
     cfg.dist.pp.split_points = ["model.layers.1"]
     model = ta.accelerate(model, config=cfg)
     opt2 = ta.optim.FusedAdamW(model.parameters(), lr=1e-3)
+    seen = []
+    stage_mod = model.pp_wrapper.executor.module
+    inner = stage_mod
+    while hasattr(inner, "module") and not hasattr(inner, "layers"):
+        inner = inner.module
+    if rank == 1:
+        inner.register_forward_pre_hook(
+            lambda m, args, kwargs: seen.append(kwargs["hidden"].detach().float().clone()) if "hidden" in kwargs else None,
+            with_kwargs=True)
     pl = model.forward_backward(input_ids=ids, labels=ids, output_fn=lambda out: out["loss"])
+    if rank == 1:
+        for i, h in enumerate(seen):
+            r = ref_hidden[i].reshape(h.shape)
+            print(f"  stage-1 input mb{i}: |h| {float(h.norm()):.4f} ref {float(r.norm()):.4f} relerr "
+                  f"{float((h - r).norm() / r.norm()):.3e}", flush=True)
     got = {canon(k, layer_offset=rank): v for k, v in grads_of(model.engine).items()}
     norm = float(model.clip_grad_norm_(1.0))
     torch.cuda.synchronize()

@@ -207,6 +207,7 @@ class FSDPConfig(Section):
     fp32, dist/fsdp.py:204-208; our peer-memory kernel reads bf16 partials and accumulates in fp32).
     ``fused_collectives``: use the symmetric-memory kernels (all-gather / reduce-scatter over NVLink peer
     memory, fused with cast and the optimizer hand-off) instead of NCCL calls.
+    ``reshard_after_forward``: see the inline comment (torch FSDP's FULL_SHARD vs SHARD_GRAD_OP trade-off).
     """
     _SPEC = {
         "size": (1, ) + _pos_int,
@@ -219,6 +220,10 @@ class FSDPConfig(Section):
         "reduce_dtype": ("fp32", lambda v: v in ("fp32", "bf16"), "must be 'fp32' or 'bf16'"),
         "fused_collectives": (True, ) + _bool,
         "prefetch": (1, lambda v: isinstance(v, int) and v >= 0, "must be an int >= 0"),
+        # None = auto: keep the gathered bf16 parameters of every unit resident from the forward through the backward
+        # (one all-gather per unit and step instead of two) whenever the full bf16 copy of the model is small next to
+        # the 180 GB of HBM3e (<= 20 %); True = classic ZeRO-3 (free after forward, gather again for backward).
+        "reshard_after_forward": (None, lambda v: v is None or isinstance(v, bool), "must be None (auto) or a bool"),
     }
 
     def _cross_validate(self):

@@ -119,6 +119,9 @@ class FusedAdamW(torch.optim.Optimizer):
                     nat.count_launch()
                 else:
                     self._reference_update(p, g, st, group, lp)
+                unit = getattr(p, "_tb_unit", None)
+                if unit is not None:
+                    unit.mark_params_updated()       # gathered copies kept across the step are stale now
         return loss
 
     def _reference_update(self, p, g, st, group, lp):

@@ -68,7 +68,7 @@ class CarryRuntime:
         return buf
 
     def push_gather(self, shard: torch.Tensor, full: torch.Tensor, background: bool = False):
-        """``full[r * n:(r + 1) * n] = shard of rank r`` for every r (this rank's own shard is copied here, now).
+        """``full[r * n:(r + 1) * n] = shard of rank r`` for every r (own shard included, copied first).
         Returns ``(job_id, channel, epoch)``."""
         d = self.domain
         buf = self._buf(shard)
@@ -76,8 +76,6 @@ class CarryRuntime:
         assert nbytes % 16 == 0 and full.numel() == shard.numel() * self.world and full.is_contiguous()
         off = shard.data_ptr() - buf.ptr
         src = (nat.u64 * self.world)(*[buf.peer_ptrs[r] + off for r in range(self.world)])
-        n = shard.numel()
-        full[self.rank * n:(self.rank + 1) * n].copy_(shard)          # local part: plain device copy
         ch = CH_GATHER_BG if background else CH_GATHER
         epoch = d.next_epoch(ch)
         L = nat.require()

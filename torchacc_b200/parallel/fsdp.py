@@ -128,6 +128,7 @@ class FlatParamUnit:
         self.gathered = False
         self.gather_event = None
         self.lp_version = -1
+        self._gathered_version = -1
         self.needs_post_backward = False
 
     @property
@@ -175,7 +176,7 @@ class FlatParamUnit:
         self.lp_version = self.flat_param._version
         if world == 1:
             self.persistent_full = self.lp_shard                        # already the full vector
-        elif not eng.reshard:
+        elif not eng.reshard or eng.keep_gathered:
             self.persistent_full = full.to(lp_dtype)
         else:
             self.persistent_full = None
@@ -216,12 +217,17 @@ class FlatParamUnit:
     def gather(self, prefetch: bool = False, background: bool = False) -> None:
         """Make ``lp_full`` valid (asynchronously on the gather stream when sharded; as a job carried by the following
         GEMM kernels when the engine runs carried collectives)."""
+        eng = self.engine
+        if self.gathered and eng.keep_gathered and eng.shard_world > 1 and \
+                self._gathered_version != self.flat_param._version:
+            self.gathered = False          # an optimizer rewrote the shard since the kept copy was gathered
         if self.gathered:
             return
-        eng = self.engine
         self.refresh_lp_shard()
-        if eng.carry is not None and self.persistent_full is None:
-            buf = eng.lp_pool.acquire(self.padded, eng.compute_dtype)
+        self._gathered_version = self.flat_param._version
+        if eng.carry is not None and (self.persistent_full is None or eng.keep_gathered):
+            buf = self.persistent_full if self.persistent_full is not None else \
+                eng.lp_pool.acquire(self.padded, eng.compute_dtype)
             self._gather_job = eng.carry.push_gather(self.lp_shard, buf, background=background)
             self.gather_event = None
             self.lp_full = buf
@@ -243,6 +249,12 @@ class FlatParamUnit:
             self.gather_event = eng.record_gather_event()
         self.lp_full = buf
         self.gathered = True
+
+    def mark_params_updated(self) -> None:
+        """The optimizer rewrote this unit's shard: a kept gathered copy (``keep_gathered``) is stale now."""
+        if self.engine.keep_gathered and self.engine.shard_world > 1:
+            self.finish_gather()
+            self.gathered = False
 
     def finish_gather(self) -> None:
         """Carried mode: whatever part of this unit's gather no GEMM has taken yet runs now (stand-alone kernel)."""
@@ -276,6 +288,7 @@ class FlatParamUnit:
             self.lp_full = None
             self.gathered = False
         elif self.engine.shard_world > 1:
+            self.finish_gather()
             self.gathered = False  # contents go stale after the next optimizer step
 
     # ---- gradients ------------------------------------------------------------------------------------
@@ -530,7 +543,8 @@ class ShardingEngine:
 
     def __init__(self, device: torch.device, shard_group=None, replica_group=None, compute_dtype=torch.bfloat16,
                  strategy: str = "FULL_SHARD", sync_module_states: bool = False, reduce_dtype: str = "fp32",
-                 prefetch: int = 1, prefer_symm: bool = True, grad_mode: str = "compat"):
+                 prefetch: int = 1, prefer_symm: bool = True, grad_mode: str = "compat",
+                 reshard_after_forward: Optional[bool] = None, model_numel: int = 0):
         self.device = device
         self.compute_dtype = compute_dtype
         self.strategy = strategy
@@ -550,6 +564,22 @@ class ShardingEngine:
         self.all_group = shard_group if shard_group is not None else replica_group
         self.world_all = self.world_data
         self.reshard = strategy in ("FULL_SHARD", "HYBRID") and self.shard_world > 1
+        # keep_gathered: parameters stay sharded (ZeRO-3 memory for master weights / optimizer state / gradients) but
+        # the gathered compute copy of every unit lives in its own persistent buffer from the forward until the end
+        # of the backward -- one all-gather per unit and step instead of two.  Auto: on when that full copy is at most
+        # 20 % of the device memory (Llama-3-8B: 16 GB of 180 GB); a 70 B model falls back to re-gathering.
+        self.keep_gathered = False
+        if self.reshard:
+            if reshard_after_forward is None:
+                import os as _os0
+                env = _os0.environ.get("TORCHACC_B200_RESHARD_AFTER_FORWARD", "")
+                if env in ("0", "1"):
+                    reshard_after_forward = env == "1"
+            if reshard_after_forward is None:
+                total = torch.cuda.get_device_properties(device).total_memory if device.type == "cuda" else (64 << 30)
+                item = 4 if compute_dtype == torch.float32 else 2
+                reshard_after_forward = not (0 < model_numel * item <= 0.2 * total)
+            self.keep_gathered = not reshard_after_forward
         self.root_unit = None
         self.stats = {}                      # diagnostics (e.g. 'wgrad_fallbacks': wgrads that missed the flat buffer)
         self.shard_coll: Collectives = make_collectives(shard_group, device, prefer_symm)
@@ -709,7 +739,8 @@ class ShardingEngine:
     def post_forward(self, unit: FlatParamUnit):
         if self.carry is not None and self.head_unit is not None and self._is_last_forward_unit(unit):
             self.head_unit.finish_gather()
-        if self.reshard and unit is not self.root_unit and not self._is_last_forward_unit(unit):
+        if self.reshard and not self.keep_gathered and unit is not self.root_unit \
+                and not self._is_last_forward_unit(unit):
             unit.reshard()
 
     def _is_last_forward_unit(self, unit):
@@ -758,7 +789,7 @@ class ShardingEngine:
                 self._deferred_reduces.append(unit)
         else:
             unit.reduce_grads()
-        if self.reshard:
+        if self.reshard and not self.keep_gathered:
             unit.reshard()
 
     def register_final_callback_unit(self, unit: FlatParamUnit):
@@ -791,12 +822,13 @@ class ShardingEngine:
             if unit.grad_full is None:
                 unit.prepare_grad_buffer()
             unit.reduce_grads()
-            if self.reshard:
+            if self.reshard and not self.keep_gathered:
                 unit.reshard()
         for unit in self.units:  # anything still gathered from prefetch
             if self.reshard and unit.gathered:
                 unit.finish_gather()
-                unit.reshard()
+                if not self.keep_gathered:       # kept copies stay valid until an optimizer rewrites the shard
+                    unit.reshard()
         if self.carry is not None:
             c = self.carry
             left = c.pending()

@@ -60,7 +60,9 @@ class _EngineModule(ParallelModule):
                                      compute_dtype=compute_dtype, strategy=self.STRATEGY,
                                      sync_module_states=c.dist.fsdp.sync_module_states,
                                      reduce_dtype=c.dist.fsdp.reduce_dtype, prefetch=c.dist.fsdp.prefetch,
-                                     prefer_symm=c.dist.fsdp.fused_collectives)
+                                     prefer_symm=c.dist.fsdp.fused_collectives,
+                                     reshard_after_forward=getattr(c.dist.fsdp, "reshard_after_forward", None),
+                                     model_numel=sum(p.numel() for p in model.parameters()))
         root = shard_model(model, self.engine, wrap, gc_cls, c.memory.gc_cnt)
         self.model = _AutocastModel(root, compute_dtype if compute_dtype != torch.float32 else None, self.device.type)
         # the optimizer-visible parameters: one fp32 flat shard per unit
