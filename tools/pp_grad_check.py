@@ -84,15 +84,61 @@ def main():
     while hasattr(inner, "module") and not hasattr(inner, "layers"):
         inner = inner.module
     if rank == 1:
-        inner.register_forward_pre_hook(
-            lambda m, args, kwargs: seen.append(kwargs["hidden"].detach().float().clone()) if "hidden" in kwargs else None,
-            with_kwargs=True)
+        seen_kw = []
+
+        def _hook(m, args, kwargs):
+            if "hidden" in kwargs and len(seen_kw) < 4:
+                seen.append(kwargs["hidden"].detach().float().clone())
+                seen_kw.append({k: (v.detach().clone() if isinstance(v, torch.Tensor) else v) for k, v in kwargs.items()})
+                print("  stage-1 call kwargs:", {k: (tuple(v.shape), str(v.dtype), v.stride()) if isinstance(v, torch.Tensor)
+                                                  else v for k, v in kwargs.items()}, "grad", torch.is_grad_enabled(),
+                      "autocast", torch.is_autocast_enabled(), flush=True)
+        inner.register_forward_pre_hook(_hook, with_kwargs=True)
+        inner.register_forward_hook(lambda m, a, o: print("  stage-1 forward returned loss", float(o["loss"]), flush=True))
     pl = model.forward_backward(input_ids=ids, labels=ids, output_fn=lambda out: out["loss"])
     if rank == 1:
         for i, h in enumerate(seen):
             r = ref_hidden[i].reshape(h.shape)
             print(f"  stage-1 input mb{i}: |h| {float(h.norm()):.4f} ref {float(r.norm()):.4f} relerr "
                   f"{float((h - r).norm() / r.norm()):.3e}", flush=True)
+    if rank == 1:
+        # weights of this stage vs the single-GPU model, and both halves run directly on the captured input
+        ref_l1 = ref_model.model.layers[1]
+        ref_l1 = getattr(ref_l1, "module", ref_l1)
+        for (n1, p1), (n2, p2) in zip(inner.layers[0].named_parameters(recurse=True) if False else
+                                       [(i.fqn, i.tensor) for i in model.engine.units[-1].infos],
+                                       [(i.fqn, i.tensor) for u in eng.units for i in u.infos
+                                        if (u.prefix + "." + i.fqn).startswith("model.layers.1") or u.prefix == ""
+                                        and ("norm" in i.fqn or "lm_head" in i.fqn)]):
+            print(f"  weight {n1:42s} vs {n2:42s} maxdiff {float((p1.float() - p2.float()).abs().max()):.3e}", flush=True)
+        with torch.no_grad():
+            hid = seen[0]
+            lab_ids = ids.chunk(a.mb)[0]
+            out_stage = inner(hidden=hid.to(torch.bfloat16), labels=lab_ids)["loss"]
+            core = ref_model.model
+            core = getattr(core, "module", core)
+            B, S = hid.shape[0], hid.shape[1]
+            h2 = ref_l1(hid.to(torch.bfloat16).reshape(B * S, -1), core.rope(hid.device), B, S, None, None, core.pctx)
+            from torchacc_b200.ops import fused_linear_cross_entropy, rmsnorm
+            y2, _ = rmsnorm(h2, core.norm.weight, core.norm.eps)
+            lab = torch.full_like(lab_ids, -100)
+            lab[:, :-1] = lab_ids[:, 1:]
+            l2 = fused_linear_cross_entropy(y2, ref_model.lm_head.weight, lab.reshape(-1))
+            print(f"  direct: stage module loss {float(out_stage):.5f}  reference second half {float(l2):.5f}", flush=True)
+        kw0 = seen_kw[0]
+        print("  labels equal ids chunk:", bool(torch.equal(kw0["labels"], lab_ids)), flush=True)
+        with torch.no_grad():
+            print("  replay of the captured kwargs:", float(inner(**kw0)["loss"]), flush=True)
+        hb = hid.to(torch.bfloat16)
+        la = float(inner(hidden=hb.clone().requires_grad_(), labels=lab_ids)["loss"])
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            lb = float(inner(hidden=hb.clone().requires_grad_(), labels=lab_ids)["loss"])
+        lc = float(model.pp_wrapper.executor.module(hidden=hb.clone().requires_grad_(), labels=lab_ids)["loss"])
+        with torch.no_grad():
+            ld = float(model.pp_wrapper.executor.module(hidden=hb.clone(), labels=lab_ids)["loss"])
+        r1, r2 = inner._owner[0].rope(hid.device), core.rope(hid.device)
+        print(f"  grad-mode {la:.5f}  grad+autocast {lb:.5f}  through engine {lc:.5f}  engine no_grad {ld:.5f}  "
+              f"rope diff {float((r1[0] - r2[0]).abs().max()):.3e}", flush=True)
     got = {canon(k, layer_offset=rank): v for k, v in grads_of(model.engine).items()}
     norm = float(model.clip_grad_norm_(1.0))
     torch.cuda.synchronize()

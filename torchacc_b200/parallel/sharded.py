@@ -19,10 +19,14 @@ class _AutocastModel(nn.Module):
     """Runs the model under autocast(compute dtype) and returns fp32 floating outputs, like the reference's FSDP
     forward wrapper (dist/fsdp.py:172-180, utils/utils.py:281-339)."""
 
-    def __init__(self, model: nn.Module, dtype: Optional[torch.dtype], device_type: str):
+    def __init__(self, model: nn.Module, dtype: Optional[torch.dtype], device_type: str, fp32_outputs: bool = True):
         super().__init__()
         self.model = model
         self.dtype, self.device_type = dtype, device_type
+        # intermediate pipeline stages hand their activations to the next stage in the compute dtype: converting them
+        # to fp32 doubled the p2p bytes AND pushed the next stage onto the non-native fp32 fallback ops (found on 2
+        # B200 in round 2: profiles/pp_gpu_r2.txt)
+        self.fp32_outputs = fp32_outputs
 
     def __getattr__(self, name):
         try:
@@ -36,6 +40,8 @@ class _AutocastModel(nn.Module):
                 out = self.model(*args, **kwargs)
         else:
             out = self.model(*args, **kwargs)
+        if not self.fp32_outputs:
+            return out
         from ..utils.utils import convert_to_fp32
         return convert_to_fp32(out)
 
@@ -64,7 +70,9 @@ class _EngineModule(ParallelModule):
                                      reshard_after_forward=getattr(c.dist.fsdp, "reshard_after_forward", None),
                                      model_numel=sum(p.numel() for p in model.parameters()))
         root = shard_model(model, self.engine, wrap, gc_cls, c.memory.gc_cnt)
-        self.model = _AutocastModel(root, compute_dtype if compute_dtype != torch.float32 else None, self.device.type)
+        last_stage = self.mesh.get_pp_num() == 1 or self.mesh.is_last_stage()
+        self.model = _AutocastModel(root, compute_dtype if compute_dtype != torch.float32 else None, self.device.type,
+                                    fp32_outputs=last_stage)
         # the optimizer-visible parameters: one fp32 flat shard per unit
         self.flat_params = nn.ParameterList(self.engine.flat_parameters())
 
