@@ -286,6 +286,20 @@ def run_ours(a):
             except Exception as e:  # noqa: BLE001  -- diagnostics must never break the benchmark line
                 comm = {"error": f"{type(e).__name__}: {e}"[:200]}
 
+    dbg_path = os.environ.get("TORCHACC_B200_CARRY_DEBUG", "")
+    if dbg_path and world > 1:
+        # in-kernel timestamps of the copy warp of CTA 0 for every carrying GEMM launch of ONE extra (untimed) step
+        nrec = 4096
+        buf = torch.zeros(nrec * 8, dtype=torch.int64, device=device)
+        L = nat.require()
+        L.tb_carry_set_debug(buf.data_ptr(), nrec)
+        step()
+        torch.cuda.synchronize(device)
+        used = L.tb_carry_set_debug(0, 0)
+        rec = buf.view(nrec, 8)[:used].cpu().tolist()
+        with open(dbg_path.replace(".json", f".rank{rank}.json"), "w") as f:
+            json.dump({"fields": ["start", "s0_entry", "s0_done", "s1_entry", "s1_done", "chunks", "kinds", "end"],
+                       "records": rec}, f)
     carry_counters = None
     try:
         from torchacc_b200.parallel.carry import CarryRuntime, available

@@ -203,3 +203,6 @@ TB_API int tb_carry_stats(long long* out4, int reset) {
 TB_API int tb_symm_wait_done(const uint64_t* pads, int rank, int world, int channel, uint32_t epoch, uint64_t stream) {
   return (int)tb::symm_wait_done(pads, rank, world, channel, epoch, S(stream));
 }
+TB_API long long tb_carry_set_debug(uint64_t buf, long long records) {
+  return tb::carry_set_debug(P<unsigned long long>(buf), records);
+}

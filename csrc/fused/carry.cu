@@ -28,6 +28,8 @@ std::mutex g_mu;             // forward runs on the main thread, backward on aut
 std::deque<Job> g_queues[2];
 long long g_next_id = 1;
 long long g_stats[4] = {0, 0, 0, 0};
+unsigned long long* g_debug = nullptr;   // device buffer of g_debug_cap records (8 x u64 each), see CarryArgs::debug
+long long g_debug_cap = 0, g_debug_next = 0;
 double g_bpf = -1.0;
 
 double bpf_locked() {
@@ -126,7 +128,10 @@ int carry_take(double flops, CarryArgs* out) {
       else break;
     }
   }
-  if (n > 0) ++g_stats[2];
+  if (n > 0) {
+    ++g_stats[2];
+    if (g_debug != nullptr && g_debug_next < g_debug_cap) out->debug = g_debug + 8 * g_debug_next++;
+  }
   return n;
 }
 
@@ -139,6 +144,13 @@ long long carry_pending(long long job_id, int queue) {
       if (job_id == 0 || j.id <= job_id) c += j.total - j.next;
   }
   return c;
+}
+
+long long carry_set_debug(unsigned long long* buf, long long records) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  const long long used = g_debug_next;
+  g_debug = buf; g_debug_cap = records; g_debug_next = 0;
+  return used;
 }
 
 void carry_stats(long long* out4, int reset) {

@@ -58,7 +58,17 @@ struct CarrySlice {
 
 struct CarryArgs {
   CarrySlice slice[kCarrySlots];
+  // optional timing record of CTA 0 (tb_carry_set_debug): per launch 8 x u64 globaltimer ns
+  //   [0] role start  [1] slice 0 entry passed  [2] slice 0 done  [3] slice 1 entry passed  [4] slice 1 done
+  //   [5] chunks of slice 0 | chunks of slice 1 << 32   [6] kinds   [7] launch index
+  unsigned long long* debug;
 };
+
+TB_DEVICE unsigned long long carry_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 TB_DEVICE void carry_st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -88,7 +98,8 @@ TB_DEVICE void spin_until_epoch(const uint32_t* flag, uint32_t epoch, int my_ran
 
 // One warp.  `ring` / `bars`: shared-memory addresses of kCarryStages x kCarryStageBytes bytes and kCarryStages
 // mbarriers (initialised by the caller with count 1).  `it` is the ring position carried across slices of one launch.
-TB_DEVICE void carry_run_slice(const CarrySlice& s, uint32_t ring, uint32_t bars, uint32_t& it, int cta, int num_ctas) {
+TB_DEVICE void carry_run_slice(const CarrySlice& s, uint32_t ring, uint32_t bars, uint32_t& it, int cta, int num_ctas,
+                                unsigned long long* dbg = nullptr) {
   const uint32_t lane = lane_id();
   constexpr uint32_t kSlotBase = 16;   // pad slots per channel: [0,8) entry, [8,16) exit
   // ---- entry ----
@@ -100,6 +111,7 @@ TB_DEVICE void carry_run_slice(const CarrySlice& s, uint32_t ring, uint32_t bars
     spin_until_epoch(s.pads[s.rank] + s.channel * kSlotBase + lane, s.epoch, s.rank, (int)lane, s.channel, "carry entry");
   __syncwarp();
   asm volatile("fence.proxy.async;" ::: "memory");   // peers' generic-proxy writes (acquired above) -> TMA reads
+  if (dbg != nullptr && lane == 0) dbg[0] = carry_now_ns();
 
   const uint32_t n = s.chunk_end > s.chunk_begin ? s.chunk_end - s.chunk_begin : 0;
   const uint32_t mine = n > (uint32_t)cta ? (n - cta + num_ctas - 1) / num_ctas : 0;   // chunks begin+cta, +num_ctas...
@@ -265,6 +277,7 @@ TB_DEVICE void carry_run_slice(const CarrySlice& s, uint32_t ring, uint32_t bars
     }
     __syncwarp();
   }
+  if (dbg != nullptr && lane == 0) dbg[1] = carry_now_ns();
   // ---- exit ----
   if (s.signal_exit) {
     uint32_t last = 0;
@@ -290,9 +303,17 @@ TB_DEVICE void carry_role(const CarryArgs& ca, uint32_t ring, uint32_t bars, int
   }
   __syncwarp();
   uint32_t it = 0;
+  unsigned long long* dbg = (ca.debug != nullptr && cta == 0) ? ca.debug : nullptr;
+  if (dbg != nullptr && lane_id() == 0) {
+    dbg[0] = carry_now_ns();
+    dbg[5] = (unsigned long long)(ca.slice[0].chunk_end - ca.slice[0].chunk_begin) |
+             ((unsigned long long)(ca.slice[1].chunk_end - ca.slice[1].chunk_begin) << 32);
+    dbg[6] = (unsigned long long)ca.slice[0].kind | ((unsigned long long)ca.slice[1].kind << 8);
+  }
 #pragma unroll 1
   for (int i = 0; i < kCarrySlots; ++i)
-    if (ca.slice[i].kind != 0) carry_run_slice(ca.slice[i], ring, bars, it, cta, num_ctas);
+    if (ca.slice[i].kind != 0)
+      carry_run_slice(ca.slice[i], ring, bars, it, cta, num_ctas, dbg != nullptr ? dbg + 1 + 2 * i : nullptr);
 }
 
 }  // namespace tb

@@ -33,6 +33,10 @@ double carry_bytes_per_flop(double v);
 cudaError_t symm_wait_done(const uint64_t* pad_ptrs, int rank, int world, int channel, uint32_t epoch,
                            cudaStream_t stream);
 
+// Timing records of carrying GEMM launches (CTA 0's copy warp, globaltimer ns; layout: CarryArgs::debug).  Pass a
+// device buffer of `records` x 8 u64 (nullptr disables); returns how many records the previous buffer received.
+long long carry_set_debug(unsigned long long* buf, long long records);
+
 // statistics: [0] chunks carried by GEMMs, [1] chunks flushed stand-alone, [2] GEMM launches that carried, [3] flushes
 void carry_stats(long long* out4, int reset);
 

@@ -600,6 +600,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tc_fence_after();
     tmem_dealloc<kCluster>(tmem_base, 512);
   }
+  if constexpr (kFuse == 0) {
+    if (args.carry.debug != nullptr && blockIdx.x == 0 && threadIdx.x == 0) args.carry.debug[7] = carry_now_ns();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------
