@@ -187,9 +187,9 @@ TB_API int tb_rs_reduce_bf16(uint64_t stage, uint64_t counters, uint32_t expecte
 TB_API long long tb_carry_push(int kind, const uint64_t* src, uint64_t dst, const uint64_t* pads, long long bytes,
                                int rank, int world, int channel, uint32_t epoch, uint64_t block_counter, float scale,
                                int in_bf16, int out_fp32, int accumulate, uint64_t stats, int background,
-                               uint64_t stream) {
+                               int entry_channel, uint32_t entry_epoch) {
   return tb::carry_push(kind, src, dst, pads, bytes, rank, world, channel, epoch, block_counter, scale, in_bf16, out_fp32,
-                        accumulate, stats, background, S(stream));
+                        accumulate, stats, background, entry_channel, entry_epoch);
 }
 TB_API long long tb_carry_pending(long long job_id, int queue) { return tb::carry_pending(job_id, queue); }
 TB_API int tb_carry_flush(long long job_id, int queue, int num_sms, uint64_t stream) {
@@ -205,4 +205,7 @@ TB_API int tb_symm_wait_done(const uint64_t* pads, int rank, int world, int chan
 }
 TB_API long long tb_carry_set_debug(uint64_t buf, long long records) {
   return tb::carry_set_debug(P<unsigned long long>(buf), records);
+}
+TB_API int tb_symm_signal(const uint64_t* pads, int rank, int world, int channel, uint32_t epoch, uint64_t stream) {
+  return (int)tb::symm_signal(pads, rank, world, channel, epoch, S(stream));
 }

@@ -46,7 +46,7 @@ void fill_slice(Job& j, uint32_t n, CarrySlice& out) {
   out = j.proto;
   out.chunk_begin = j.next;
   out.chunk_end = j.next + n;
-  out.signal_entry = 0;      // published at push time (carry_push)
+  out.signal_entry = 0;      // published by symm_signal when the source data became final
   out.signal_exit = (j.next + n == j.total) ? 1 : 0;
   j.next += n;
 }
@@ -59,21 +59,35 @@ double carry_bytes_per_flop(double v) {
   return bpf_locked();
 }
 
-__global__ void __launch_bounds__(32) signal_entry_kernel(const CarrySlice s) {
-  if ((int)threadIdx.x < s.world) {
+struct SignalArgs {
+  uint32_t* pads[kCarryMaxWorld];
+};
+__global__ void __launch_bounds__(32) signal_entry_kernel(const SignalArgs a, int rank, int world, int channel,
+                                                          uint32_t epoch) {
+  if ((int)threadIdx.x < world) {
     __threadfence_system();
-    carry_st_release_sys(s.pads[threadIdx.x] + s.channel * 16 + s.rank, s.epoch);
+    carry_st_release_sys(a.pads[threadIdx.x] + channel * 16 + rank, epoch);
   }
+}
+
+cudaError_t symm_signal(const uint64_t* pad_ptrs, int rank, int world, int channel, uint32_t epoch, cudaStream_t stream) {
+  if (world > kCarryMaxWorld || rank < 0 || rank >= world) return cudaErrorInvalidValue;
+  SignalArgs a;
+  for (int r = 0; r < kCarryMaxWorld; ++r) a.pads[r] = r < world ? reinterpret_cast<uint32_t*>(pad_ptrs[r]) : nullptr;
+  signal_entry_kernel<<<1, 32, 0, stream>>>(a, rank, world, channel, epoch);
+  return cudaGetLastError();
 }
 
 long long carry_push(int kind, const uint64_t* src, uint64_t dst, const uint64_t* pads, long long bytes, int rank,
                      int world, int channel, uint32_t epoch, uint64_t block_counter, float scale, int in_bf16,
-                     int out_fp32, int accumulate, uint64_t stats, int background, cudaStream_t stream) {
+                     int out_fp32, int accumulate, uint64_t stats, int background, int entry_channel,
+                     uint32_t entry_epoch) {
   if ((kind != 1 && kind != 2) || world < 2 || world > kCarryMaxWorld || bytes <= 0 || bytes % 16 != 0) return -1;
   Job j;
   memset(&j.proto, 0, sizeof(j.proto));
   CarrySlice& p = j.proto;
   p.kind = kind; p.rank = rank; p.world = world; p.channel = channel; p.epoch = epoch;
+  p.entry_channel = entry_channel; p.entry_epoch = entry_epoch;
   for (int r = 0; r < world; ++r) {
     p.src[r] = reinterpret_cast<const uint8_t*>(src[r]) + (kind == 2 ? (long long)rank * bytes : 0ll);
     p.pads[r] = reinterpret_cast<uint32_t*>(pads[r]);
@@ -94,13 +108,6 @@ long long carry_push(int kind, const uint64_t* src, uint64_t dst, const uint64_t
     j.bytes_per_chunk = (double)p.chunk_bytes * world;      // every source passes through the reducing warp
   }
   j.next = 0;
-  // The entry flag ("my source buffer is final") is published HERE, stream-ordered after the kernels that produced the
-  // buffer, not by the first slice: which launch carries the first slice depends on rank-local byte budgets (token
-  // counts may differ between ranks), and two ranks that interleave foreground and background jobs differently would
-  // otherwise wait for each other's first slices in a cycle.  With the flag tied to the push point, a kernel only ever
-  // waits for peers to REACH a program point they reach without waiting for anything this rank has not yet published.
-  signal_entry_kernel<<<1, 32, 0, stream>>>(p);
-  if (cudaGetLastError() != cudaSuccess) return -2;
   std::lock_guard<std::mutex> lk(g_mu);
   j.id = g_next_id++;
   g_queues[background ? 1 : 0].push_back(j);

@@ -14,10 +14,13 @@
 //                              squares of the result is accumulated for the global gradient norm (no separate pass)
 //
 // Cross-rank protocol (epoch e of a channel on the symmetric signal pad, see comm/symm_comm.cu for the layout):
-//   entry : when a job is ENQUEUED (carry_push, a one-warp kernel ordered after the producers of the source buffer) the
-//           rank publishes e into slot [ch][rank] of every peer ("my source buffer is final"); every slice waits until
-//           all peers have published >= e before touching peer memory.  (Tying the flag to the enqueue point instead
-//           of the first slice keeps ranks whose byte budgets differ from waiting on each other's scheduling.)
+//   entry : a rank publishes "my source buffer is final" (symm_signal, a one-warp kernel ordered after the producers
+//           of the buffer) into slot [entry channel][rank] of every peer -- for gradients when a unit's backward ends,
+//           for parameter shards ONCE per step after the optimizer; every slice waits until all peers have published
+//           >= its entry epoch before touching peer memory.  The flag is tied to the point where the data becomes
+//           final, not to the launch that happens to carry the first slice: ranks whose byte budgets differ never
+//           wait on each other's scheduling, and a job may be enqueued later than its data is ready (slack against
+//           GPUs that run a phase a few percent slower, see profiles/carry_skew_n2_r2.txt).
 //   exit  : the LAST slice, once every CTA of this rank has finished, publishes e into slot [ch][8 + rank] of every
 //           peer ("I am done reading your buffer") and does NOT wait; whoever is about to overwrite a source buffer
 //           waits for those flags first (symm_wait_done, a one-warp kernel).
@@ -41,8 +44,10 @@ constexpr int kCarrySlots = 2;                                              // s
 struct CarrySlice {
   int kind;                               // 0 none, 1 all-gather copy, 2 reduce-scatter
   int rank, world;
-  int channel;
+  int channel;                            // exit ("done") flags: slot [channel][8 + rank] = epoch
   uint32_t epoch;
+  int entry_channel;                      // entry ("source buffers are final") flags: slot [entry_channel][rank] >=
+  uint32_t entry_epoch;                   //   entry_epoch on every rank before peer memory is touched
   int signal_entry, signal_exit;
   const uint8_t* src[kCarryMaxWorld];     // kind 1: peer r's shard; kind 2: peer r's flat buffer + rank * bytes
   uint8_t* dst;                           // kind 1: gathered buffer (shard r at dst + r * bytes); kind 2: output shard
@@ -105,10 +110,11 @@ TB_DEVICE void carry_run_slice(const CarrySlice& s, uint32_t ring, uint32_t bars
   // ---- entry ----
   if (s.signal_entry && cta == 0 && (int)lane < s.world) {
     __threadfence_system();
-    carry_st_release_sys(s.pads[lane] + s.channel * kSlotBase + s.rank, s.epoch);
+    carry_st_release_sys(s.pads[lane] + s.entry_channel * kSlotBase + s.rank, s.entry_epoch);
   }
   if ((int)lane < s.world)
-    spin_until_epoch(s.pads[s.rank] + s.channel * kSlotBase + lane, s.epoch, s.rank, (int)lane, s.channel, "carry entry");
+    spin_until_epoch(s.pads[s.rank] + s.entry_channel * kSlotBase + lane, s.entry_epoch, s.rank, (int)lane,
+                     s.entry_channel, "carry entry");
   __syncwarp();
   asm volatile("fence.proxy.async;" ::: "memory");   // peers' generic-proxy writes (acquired above) -> TMA reads
   if (dbg != nullptr && lane == 0) dbg[0] = carry_now_ns();

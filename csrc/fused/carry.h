@@ -13,7 +13,12 @@ struct CarryArgs;
 //   kind 2: src[r] = peer r's flat buffer (world * bytes, this rank's slice at + rank * bytes), dst = output shard
 long long carry_push(int kind, const uint64_t* src, uint64_t dst, const uint64_t* pads, long long bytes, int rank,
                      int world, int channel, uint32_t epoch, uint64_t block_counter, float scale, int in_bf16,
-                     int out_fp32, int accumulate, uint64_t stats, int background, cudaStream_t stream);
+                     int out_fp32, int accumulate, uint64_t stats, int background, int entry_channel,
+                     uint32_t entry_epoch);
+
+// Publish `epoch` in this rank's ENTRY slot of `channel` on every peer's signal pad, ordered after the work already
+// queued on `stream` ("the buffers jobs with this entry epoch read from me are final").
+cudaError_t symm_signal(const uint64_t* pad_ptrs, int rank, int world, int channel, uint32_t epoch, cudaStream_t stream);
 
 // Called by the GEMM launcher: move up to `flops * bytes_per_flop` bytes worth of pending chunks into `out`.
 // Returns the number of slices filled (0 = nothing to carry).

@@ -95,8 +95,11 @@ def test_carried_collectives_match_reference():
     ref_y = (a.float() @ b.float().t())
     CarryRuntime.counters(reset=True)
     rt.arm_stats()
+    rt.publish_params()                           # "my shards are final" (once per step in the engine)
     jg = rt.push_gather(shard, full)
-    jr = rt.push_reduce(grads, out, 1.0 / WORLD, accumulate=False)
+    e = rt.publish_grads()                        # "my gradient buffer is final" ...
+    ys0 = gemm(a, b)                              # ... the job may be enqueued later than that
+    jr = rt.push_reduce(grads, out, 1.0 / WORLD, accumulate=False, epoch=e)
     ys = [gemm(a, b) for _ in range(6)]           # 6 x 137 GFLOP: carries most of the 2 x 12 MB x (W-1)
     rt.flush()                                    # whatever is left
     rt.wait_done(jg[1], jg[2])
@@ -112,10 +115,10 @@ def test_carried_collectives_match_reference():
     assert torch.allclose(out, ref_out, atol=1e-5, rtol=1e-5), float((out - ref_out).abs().max())
     assert torch.allclose(rt.stats[0], (ref_out.double() ** 2).sum().float(), rtol=1e-4), (rt.stats, (ref_out ** 2).sum())
     assert float(rt.stats[1]) == 0.0
-    for y in ys:
+    for y in ys + [ys0]:
         assert torch.allclose(y.float(), ref_y, atol=2.0, rtol=2e-2)
     # accumulate into the existing shard + everything through the stand-alone kernel
-    jr2 = rt.push_reduce(grads, out, 1.0 / WORLD, accumulate=True)
+    jr2 = rt.push_reduce(grads, out, 1.0 / WORLD, accumulate=True, epoch=rt.publish_grads())
     rt.flush(jr2[0], BACKGROUND)
     rt.wait_done(jr2[1], jr2[2])
     torch.cuda.synchronize()

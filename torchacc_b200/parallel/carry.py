@@ -27,8 +27,9 @@ from .. import _native as nat
 
 nat.register_signatures({
     "tb_carry_push": ([nat.i32, ctypes.POINTER(nat.u64), nat.u64, ctypes.POINTER(nat.u64), nat.i64, nat.i32, nat.i32,
-                       nat.i32, ctypes.c_uint32, nat.u64, nat.f32, nat.i32, nat.i32, nat.i32, nat.u64, nat.i32, nat.u64],
-                      nat.i64),
+                       nat.i32, ctypes.c_uint32, nat.u64, nat.f32, nat.i32, nat.i32, nat.i32, nat.u64, nat.i32, nat.i32,
+                       ctypes.c_uint32], nat.i64),
+    "tb_symm_signal": ([ctypes.POINTER(nat.u64), nat.i32, nat.i32, nat.i32, ctypes.c_uint32, nat.u64], nat.i32),
     "tb_carry_pending": ([nat.i64, nat.i32], nat.i64),
     "tb_carry_flush": ([nat.i64, nat.i32, nat.i32, nat.u64], nat.i32),
     "tb_carry_bytes_per_flop": ([ctypes.c_double], ctypes.c_double),
@@ -37,8 +38,9 @@ nat.register_signatures({
     "tb_symm_wait_done": ([ctypes.POINTER(nat.u64), nat.i32, nat.i32, nat.i32, ctypes.c_uint32, nat.u64], nat.i32),
 })
 
-# signal-pad channels (parallel/symm_mem.py uses 0-3, fused TP 8+)
-CH_GATHER, CH_REDUCE, CH_GATHER_BG = 4, 5, 6
+# signal-pad channels (parallel/symm_mem.py uses 0-3, fused TP 8+).  CH_PARAMS carries only ENTRY flags: "my parameter
+# shards of this step are final" -- one epoch per step, every gather job of the step waits for it.
+CH_GATHER, CH_REDUCE, CH_GATHER_BG, CH_PARAMS = 4, 5, 6, 7
 FOREGROUND, BACKGROUND, ALL_QUEUES = 0, 1, -1
 
 
@@ -60,6 +62,7 @@ class CarryRuntime:
         self.reduce_jobs = 0                  # reduce-scatters pushed since the statistics were armed
         self.stats_exact = True               # False once a job accumulated into an existing shard (micro-batching)
         self.last_epoch = {CH_GATHER: 0, CH_REDUCE: 0, CH_GATHER_BG: 0}
+        self.params_epoch = 0
 
     # ---- submission ---------------------------------------------------------------------------------------
     def _buf(self, t: torch.Tensor):
@@ -68,9 +71,30 @@ class CarryRuntime:
             raise RuntimeError("carried collectives need their peer-visible operand inside the symmetric domain")
         return buf
 
+    def _signal(self, channel: int, epoch: int) -> None:
+        d = self.domain
+        nat.check(nat.require().tb_symm_signal(d.pad_ptrs, self.rank, self.world, channel, epoch, nat.stream()),
+                  "tb_symm_signal")
+        nat.count_launch()
+
+    def publish_params(self) -> int:
+        """Tell every peer that ALL parameter shards of this rank are final for the coming step (call once per step,
+        after the optimizer / the bf16 refresh of every unit).  Gather jobs pushed afterwards wait for this epoch on
+        every rank -- they never depend on how far a peer has progressed inside the step."""
+        self.params_epoch = self.domain.next_epoch(CH_PARAMS)
+        self._signal(CH_PARAMS, self.params_epoch)
+        return self.params_epoch
+
+    def publish_grads(self) -> int:
+        """Tell every peer that the flat gradient buffer of the unit whose backward just ended is final.  Returns the
+        epoch the (possibly later enqueued) reduce job has to be pushed with."""
+        epoch = self.domain.next_epoch(CH_REDUCE)
+        self._signal(CH_REDUCE, epoch)
+        return epoch
+
     def push_gather(self, shard: torch.Tensor, full: torch.Tensor, background: bool = False):
         """``full[r * n:(r + 1) * n] = shard of rank r`` for every r (own shard included, copied first).
-        Returns ``(job_id, channel, epoch)``."""
+        Needs ``publish_params()`` of this step.  Returns ``(job_id, channel, epoch)``."""
         d = self.domain
         buf = self._buf(shard)
         nbytes = shard.numel() * shard.element_size()
@@ -81,15 +105,16 @@ class CarryRuntime:
         epoch = d.next_epoch(ch)
         L = nat.require()
         job = L.tb_carry_push(1, src, full.data_ptr(), d.pad_ptrs, nbytes, self.rank, self.world, ch, epoch,
-                              d.counter_ptr(ch), 1.0, 0, 0, 0, 0, int(background), nat.stream())
+                              d.counter_ptr(ch), 1.0, 0, 0, 0, 0, int(background), CH_PARAMS, self.params_epoch)
         if job <= 0:
             raise nat.NativeError("tb_carry_push (gather) rejected the job")
         self.last_epoch[ch] = epoch
         return job, ch, epoch
 
-    def push_reduce(self, full: torch.Tensor, out: torch.Tensor, scale: float, accumulate: bool):
+    def push_reduce(self, full: torch.Tensor, out: torch.Tensor, scale: float, accumulate: bool, epoch: int):
         """``out (+)= scale * sum_r full_of_rank_r[rank * n:(rank + 1) * n]`` with fp32 accumulation; the sum of
-        squares of the new ``out`` is added to ``self.stats``.  Returns ``(job_id, channel, epoch)``."""
+        squares of the new ``out`` is added to ``self.stats``.  ``epoch`` comes from ``publish_grads()`` (called when
+        the buffer became final; the job itself may be enqueued later).  Returns ``(job_id, channel, epoch)``."""
         d = self.domain
         buf = self._buf(full)
         n = out.numel()
@@ -99,12 +124,11 @@ class CarryRuntime:
         assert slice_bytes % 256 == 0, "shard sizes are multiples of 128 elements"
         off = full.data_ptr() - buf.ptr
         src = (nat.u64 * self.world)(*[buf.peer_ptrs[r] + off for r in range(self.world)])
-        epoch = d.next_epoch(CH_REDUCE)
         L = nat.require()
         job = L.tb_carry_push(2, src, out.data_ptr(), d.pad_ptrs, slice_bytes, self.rank, self.world, CH_REDUCE, epoch,
                               d.counter_ptr(CH_REDUCE), float(scale), int(full.dtype == torch.bfloat16),
                               int(out.dtype == torch.float32), int(accumulate), self.stats.data_ptr(), 1,
-                              nat.stream())
+                              CH_REDUCE, epoch)
         if job <= 0:
             raise nat.NativeError("tb_carry_push (reduce) rejected the job")
         self.last_epoch[CH_REDUCE] = epoch

@@ -226,6 +226,7 @@ class FlatParamUnit:
         self.refresh_lp_shard()
         self._gathered_version = self.flat_param._version
         if eng.carry is not None and (self.persistent_full is None or eng.keep_gathered):
+            eng.publish_params_once()
             buf = self.persistent_full if self.persistent_full is not None else \
                 eng.lp_pool.acquire(self.padded, eng.compute_dtype)
             self._gather_job = eng.carry.push_gather(self.lp_shard, buf, background=background)
@@ -305,6 +306,8 @@ class FlatParamUnit:
             if eng.carry is not None:
                 # the previous user's reduce-scatter reads this buffer from EVERY rank: it must have been issued here
                 # and finished everywhere before the wgrad epilogues write into it again
+                if any(p[1].data_ptr() == self.grad_full.data_ptr() for p in eng._carry_pending_reduces):
+                    eng.enqueue_delayed_reduces(0)     # pool too shallow for the configured delay: enqueue now
                 prev = eng._carry_reduce_of.pop(self.grad_full.data_ptr(), None)
                 if prev is not None:
                     from .carry import BACKGROUND
@@ -395,8 +398,11 @@ class FlatParamUnit:
             if not eng._carry_stats_armed:
                 eng.carry.arm_stats()
                 eng._carry_stats_armed = True
-            job = eng.carry.push_reduce(src, self._grad_shard, 1.0 / eng.world_data, accumulate=not first)
-            eng._carry_reduce_of[src.data_ptr()] = job
+            # the gradients are final NOW (flag to the peers); the job is enqueued `reduce_delay` units later so that
+            # a peer whose backward runs a few percent slower is not waited for inside our next GEMM
+            epoch = eng.carry.publish_grads()
+            eng._carry_pending_reduces.append((self, src, not first, epoch))
+            eng.enqueue_delayed_reduces(eng.reduce_delay)
             eng.grad_pool.release(src, torch.cuda.current_stream())
             self._reduce_ready = None
             if eng.grad_mode == "fused" or self._grad_shard.dtype != fp.dtype:
@@ -590,7 +596,6 @@ class ShardingEngine:
         self.units: List[FlatParamUnit] = []
         self.lp_pool = _BufferPool(device, depth=2 + prefetch)
         symm_grad = hasattr(self.shard_coll, "domain")
-        self.grad_pool = _BufferPool(device, depth=2, allocator=(self.shard_coll.alloc if symm_grad else None))
         self._empty = torch.empty(0, dtype=compute_dtype, device=device)
         cuda = device.type == "cuda"
         # Carried collectives (parallel/carry.py): parameter all-gathers and gradient reduce-scatters ride inside the
@@ -599,9 +604,15 @@ class ShardingEngine:
         self.carry = None
         self._carry_reduce_of: Dict[int, tuple] = {}
         self._carry_stats_armed = False
+        self._carry_pending_reduces: List[tuple] = []      # (unit, flat gradient buffer, accumulate, entry epoch)
+        self._params_published_for = -1
+        import os as _os1
+        self.reduce_delay = max(0, int(_os1.environ.get("TORCHACC_B200_REDUCE_DELAY", "2")))
         if cuda and self.reshard and self.replica_world == 1:
             from .carry import make_carry
             self.carry = make_carry(self.shard_coll, device)
+        self.grad_pool = _BufferPool(device, depth=2 + (self.reduce_delay if self.carry is not None else 0),
+                                     allocator=(self.shard_coll.alloc if symm_grad else None))
         if cuda and self.world_data > 1:
             # without carried collectives they run on side streams next to the GEMMs: claim GEMM tiles dynamically so
             # SMs that are busy with a collective CTA do not stall a whole GEMM (csrc/gemm/gemm_bf16.cu, "tile
@@ -635,6 +646,23 @@ class ShardingEngine:
         self._callback_queued = False
         self._pending_reduce = False
         self.training_step = 0
+
+    def publish_params_once(self) -> None:
+        """First gather after an optimizer step: bring every unit's bf16 shard up to date, then tell the peers ONCE
+        that all shards of this rank are final (entry flag of every gather job of the step)."""
+        if self._params_published_for == self.training_step:
+            return
+        self._params_published_for = self.training_step
+        for u in self.units:
+            u.refresh_lp_shard()
+        self.carry.publish_params()
+
+    def enqueue_delayed_reduces(self, keep: int) -> None:
+        """Hand all but the newest ``keep`` finished gradient buffers to the carry queue."""
+        while len(self._carry_pending_reduces) > keep:
+            unit, src, accumulate, epoch = self._carry_pending_reduces.pop(0)
+            job = self.carry.push_reduce(src, unit._grad_shard, 1.0 / self.world_data, accumulate, epoch)
+            self._carry_reduce_of[src.data_ptr()] = job
 
     @property
     def accumulate_in_flat(self) -> bool:
@@ -831,6 +859,7 @@ class ShardingEngine:
                     unit.reshard()
         if self.carry is not None:
             c = self.carry
+            self.enqueue_delayed_reduces(0)
             left = c.pending()
             if left:
                 self.stats["tail_chunks_flushed"] = self.stats.get("tail_chunks_flushed", 0) + left
