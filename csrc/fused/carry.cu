@@ -101,7 +101,7 @@ long long carry_push(int kind, const uint64_t* src, uint64_t dst, const uint64_t
     p.chunk_bytes = kCarryStageBytes;
     const long long cps = (bytes + p.chunk_bytes - 1) / p.chunk_bytes;
     j.total = (uint32_t)(cps * world);              // own shard included: no separate local copy
-    j.bytes_per_chunk = (double)p.chunk_bytes;
+    j.bytes_per_chunk = (double)p.chunk_bytes * (world - 1) / world;   // the own shard's chunks never leave the GPU
   } else {
     p.chunk_bytes = (kCarryStageBytes / (uint32_t)world) & ~127u;        // one ring stage holds `world` sub-chunks
     j.total = (uint32_t)((bytes + p.chunk_bytes - 1) / p.chunk_bytes);
