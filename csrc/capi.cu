@@ -209,3 +209,16 @@ TB_API long long tb_carry_set_debug(uint64_t buf, long long records) {
 TB_API int tb_symm_signal(const uint64_t* pads, int rank, int world, int channel, uint32_t epoch, uint64_t stream) {
   return (int)tb::symm_signal(pads, rank, world, channel, epoch, S(stream));
 }
+
+// ---- block-scaled fp8 ---------------------------------------------------------------------------------------------
+TB_API int tb_quant_mxfp8(uint64_t x, long long ldx, int R, int C, uint64_t q, long long ldq, uint64_t sf, uint64_t qt,
+                          long long ldqt, uint64_t sft, uint64_t stream) {
+  return (int)tb::quant_mxfp8(P<void>(x), ldx, R, C, P<void>(q), ldq, P<void>(sf), P<void>(qt), ldqt, P<void>(sft),
+                              S(stream));
+}
+TB_API int tb_gemm_mxfp8(uint64_t A, uint64_t sfa, uint64_t B, uint64_t sfb, uint64_t D, uint64_t C, int M, int N, int K,
+                         long long lda, long long ldb, long long ldd, long long ldc, int out_fp32, int num_sms,
+                         uint64_t stream) {
+  return (int)tb::gemm_mxfp8(P<void>(A), P<void>(sfa), P<void>(B), P<void>(sfb), P<void>(D), P<void>(C), M, N, K, lda, ldb,
+                             ldd, ldc, out_fp32 != 0, num_sms, S(stream));
+}

@@ -44,4 +44,10 @@ cudaError_t gemm_rs_bf16(const void* A, const void* B, const uint64_t* peer_stag
 cudaError_t rs_reduce_bf16(const void* stage, const uint32_t* counters, uint32_t expected, const void* residual,
                            void* out, int rows, int N, int world, long long slot_stride, int num_sms, cudaStream_t stream);
 
+// Block-scaled FP8 GEMM (gemm_mxfp8.cu): D[M,N] = (A[M,K] * SFA) (B[N,K] * SFB)^T (+ C); e4m3 operands, UE8M0 scales per
+// 32 elements of K in the atom-tiled layout written by ops/quant_mxfp8.cu; K % 128 == 0.
+cudaError_t gemm_mxfp8(const void* A, const void* sfa, const void* B, const void* sfb, void* D, const void* C, int M,
+                       int N, int K, long long lda, long long ldb, long long ldd, long long ldc, bool out_fp32,
+                       int num_sms, cudaStream_t stream);
+
 }  // namespace tb

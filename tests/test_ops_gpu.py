@@ -306,3 +306,65 @@ def test_cpu_offload_moves_activations_and_preserves_grads():
     assert mem_off < mem_ref - 3 * 4096 * 2048 * 4, (mem_off, mem_ref)              # device memory really dropped
     for a, b in zip(g_off, g_ref):
         assert torch.equal(a, b)
+
+
+# ---- block-scaled fp8 ------------------------------------------------------------------------------------------------
+def test_mxfp8_quantizer_matches_reference_and_layouts():
+    from torchacc_b200.ops import fp8
+    torch.manual_seed(0)
+    x = (torch.randn(384, 512, device=_dev()) * torch.logspace(-3, 2, 512, device=_dev())).bfloat16()
+    row, col = fp8.quantize_mxfp8(x, True, True)
+    ref = fp8.quantize_mxfp8_ref(x)
+    assert torch.equal(fp8.dequantize_mxfp8(row), ref), "row-wise payload / scale layout"
+    ref_t = fp8.quantize_mxfp8_ref(x.t().contiguous())
+    assert torch.equal(fp8.dequantize_mxfp8(col), ref_t), "transposed payload / scale layout"
+    rel = (ref - x.float()).abs().max() / x.float().abs().max()
+    assert rel < 0.07                                    # e4m3: 3 mantissa bits
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 192, 128), (256, 384, 512), (1000, 776, 384), (4096, 4096, 4096)])
+def test_mxfp8_gemm_matches_fp32_oracle(M, N, K):
+    """The tensor core applies the UE8M0 block scales itself: D must equal the fp32 product of the DEQUANTISED operands
+    (exact up to accumulation order), which pins the scale atom layout, the sf_id selection and the 192-column tiling."""
+    from torchacc_b200.ops import fp8
+    torch.manual_seed(1)
+    # per-row and per-K-block magnitudes differ by orders of magnitude: a wrong scale mapping cannot hide
+    a = (torch.randn(M, K, device=_dev()) * torch.logspace(-2, 2, M, device=_dev())[:, None]
+         * (1 + torch.arange(K, device=_dev()) // 32 % 7)[None, :]).bfloat16()
+    b = (torch.randn(N, K, device=_dev()) * torch.logspace(1, -2, N, device=_dev())[:, None]).bfloat16()
+    aq, _ = fp8.quantize_mxfp8(a)
+    bq, _ = fp8.quantize_mxfp8(b)
+    d = fp8.gemm_mxfp8(aq, bq, out_dtype=torch.float32)
+    ref = fp8.dequantize_mxfp8(aq).double() @ fp8.dequantize_mxfp8(bq).double().t()
+    err = (d.double() - ref).abs().max() / ref.abs().max()
+    assert err < 1e-5, float(err)
+    # against the unquantised product: fp8 precision
+    full = a.double() @ b.double().t()
+    assert ((d.double() - full).norm() / full.norm()) < 0.06
+    # bf16 output + addend
+    c = torch.randn(M, N, device=_dev()).bfloat16()
+    d2 = fp8.gemm_mxfp8(aq, bq, addend=c)
+    _close(d2, ref.float() + c.float(), 2e-2, 2e-2 * float(ref.abs().max()), "bf16 out + addend")
+
+
+def test_fp8_linear_fwd_bwd_close_to_bf16():
+    from torchacc_b200.ops import fp8
+    from torchacc_b200.ops.linear import linear
+    torch.manual_seed(2)
+    T, K, N = 512, 1024, 768
+    x = torch.randn(T, K, device=_dev()).bfloat16().requires_grad_()
+    w = (torch.randn(N, K, device=_dev()) * 0.05).bfloat16().requires_grad_()
+    dy = torch.randn(T, N, device=_dev()).bfloat16()
+    y0 = linear(x, w)
+    y0.backward(dy)
+    gx0, gw0 = x.grad.clone(), w.grad.clone()
+    x.grad = w.grad = None
+    fp8.enable(True)
+    try:
+        y1 = linear(x, w)
+        y1.backward(dy)
+    finally:
+        fp8.enable(False)
+    for a, b, what in ((y1, y0, "y"), (x.grad, gx0, "dx"), (w.grad, gw0, "dw")):
+        rel = (a.float() - b.float()).norm() / b.float().norm()
+        assert rel < 0.06, (what, float(rel))

@@ -58,10 +58,16 @@ def accelerate(model: nn.Module, dataloader=None, config: Optional[Config] = Non
                              num_buckets=dl.num_buckets, pad_value_dict=dl.pad_value_dict, prefetch=dl.prefetch,
                              pin_memory=dl.pin_memory)
 
+    from .ops import fp8 as _fp8
     if getattr(config.compute, "fp8", False):
-        from .utils.logger import logger
-        logger.warning("compute.fp8: the block-scaled fp8 tcgen05 GEMM is not available in this build; linear layers "
-                       "run the bf16 tcgen05 GEMM")
+        if device.type == "cuda" and _fp8.available():
+            _fp8.enable(True)           # linear layers: MX-FP8 (e4m3 + UE8M0 block scales) tcgen05 GEMMs, ops/fp8.py
+        else:
+            from .utils.logger import logger
+            logger.warning("compute.fp8 needs a CUDA device and the native library; linear layers stay in %s",
+                           "bf16" if config.compute.bf16 else "fp32")
+    else:
+        _fp8.enable(False)
     if config.compute.acc_scaled_dot_attn:
         from .ops.sdpa import patch_sdpa
         patch_sdpa()

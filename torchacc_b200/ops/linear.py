@@ -136,6 +136,9 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     """Drop-in for ``F.linear`` (bf16 CUDA tensors go through the tcgen05 GEMM).  ``residual`` (same shape as the
     result) is added inside the GEMM epilogue: ``x @ w.T + bias + residual`` without a separate elementwise pass."""
     if x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and nat.use_native(x, w):
+        from . import fp8
+        if fp8.enabled() and fp8.eligible(x.reshape(-1, x.shape[-1]), w):
+            return fp8.fp8_linear(x, w, bias, residual)          # compute.fp8: block-scaled e4m3 GEMMs (ops/fp8.py)
         return _LinearFn.apply(x, w, bias, residual)
     y = F.linear(x, w, bias)
     return y if residual is None else y + residual
