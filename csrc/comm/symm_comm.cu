@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "../common/ptx.cuh"
+#include "../common/spin.cuh"
 #include "comm.h"
 
 namespace tb {
@@ -78,11 +79,8 @@ TB_DEVICE void barrier_enter(const Pads& pads, int rank, int world, int ch, uint
     __threadfence_system();
     st_release_sys(pads.ptr[threadIdx.x] + ch * kPadSlots + rank, epoch);
   }
-  if (threadIdx.x < world) {
-    const uint32_t* mine = pads.ptr[rank] + ch * kPadSlots + threadIdx.x;
-    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
-    }
-  }
+  if (threadIdx.x < world)
+    spin_until_epoch(pads.ptr[rank] + ch * kPadSlots + threadIdx.x, epoch, rank, (int)threadIdx.x, ch, "collective entry");
   __syncthreads();
 }
 
@@ -101,9 +99,8 @@ TB_DEVICE void barrier_exit(const Pads& pads, int rank, int world, int ch, uint3
   if (threadIdx.x < world) {
     __threadfence_system();
     st_release_sys(pads.ptr[threadIdx.x] + ch * kPadSlots + 8 + rank, epoch);
-    const uint32_t* mine = pads.ptr[rank] + ch * kPadSlots + 8 + threadIdx.x;
-    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
-    }
+    spin_until_epoch(pads.ptr[rank] + ch * kPadSlots + 8 + threadIdx.x, epoch, rank, (int)threadIdx.x, ch,
+                     "collective exit");
   }
   __syncthreads();
 }

@@ -32,6 +32,7 @@
 #include <stdio.h>
 
 #include "../common/ptx.cuh"
+#include "../common/spin.cuh"
 
 namespace tb {
 
@@ -75,32 +76,6 @@ TB_DEVICE unsigned long long carry_now_ns() {
   return t;
 }
 
-TB_DEVICE void carry_st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-TB_DEVICE uint32_t carry_ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-constexpr long long kSpinTimeoutCycles = 120000000000ll;   // ~60 s at 1.9 GHz
-
-// Wait until *flag (epoch numbering, wrap-safe) reaches `epoch`; trap with a diagnostic after kSpinTimeoutCycles.
-TB_DEVICE void spin_until_epoch(const uint32_t* flag, uint32_t epoch, int my_rank, int peer, int channel,
-                                const char* what) {
-  if ((int32_t)(carry_ld_acquire_sys(flag) - epoch) >= 0) return;
-  const long long t0 = clock64();
-  uint32_t polls = 0;
-  while ((int32_t)(carry_ld_acquire_sys(flag) - epoch) < 0) {
-    if ((++polls & 0x3FFu) == 0 && clock64() - t0 > kSpinTimeoutCycles) {
-      printf("[torchacc_b200] rank %d: timed out waiting for rank %d (%s, channel %d, epoch %u, flag %u)\n", my_rank,
-             peer, what, channel, epoch, *(volatile const uint32_t*)flag);
-      __trap();
-    }
-  }
-}
-
 // One warp.  `ring` / `bars`: shared-memory addresses of kCarryStages x kCarryStageBytes bytes and kCarryStages
 // mbarriers (initialised by the caller with count 1).  `it` is the ring position carried across slices of one launch.
 TB_DEVICE void carry_run_slice(const CarrySlice& s, uint32_t ring, uint32_t bars, uint32_t& it, int cta, int num_ctas,
@@ -138,16 +113,16 @@ TB_DEVICE void carry_run_slice(const CarrySlice& s, uint32_t ring, uint32_t bars
         locate(j, sp, dp, len);
         const uint32_t st = (it + j) % kCarryStages;
         mbar_arrive_expect_tx(bars + 8u * st, len);
-        bulk_load(ring + st * kCarryStageBytes, sp, len, bars + 8u * st);
+        bulk_load_hint(ring + st * kCarryStageBytes, sp, len, bars + 8u * st, kEvictFirst);
       };
       uint32_t issued = 0;
       for (; issued < (uint32_t)kCarryStages - 1 && issued < mine; ++issued) issue(issued);
       for (uint32_t i = 0; i < mine; ++i) {
         const uint32_t st = (it + i) % kCarryStages;
-        mbar_wait(bars + 8u * st, ((it + i) / kCarryStages) & 1);
+        mbar_wait_relaxed(bars + 8u * st, ((it + i) / kCarryStages) & 1);
         const uint8_t* sp; uint8_t* dp; uint32_t len;
         locate(i, sp, dp, len);
-        bulk_store(dp, ring + st * kCarryStageBytes, len);
+        bulk_store_hint(dp, ring + st * kCarryStageBytes, len, kEvictFirst);
         tma_store_commit();
         if (issued < mine) {
           tma_store_wait_read<1>();      // every store but the newest has left smem: stage (i-1) % stages is free
@@ -171,7 +146,7 @@ TB_DEVICE void carry_run_slice(const CarrySlice& s, uint32_t ring, uint32_t bars
       mbar_arrive_expect_tx(bars + 8u * st, len * s.world);
       for (int p = 0; p < s.world; ++p) {
         const int r = (s.rank + p) % s.world;
-        bulk_load(ring + st * stage_stride + p * sub, s.src[r] + off, len, bars + 8u * st);
+        bulk_load_hint(ring + st * stage_stride + p * sub, s.src[r] + off, len, bars + 8u * st, kEvictFirst);
       }
     };
     uint32_t issued = 0;
@@ -180,7 +155,8 @@ TB_DEVICE void carry_run_slice(const CarrySlice& s, uint32_t ring, uint32_t bars
     issued = __shfl_sync(0xffffffffu, issued, 0);
     for (uint32_t i = 0; i < mine; ++i) {
       const uint32_t st = (it + i) % kCarryStages;
-      mbar_wait(bars + 8u * st, ((it + i) / kCarryStages) & 1);
+      if (lane == 0) mbar_wait_relaxed(bars + 8u * st, ((it + i) / kCarryStages) & 1);
+      __syncwarp();                       // lane 0 observed the phase; the warp barrier orders the smem reads below
       const uint32_t c = s.chunk_begin + cta + i * num_ctas;
       const long long off = (long long)c * sub;
       const long long left = s.bytes - off;
@@ -211,8 +187,8 @@ TB_DEVICE void carry_run_slice(const CarrySlice& s, uint32_t ring, uint32_t bars
               acc[0] += o0.x; acc[1] += o0.y; acc[2] += o0.z; acc[3] += o0.w;
               acc[4] += o1.x; acc[5] += o1.y; acc[6] += o1.z; acc[7] += o1.w;
             }
-            op[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            op[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            __stcs(op, make_float4(acc[0], acc[1], acc[2], acc[3]));          // streaming: read once by the optimizer
+            __stcs(op + 1, make_float4(acc[4], acc[5], acc[6], acc[7]));
           } else {
             uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(s.dst) + e0 + (long long)v * 8);
             if (s.accumulate) {

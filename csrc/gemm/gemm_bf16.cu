@@ -111,11 +111,9 @@ TB_DEVICE void fused_barrier(const FuseArgs& f, bool signal, int slot_base, int 
     __threadfence_system();
     st_release_sys_u32(f.pads[tid] + f.channel * 16 + slot_base + f.rank, f.epoch);
   }
-  if (tid < f.world) {
-    const uint32_t* mine = f.pads[f.rank] + f.channel * 16 + slot_base + tid;
-    while ((int32_t)(ld_acquire_sys_u32(mine) - f.epoch) < 0) {
-    }
-  }
+  if (tid < f.world)
+    spin_until_epoch(f.pads[f.rank] + f.channel * 16 + slot_base + tid, f.epoch, f.rank, tid, f.channel,
+                     "fused GEMM barrier");
 }
 
 // Copy-engine role of the all-gather -> GEMM kernel (executed by whole clusters).  One thread per CTA drives a ring
@@ -357,8 +355,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int n0 = tn * kBlockN + (int)cta_rank * kLoadN;
         if constexpr (kFuse == 1) {
           if (shard != args.fuse.rank) {   // wait until the copy clusters have landed this source rank's rows
-            while ((int32_t)(ld_acquire_gpu_u32(args.fuse.flags + shard) - args.fuse.flag_target) < 0) {
-            }
+            spin_until_count(args.fuse.flags + shard, args.fuse.flag_target, args.fuse.rank, shard,
+                             "all-gather -> GEMM shard flag");
             fence_proxy_async_all();       // generic-proxy writes of the copy CTAs -> visible to TMA
           }
         }
@@ -797,10 +795,8 @@ __global__ void __launch_bounds__(256)
 rs_reduce_kernel(const __nv_bfloat16* __restrict__ stage, const uint32_t* __restrict__ counters, uint32_t expected,
                  const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out, int rows, int N, int world,
                  long long slot_stride) {
-  if (threadIdx.x < world) {
-    while ((int32_t)(ld_acquire_sys_u32(counters + threadIdx.x) - expected) < 0) {
-    }
-  }
+  if (threadIdx.x < world)
+    spin_until_count(counters + threadIdx.x, expected, -1, (int)threadIdx.x, "GEMM -> reduce-scatter arrivals");
   __syncthreads();
   const int num_n_tiles = (N + 255) / 256;
   const long long num_blocks = (long long)(rows / 256) * num_n_tiles * 64;
