@@ -34,6 +34,9 @@ def parse():
                    help="ours | reference (UNMODIFIED reference, stock path) | torch_fsdp (NOT the reference: the stack "
                         "the reference's eager FSDP path would build -- torch FSDP1 + its kernel patches -- so that "
                         "N > 1 has a same-box competitor; see DESIGN.md section 4)")
+    p.add_argument("--fp8", action="store_true",
+                   help="ours: Config.compute.fp8 (MX-FP8 block-scaled linear layers).  Lower precision than the "
+                        "reference arm: reported as its own config, never as the headline")
     p.add_argument("--hf", action="store_true",
                    help="ours: run the SAME HuggingFace LlamaForCausalLM object as the reference arm through "
                         "ta.accelerate (kernel patches + FSDP engine) instead of the native model definition")
@@ -177,6 +180,7 @@ def run_ours(a):
 
     cfg = ta.Config()
     cfg.compute.bf16 = True
+    cfg.compute.fp8 = bool(a.fp8)
     cfg.memory.gc = not a.no_gc
     cfg.memory.gc_cls = {"LlamaDecoderLayer"}
     cfg.dist.fsdp.size = world
@@ -312,9 +316,10 @@ def run_ours(a):
             "metric": METRIC,
             "value": value, "unit": "tokens/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": value / (A100_TOKENS_PER_S_PER_GPU * world), "dtype": "bf16", "data": "synthetic",
+            "vs_baseline": value / (A100_TOKENS_PER_S_PER_GPU * world),
+            "dtype": "mxfp8 linears (e4m3 + ue8m0/32), bf16 elsewhere" if a.fp8 else "bf16", "data": "synthetic",
             "impl": "ours",
-            "config": bench_config(a, world, mcfg.num_hidden_layers),
+            "config": dict(bench_config(a, world, mcfg.num_hidden_layers), **({"fp8": True} if a.fp8 else {})),
             "detail": {"model_code": "HF LlamaForCausalLM through ta.accelerate" if a.hf else "native build_llama",
                        "optimizer": "FusedAdamW + clip_grad_norm(1.0)", "attention": ta.ops.get_attention_backend(),
                        "stack": "torchacc_b200: own FSDP engine + tcgen05 GEMM/attention + symmetric-memory collectives",

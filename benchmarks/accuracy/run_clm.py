@@ -37,6 +37,7 @@ def main():
     p.add_argument("--text", default=None)
     p.add_argument("--vocab", type=int, default=4096, help="synthetic corpus vocabulary")
     p.add_argument("--device", default=None)
+    p.add_argument("--fp8", action="store_true", help="native arm with Config.compute.fp8 (MX-FP8 linear layers)")
     p.add_argument("--out", default=None)
     a = p.parse_args()
     if a.impl == "torch":
@@ -61,6 +62,7 @@ def main():
         model = build_llama(llama_config(a.model, **over), dtype=dtype)
     cfg = ta.Config()
     cfg.compute.bf16 = dtype == torch.bfloat16
+    cfg.compute.fp8 = bool(a.fp8)
     cfg.memory.gc = True
     cfg.dist.fsdp.size = a.fsdp_size or world
     cfg.dist.fsdp.wrap_layer_cls = {"LlamaDecoderLayer"}
@@ -79,7 +81,7 @@ def main():
         if rank == 0 and (step % 20 == 0 or step == a.steps - 1):
             print(f"[{a.impl}] step {step:4d} loss {losses[-1]:.4f}", flush=True)
     train_loss = sum(losses[-a.avg_last:]) / min(a.avg_last, len(losses))
-    res = {"impl": a.impl, "train_loss": train_loss, "first_loss": losses[0], "steps": a.steps,
+    res = {"impl": a.impl + ("+fp8" if a.fp8 else ""), "train_loss": train_loss, "first_loss": losses[0], "steps": a.steps,
            "optimal_loss": getattr(ds, "optimal_loss", None)}
     if rank == 0:
         print(json.dumps(res), flush=True)
