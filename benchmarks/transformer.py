@@ -43,6 +43,7 @@ def parse():
     p.add_argument("--fp16", action="store_true")
     p.add_argument("--profile", action="store_true", help="torch.profiler trace to ./log/profile")
     p.add_argument("--disable_loss_print", action="store_true")
+    p.add_argument("--tp_no_sequence_parallel", action="store_true")
     return p.parse_args()
 
 
@@ -55,7 +56,13 @@ def main():
     dtype = torch.bfloat16 if a.bf16 else (torch.float16 if a.fp16 else torch.float32)
     is_gpt2 = a.model_name in GPT2_PRESETS
     with torch.device(device):
-        model = build_gpt2(a.model_name, dtype=dtype) if is_gpt2 else build_llama(a.model_name, dtype=dtype)
+        if is_gpt2:
+            model = build_gpt2(a.model_name, dtype=dtype)
+        else:
+            from torchacc_b200.models import llama_config
+            base = llama_config(a.model_name)
+            model = build_llama(a.model_name, dtype=dtype,
+                                max_position_embeddings=max(a.max_seq_length, base.max_position_embeddings))
     layer_cls = "GPT2Block" if is_gpt2 else "LlamaDecoderLayer"
     vocab = model.config.vocab_size
 
@@ -66,6 +73,8 @@ def main():
     cfg.dist.dp.size = a.dp_size
     cfg.dist.tp.size, cfg.dist.fsdp.size, cfg.dist.sp.size = a.tp_size, a.fsdp_size, a.sp_size
     cfg.dist.sp.mode = a.sp_mode
+    if a.tp_no_sequence_parallel:
+        cfg.dist.tp.sequence_parallel = False
     cfg.dist.fsdp.wrap_layer_cls = {layer_cls}
     if a.pp_size > 1:
         n_layers = model.config.n_layer if is_gpt2 else model.config.num_hidden_layers

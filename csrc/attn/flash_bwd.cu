@@ -34,8 +34,10 @@ struct BwdArgs {
   const float* lse;
   const float* delta;
   float* dq_acc;
-  __nv_bfloat16* dk;
-  __nv_bfloat16* dv;
+  uint16_t* dk;                // bf16 or fp16 (kernel template)
+  uint16_t* dv;
+  const float* alibi;          // optional ALiBi slopes [Hq] (alibi_bs == 0) or [B, Hq]
+  int alibi_bs;
   const int* cu_q;
   const int* cu_k;
   int B, Sq, Sk, Hq, Hk;
@@ -70,16 +72,16 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int D>
+template <int D, bool kBf16>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                  const __grid_constant__ CUtensorMap tmap_dq, const BwdArgs args) {
   using S = BwdSmem<D>;
   constexpr int kChunks = S::kChunks;
-  constexpr uint32_t kIdescST = make_idesc_f16(kTile, kTile, Major::K, Major::K, true);   // (a), (b)
-  constexpr uint32_t kIdescDQ = make_idesc_f16(kTile, D, Major::MN, Major::MN, true);     // (e)
-  constexpr uint32_t kIdescDKV = make_idesc_f16(kTile, D, Major::K, Major::MN, true);     // (c), (d)
+  constexpr uint32_t kIdescST = make_idesc_f16(kTile, kTile, Major::K, Major::K, kBf16);   // (a), (b)
+  constexpr uint32_t kIdescDQ = make_idesc_f16(kTile, D, Major::MN, Major::MN, kBf16);     // (e)
+  constexpr uint32_t kIdescDKV = make_idesc_f16(kTile, D, Major::K, Major::MN, kBf16);     // (c), (d)
   constexpr uint32_t R0 = 0, R1 = 128, R2 = 256, R3 = 384;
 
   const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -108,9 +110,9 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
   if (n_iter == 0) {  // no query sees these keys: dK = dV = 0
     for (int r = threadIdx.x; r < min(kTile, k_len - n0); r += blockDim.x) {
-      __nv_bfloat16* pk = args.dk + (long long)(k_start + n0 + r) * args.dk_ts + (long long)hk * D;
-      __nv_bfloat16* pv = args.dv + (long long)(k_start + n0 + r) * args.dv_ts + (long long)hk * D;
-      for (int d = 0; d < D; ++d) { pk[d] = __float2bfloat16(0.f); pv[d] = __float2bfloat16(0.f); }
+      uint16_t* pk = args.dk + (long long)(k_start + n0 + r) * args.dk_ts + (long long)hk * D;
+      uint16_t* pv = args.dv + (long long)(k_start + n0 + r) * args.dv_ts + (long long)hk * D;
+      for (int d = 0; d < D; ++d) { pk[d] = 0; pv[d] = 0; }
     }
     return;
   }
@@ -259,6 +261,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_wait(s_full, it & 1);
       tc_fence_after();
       if (warp_idx == 4 && lane == 0) TB_TRACE(5);
+      const float slope_l2 = args.alibi ? args.alibi[(long long)b * args.alibi_bs + h] * 1.4426950408889634f : 0.f;
       // interior tile: every query row of the tile sees every key of the tile -> no per-element mask
       bool interior = (m0 + kTile <= q_len) && (n0 + kTile <= k_len);
       if (interior) {
@@ -280,6 +283,13 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       for (int cc = 0; cc < 2; ++cc) {
         const int c = 2 * grp + cc;
         const float4* lse4 = reinterpret_cast<const float4*>(stat + c * 32);
+        if (args.alibi != nullptr) {   // ALiBi: the forward folded -slope * |query position - key| into the scores
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float dist = fabsf((float)(m0 + c * 32 + i + shift - key));
+            sv[cc][i] = __float_as_uint(__uint_as_float(sv[cc][i]) - slope_l2 * dist / sl2);
+          }
+        }
         // branch-free: exponentiate everything (straight-line FFMA + MUFU so the SFU latency pipelines), then zero
         // the masked entries of boundary tiles with selects
 #pragma unroll
@@ -303,7 +313,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(sv[cc][2 * i]), __uint_as_float(sv[cc][2 * i + 1]));
+        for (int i = 0; i < 16; ++i) pk[i] = pack_h2<kBf16>(__uint_as_float(sv[cc][2 * i]), __uint_as_float(sv[cc][2 * i + 1]));
         tmem_st_32x32b_x16(tmem_base + lane_off + R0 + c * 16, pk);   // P^T chunk -> TMEM R0 columns [16c, 16c+16)
       }
       if (warp_idx == 4 && lane == 0) TB_TRACE(10);   // phase 1 done (P^T stores issued)
@@ -335,8 +345,8 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           const float d1 = __uint_as_float(sv[cc][g4 * 4 + 1]) * (__uint_as_float(dpv[g4 * 4 + 1]) - dl.y) * sc;
           const float d2 = __uint_as_float(sv[cc][g4 * 4 + 2]) * (__uint_as_float(dpv[g4 * 4 + 2]) - dl.z) * sc;
           const float d3 = __uint_as_float(sv[cc][g4 * 4 + 3]) * (__uint_as_float(dpv[g4 * 4 + 3]) - dl.w) * sc;
-          dsk[g4 * 2] = pack_bf16x2(d0, d1);
-          dsk[g4 * 2 + 1] = pack_bf16x2(d2, d3);
+          dsk[g4 * 2] = pack_h2<kBf16>(d0, d1);
+          dsk[g4 * 2 + 1] = pack_h2<kBf16>(d2, d3);
         }
         // dS^T chunk -> smem row r (keys), 64 bytes = 4 x 16B units, 128B-swizzled
         const uint32_t row_base = sDS + (c >> 1) * 16384 + r * 128;
@@ -399,11 +409,11 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // ---- epilogue: dV (R2), dK (R3) -> bf16; each group writes half of the D columns ----
     mbar_wait(dkv_full, 0);
     tc_fence_after();
-    __nv_bfloat16* pdv = args.dv + (long long)(k_start + key) * args.dv_ts + (long long)hk * D;
-    __nv_bfloat16* pdk = args.dk + (long long)(k_start + key) * args.dk_ts + (long long)hk * D;
+    uint16_t* pdv = args.dv + (long long)(k_start + key) * args.dv_ts + (long long)hk * D;
+    uint16_t* pdk = args.dk + (long long)(k_start + key) * args.dk_ts + (long long)hk * D;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-      __nv_bfloat16* dst = which == 0 ? pdv : pdk;
+      uint16_t* dst = which == 0 ? pdv : pdk;
       const uint32_t reg = which == 0 ? R2 : R3;
 #pragma unroll
       for (int cc = 0; cc < D / 64; ++cc) {
@@ -415,10 +425,10 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(v[8 * u + 0]), __uint_as_float(v[8 * u + 1]));
-            w.y = pack_bf16x2(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3]));
-            w.z = pack_bf16x2(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5]));
-            w.w = pack_bf16x2(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7]));
+            w.x = pack_h2<kBf16>(__uint_as_float(v[8 * u + 0]), __uint_as_float(v[8 * u + 1]));
+            w.y = pack_h2<kBf16>(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3]));
+            w.z = pack_h2<kBf16>(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5]));
+            w.w = pack_h2<kBf16>(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7]));
             *reinterpret_cast<uint4*>(dst + c * 32 + u * 8) = w;
           }
         }
@@ -437,9 +447,9 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 }
 
 // delta[h, t] = sum_d dO[t,h,d] * O[t,h,d];  dq_acc[t,h,:] = 0.   One warp per (token, head).
-template <int D>
+template <int D, bool kBf16>
 __global__ void __launch_bounds__(256)
-bwd_preprocess_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+bwd_preprocess_kernel(const uint16_t* __restrict__ o, const uint16_t* __restrict__ dout,
                       float* __restrict__ delta, float* __restrict__ dq_acc, long long Tq, int Hq, long long do_ts) {
   const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -447,13 +457,13 @@ bwd_preprocess_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* 
   const long long t = w / Hq;
   const int h = (int)(w % Hq);
   constexpr int kPer = D / 32;  // 4 (D=128) or 2 (D=64) elements per lane
-  const __nv_bfloat16* op = o + (t * Hq + h) * D + lane * kPer;
-  const __nv_bfloat16* dp = dout + t * do_ts + (long long)h * D + lane * kPer;
+  const uint16_t* op = o + (t * Hq + h) * D + lane * kPer;
+  const uint16_t* dp = dout + t * do_ts + (long long)h * D + lane * kPer;
   float acc = 0.f;
 #pragma unroll
   for (int i = 0; i < kPer; i += 2) {
-    float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(op + i));
-    float2 g = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dp + i));
+    float2 a = unpack_h2<kBf16>(*reinterpret_cast<const uint32_t*>(op + i));
+    float2 g = unpack_h2<kBf16>(*reinterpret_cast<const uint32_t*>(dp + i));
     acc += a.x * g.x + a.y * g.y;
   }
   acc = warp_reduce_sum(acc);
@@ -463,8 +473,9 @@ bwd_preprocess_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* 
   for (int i = 0; i < kPer; ++i) q[i] = 0.f;
 }
 
+template <bool kBf16>
 __global__ void __launch_bounds__(256)
-bwd_convert_dq_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dq, long long Tq, int HD,
+bwd_convert_dq_kernel(const float* __restrict__ dq_acc, uint16_t* __restrict__ dq, long long Tq, int HD,
                       long long dq_ts) {
   const long long n = Tq * (HD / 4);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -472,8 +483,8 @@ bwd_convert_dq_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restric
     const int c = (int)(i % (HD / 4)) * 4;
     float4 v = *reinterpret_cast<const float4*>(dq_acc + t * HD + c);
     uint2 o;
-    o.x = pack_bf16x2(v.x, v.y);
-    o.y = pack_bf16x2(v.z, v.w);
+    o.x = pack_h2<kBf16>(v.x, v.y);
+    o.y = pack_h2<kBf16>(v.z, v.w);
     *reinterpret_cast<uint2*>(dq + t * dq_ts + c) = o;
   }
 }
@@ -481,19 +492,20 @@ bwd_convert_dq_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restric
 static long long* g_bwd_trace = nullptr;
 void flash_attn_bwd_set_trace(long long* p) { g_bwd_trace = p; }
 
-static CUtensorMap make_map_thd_b(const void* base, long long tokens, int heads, int D, long long ts) {
+static CUtensorMap make_map_thd_b(const void* base, long long tokens, int heads, int D, long long ts, bool bf16) {
   uint64_t dims[3] = {(uint64_t)D, (uint64_t)heads, (uint64_t)tokens};
   uint64_t strides[2] = {(uint64_t)D * 2, (uint64_t)ts * 2};
   uint32_t box[3] = {64, 1, 128};
-  return make_tensor_map(base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  return make_tensor_map(base, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, dims,
+                         strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int D>
+template <int D, bool kBf16>
 static cudaError_t launch_bwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
                               const CUtensorMap& mdo, const CUtensorMap& mdq, const BwdArgs& a, int num_k_tiles,
                               cudaStream_t stream) {
   using S = BwdSmem<D>;
-  auto kern = flash_bwd_kernel<D>;
+  auto kern = flash_bwd_kernel<D, kBf16>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
@@ -510,7 +522,8 @@ cudaError_t flash_attn_bwd(const void* q, const void* k, const void* v, const vo
                            const int* cu_q, const int* cu_k, int B, int Sq, int Sk, int Hq, int Hk, int D,
                            long long q_ts, long long k_ts, long long v_ts, long long do_ts, float scale, bool causal,
                            int wl, int wr, long long Tq, long long Tk, long long dq_ts, long long dk_ts,
-                           long long dv_ts, int num_sms, cudaStream_t stream) {
+                           long long dv_ts, int num_sms, bool is_bf16, const float* alibi_slopes,
+                           int alibi_batch_stride, cudaStream_t stream) {
   if (B == 0 || Tq == 0 || Tk == 0) return cudaSuccess;
   if (D != 64 && D != 128) return cudaErrorInvalidValue;
   if (Hq % Hk != 0) return cudaErrorInvalidValue;
@@ -518,24 +531,22 @@ cudaError_t flash_attn_bwd(const void* q, const void* k, const void* v, const vo
   {
     const long long warps = Tq * Hq;
     const long long blocks = (warps * 32 + 255) / 256;
-    if (D == 128)
-      bwd_preprocess_kernel<128><<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)o,
-                                                                        (const __nv_bfloat16*)dout, delta, dq_acc, Tq,
-                                                                        Hq, do_ts);
-    else
-      bwd_preprocess_kernel<64><<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)o,
-                                                                       (const __nv_bfloat16*)dout, delta, dq_acc, Tq,
-                                                                       Hq, do_ts);
+#define TB_PRE(DD, BF)                                                                                       \
+  bwd_preprocess_kernel<DD, BF><<<(unsigned)blocks, 256, 0, stream>>>((const uint16_t*)o, (const uint16_t*)dout, delta, \
+                                                                      dq_acc, Tq, Hq, do_ts)
+    if (D == 128) { if (is_bf16) TB_PRE(128, true); else TB_PRE(128, false); }
+    else { if (is_bf16) TB_PRE(64, true); else TB_PRE(64, false); }
+#undef TB_PRE
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
   // 2) main kernel
   CUtensorMap mq, mk, mv, mdo, mdq;
   try {
-    mq = make_map_thd_b(q, Tq, Hq, D, q_ts);
-    mk = make_map_thd_b(k, Tk, Hk, D, k_ts);
-    mv = make_map_thd_b(v, Tk, Hk, D, v_ts);
-    mdo = make_map_thd_b(dout, Tq, Hq, D, do_ts);
+    mq = make_map_thd_b(q, Tq, Hq, D, q_ts, is_bf16);
+    mk = make_map_thd_b(k, Tk, Hk, D, k_ts, is_bf16);
+    mv = make_map_thd_b(v, Tk, Hk, D, v_ts, is_bf16);
+    mdo = make_map_thd_b(dout, Tq, Hq, D, do_ts, is_bf16);
     {  // fp32 dQ accumulator [Tq, Hq*D]: 128 x 32 boxes (128 B rows, SWIZZLE_128B) for the bulk reduce-add
       uint64_t dims[2] = {(uint64_t)Hq * D, (uint64_t)Tq};
       uint64_t strides[1] = {(uint64_t)Hq * D * 4};
@@ -548,7 +559,8 @@ cudaError_t flash_attn_bwd(const void* q, const void* k, const void* v, const vo
   }
   BwdArgs a;
   a.lse = lse; a.delta = delta; a.dq_acc = dq_acc;
-  a.dk = (__nv_bfloat16*)dk; a.dv = (__nv_bfloat16*)dv;
+  a.dk = (uint16_t*)dk; a.dv = (uint16_t*)dv;
+  a.alibi = alibi_slopes; a.alibi_bs = alibi_batch_stride;
   a.cu_q = cu_q; a.cu_k = cu_k;
   a.B = B; a.Sq = Sq; a.Sk = Sk; a.Hq = Hq; a.Hk = Hk;
   a.Tq = Tq;
@@ -560,15 +572,21 @@ cudaError_t flash_attn_bwd(const void* q, const void* k, const void* v, const vo
   a.trace = g_bwd_trace;
   const int max_k = cu_k ? (int)Tk : Sk;
   const int num_k_tiles = (max_k + kTile - 1) / kTile;
-  cudaError_t e = (D == 128) ? launch_bwd<128>(mq, mk, mv, mdo, mdq, a, num_k_tiles, stream)
-                             : launch_bwd<64>(mq, mk, mv, mdo, mdq, a, num_k_tiles, stream);
+  cudaError_t e;
+  if (is_bf16)
+    e = (D == 128) ? launch_bwd<128, true>(mq, mk, mv, mdo, mdq, a, num_k_tiles, stream)
+                   : launch_bwd<64, true>(mq, mk, mv, mdo, mdq, a, num_k_tiles, stream);
+  else
+    e = (D == 128) ? launch_bwd<128, false>(mq, mk, mv, mdo, mdq, a, num_k_tiles, stream)
+                   : launch_bwd<64, false>(mq, mk, mv, mdo, mdq, a, num_k_tiles, stream);
   if (e != cudaSuccess) return e;
   // 3) dq = bf16(dq_acc)
   {
     const long long n = Tq * (long long)(Hq * D / 4);
     long long blocks = (n + 255) / 256;
     if (blocks > (long long)num_sms * 16) blocks = (long long)num_sms * 16;
-    bwd_convert_dq_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dq_acc, (__nv_bfloat16*)dq, Tq, Hq * D, dq_ts);
+    if (is_bf16) bwd_convert_dq_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(dq_acc, (uint16_t*)dq, Tq, Hq * D, dq_ts);
+    else bwd_convert_dq_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(dq_acc, (uint16_t*)dq, Tq, Hq * D, dq_ts);
     e = cudaGetLastError();
   }
   return e;

@@ -32,7 +32,9 @@ constexpr int kFwdThreads = 384;  // 4 control warps + 2 softmax warpgroups (64 
 constexpr float kRescaleThreshold = 8.0f;  // log2 domain
 
 struct FwdArgs {
-  __nv_bfloat16* o;
+  uint16_t* o;                 // bf16 or fp16 (kernel template)
+  const float* alibi;          // optional ALiBi slopes [Hq] (alibi_bs == 0) or [B, Hq]
+  int alibi_bs;
   float* lse;
   const int* cu_q;
   const int* cu_k;
@@ -75,14 +77,14 @@ __device__ __forceinline__ void key_bounds(int row, int q_len, int k_len, int ca
   lo = (wl < 0) ? 0 : max(0, pos - wl);
 }
 
-template <int D>
+template <int D, bool kBf16>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const FwdArgs args) {
   using S = FwdSmem<D>;
   constexpr int kChunks = S::kChunks;
-  constexpr uint32_t kIdescS = make_idesc_f16(kBM, kBN, Major::K, Major::K, true);
-  constexpr uint32_t kIdescO = make_idesc_f16(kBM, D, Major::K, Major::MN, true);
+  constexpr uint32_t kIdescS = make_idesc_f16(kBM, kBN, Major::K, Major::K, kBf16);
+  constexpr uint32_t kIdescO = make_idesc_f16(kBM, D, Major::K, Major::MN, kBf16);
   constexpr uint32_t kTmemS0 = 0, kTmemO = 2 * kBN;
 
   const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -109,8 +111,8 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
   if (n_tiles <= 0) {  // nothing visible: O = 0, LSE = -inf
     for (int r = threadIdx.x; r < min(kBM, q_len - m0); r += blockDim.x) {
-      __nv_bfloat16* op = args.o + (long long)(q_start + m0 + r) * args.o_ts + (long long)h * D;
-      for (int d = 0; d < D; ++d) op[d] = __float2bfloat16(0.f);
+      uint16_t* op = args.o + (long long)(q_start + m0 + r) * args.o_ts + (long long)h * D;
+      for (int d = 0; d < D; ++d) op[d] = 0;
       args.lse[(long long)h * args.Tq + q_start + m0 + r] = -INFINITY;
     }
     return;
@@ -249,7 +251,12 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t lane_off = (q4 * 32u) << 16;
     float* xchg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + S::kXchg);
     float m_used = -INFINITY, l_part = 0.f;
-    const float sl2 = args.scale_log2;
+    // ALiBi: bias -slope * |query position - key| is folded into the scores (log2 units) right after the TMEM load;
+    // the rest of the softmax then runs with scale 1
+    const bool has_alibi = args.alibi != nullptr;
+    const float slope_l2 = has_alibi ? args.alibi[(long long)b * args.alibi_bs + h] * 1.4426950408889634f : 0.f;
+    const float sl2 = has_alibi ? 1.f : args.scale_log2;
+    const int pos_q = min(row, q_len - 1) + (k_len - q_len);
 
     for (int t = 0; t < n_tiles; ++t) {
       const int n0 = (j_lo + t) * kBN + grp * 64;   // first key column owned by this thread
@@ -265,6 +272,15 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free(t & 1));  // S buffer may be overwritten by S(t+2)
 
+      if (has_alibi) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float dist = fabsf((float)(pos_q - (n0 + c * 32 + i)));
+            sv[c][i] = __float_as_uint(fmaf(__uint_as_float(sv[c][i]), args.scale_log2, -slope_l2 * dist));
+          }
+      }
       const bool full_tile = (n0 >= lo) && (n0 + 63 <= hi);
       const bool warp_full = __all_sync(0xffffffffu, full_tile);
       float mx = -INFINITY;
@@ -311,7 +327,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           const float p0 = fast_exp2(fmaf(__uint_as_float(sv[c][2 * i]), sl2, -mref));
           const float p1 = fast_exp2(fmaf(__uint_as_float(sv[c][2 * i + 1]), sl2, -mref));
           psum += p0 + p1;
-          pk[c][i] = pack_bf16x2(p0, p1);
+          pk[c][i] = pack_h2<kBf16>(p0, p1);
         }
       l_part = l_part * alpha + psum;
       if (warp_idx == 4 && lane == 0) TB_FTRACE(4);
@@ -364,7 +380,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     tc_fence_after();
     const float inv_l = (l_run > 0.f) ? (1.f / l_run) : 0.f;
     const bool valid = row < q_len;
-    __nv_bfloat16* op = args.o + (long long)(q_start + row) * args.o_ts + (long long)h * D + grp * (D / 2);
+    uint16_t* op = args.o + (long long)(q_start + row) * args.o_ts + (long long)h * D + grp * (D / 2);
 #pragma unroll
     for (int c = 0; c < D / 64; ++c) {
       uint32_t ov[32];
@@ -374,10 +390,10 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(ov[8 * u + 0]) * inv_l, __uint_as_float(ov[8 * u + 1]) * inv_l);
-          w.y = pack_bf16x2(__uint_as_float(ov[8 * u + 2]) * inv_l, __uint_as_float(ov[8 * u + 3]) * inv_l);
-          w.z = pack_bf16x2(__uint_as_float(ov[8 * u + 4]) * inv_l, __uint_as_float(ov[8 * u + 5]) * inv_l);
-          w.w = pack_bf16x2(__uint_as_float(ov[8 * u + 6]) * inv_l, __uint_as_float(ov[8 * u + 7]) * inv_l);
+          w.x = pack_h2<kBf16>(__uint_as_float(ov[8 * u + 0]) * inv_l, __uint_as_float(ov[8 * u + 1]) * inv_l);
+          w.y = pack_h2<kBf16>(__uint_as_float(ov[8 * u + 2]) * inv_l, __uint_as_float(ov[8 * u + 3]) * inv_l);
+          w.z = pack_h2<kBf16>(__uint_as_float(ov[8 * u + 4]) * inv_l, __uint_as_float(ov[8 * u + 5]) * inv_l);
+          w.w = pack_h2<kBf16>(__uint_as_float(ov[8 * u + 6]) * inv_l, __uint_as_float(ov[8 * u + 7]) * inv_l);
           *reinterpret_cast<uint4*>(op + c * 32 + u * 8) = w;
         }
       }
@@ -401,18 +417,19 @@ static long long* g_fwd_trace = nullptr;
 void flash_attn_fwd_set_trace(long long* p) { g_fwd_trace = p; }
 
 // 3-D tensor map over a token-major [tokens, heads, D] bf16 tensor with token stride `ts` elements.
-static CUtensorMap make_map_thd(const void* base, long long tokens, int heads, int D, long long ts) {
+static CUtensorMap make_map_thd(const void* base, long long tokens, int heads, int D, long long ts, bool bf16) {
   uint64_t dims[3] = {(uint64_t)D, (uint64_t)heads, (uint64_t)tokens};
   uint64_t strides[2] = {(uint64_t)D * 2, (uint64_t)ts * 2};
   uint32_t box[3] = {64, 1, 128};
-  return make_tensor_map(base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  return make_tensor_map(base, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, dims,
+                         strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int D>
+template <int D, bool kBf16>
 static cudaError_t launch_fwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const FwdArgs& a,
                               int max_q_len, cudaStream_t stream) {
   using S = FwdSmem<D>;
-  auto kern = flash_fwd_kernel<D>;
+  auto kern = flash_fwd_kernel<D, kBf16>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
@@ -427,21 +444,24 @@ static cudaError_t launch_fwd(const CUtensorMap& mq, const CUtensorMap& mk, cons
 cudaError_t flash_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const int* cu_q,
                            const int* cu_k, int B, int Sq, int Sk, int Hq, int Hk, int D, long long q_ts,
                            long long k_ts, long long v_ts, long long o_ts, float scale, bool causal, int wl, int wr,
-                           long long Tq, long long Tk, int max_q_len, cudaStream_t stream) {
+                           long long Tq, long long Tk, int max_q_len, bool is_bf16, const float* alibi_slopes,
+                           int alibi_batch_stride, cudaStream_t stream) {
   if (B == 0 || Tq == 0) return cudaSuccess;
   if (D != 64 && D != 128) return cudaErrorInvalidValue;
   if (Hq % Hk != 0) return cudaErrorInvalidValue;
   CUtensorMap mq, mk, mv;
   try {
-    mq = make_map_thd(q, Tq, Hq, D, q_ts);
-    mk = make_map_thd(k, Tk, Hk, D, k_ts);
-    mv = make_map_thd(v, Tk, Hk, D, v_ts);
+    mq = make_map_thd(q, Tq, Hq, D, q_ts, is_bf16);
+    mk = make_map_thd(k, Tk, Hk, D, k_ts, is_bf16);
+    mv = make_map_thd(v, Tk, Hk, D, v_ts, is_bf16);
   } catch (const std::exception& e) {
     fprintf(stderr, "%s\n", e.what());
     return cudaErrorInvalidValue;
   }
   FwdArgs a;
-  a.o = (__nv_bfloat16*)o;
+  a.o = (uint16_t*)o;
+  a.alibi = alibi_slopes;
+  a.alibi_bs = alibi_batch_stride;
   a.lse = lse;
   a.cu_q = cu_q;
   a.cu_k = cu_k;
@@ -454,8 +474,12 @@ cudaError_t flash_attn_fwd(const void* q, const void* k, const void* v, void* o,
   a.trace = g_fwd_trace;
   const int mq_len = cu_q ? (max_q_len > 0 ? max_q_len : (int)Tq) : Sq;
   a.num_q_tiles = (mq_len + kBM - 1) / kBM;
-  if (D == 128) return launch_fwd<128>(mq, mk, mv, a, mq_len, stream);
-  return launch_fwd<64>(mq, mk, mv, a, mq_len, stream);
+  if (is_bf16) {
+    if (D == 128) return launch_fwd<128, true>(mq, mk, mv, a, mq_len, stream);
+    return launch_fwd<64, true>(mq, mk, mv, a, mq_len, stream);
+  }
+  if (D == 128) return launch_fwd<128, false>(mq, mk, mv, a, mq_len, stream);
+  return launch_fwd<64, false>(mq, mk, mv, a, mq_len, stream);
 }
 
 }  // namespace tb

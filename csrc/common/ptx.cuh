@@ -429,6 +429,25 @@ TB_DEVICE float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+TB_DEVICE uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+TB_DEVICE float2 unpack_f16x2(uint32_t u) {
+  __half2 v = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(v);
+}
+// 16-bit float pair in the kernel's element type (bf16 or fp16)
+template <bool kBf16>
+TB_DEVICE uint32_t pack_h2(float lo, float hi) {
+  if constexpr (kBf16) return pack_bf16x2(lo, hi);
+  else return pack_f16x2(lo, hi);
+}
+template <bool kBf16>
+TB_DEVICE float2 unpack_h2(uint32_t u) {
+  if constexpr (kBf16) return unpack_bf16x2(u);
+  else return unpack_f16x2(u);
+}
 TB_DEVICE float fast_exp2(float x) {
   float y;
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

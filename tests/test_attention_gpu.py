@@ -107,3 +107,71 @@ def test_qkvpacked_tokens_fwd_bwd():
     _check(out, ref.reshape(T, hq * D), "out")
     _check(qkv.grad, x.grad, "dqkv")
     A.set_attention_backend("auto")
+
+
+# ---- reference parametrisation (tests/ops/test_flash_attn.py:41-181): dtype x mha/mqa/gqa x alibi x local x causal x
+# head_dim {32, 96, 111 -> n/a (not a multiple of 8), 128} x seqlen pairs -- including the cases the reference skips
+FEATURE_CASES = [
+    # dtype,        B, Sq,  Sk,  Hq, Hk, D,   causal, window,    alibi
+    (torch.float16, 2, 256, 256, 4, 4, 128, True, (-1, -1), False),
+    (torch.float16, 1, 384, 384, 8, 2, 64, False, (-1, -1), False),
+    (torch.float16, 1, 200, 328, 4, 1, 128, True, (64, 0), True),
+    (torch.bfloat16, 2, 256, 256, 4, 4, 128, True, (-1, -1), True),       # ALiBi, causal
+    (torch.bfloat16, 1, 130, 390, 4, 2, 128, False, (-1, -1), True),      # ALiBi, Sq != Sk, non-causal
+    (torch.bfloat16, 1, 512, 512, 6, 6, 64, True, (128, 0), True),        # ALiBi + sliding window
+    (torch.bfloat16, 2, 256, 256, 4, 2, 32, True, (-1, -1), False),       # head_dim 32 (zero-padded to 64)
+    (torch.bfloat16, 1, 320, 320, 4, 4, 96, False, (-1, -1), False),      # head_dim 96 (padded to 128)
+    (torch.float16, 1, 256, 256, 2, 2, 96, True, (-1, -1), True),         # fp16 + head_dim 96 + ALiBi
+]
+
+
+@pytest.mark.parametrize("dtype,B,Sq,Sk,Hq,Hk,D,causal,window,alibi", FEATURE_CASES)
+def test_flash_attn_features(dtype, B, Sq, Sk, Hq, Hk, D, causal, window, alibi):
+    from torchacc_b200.ops import attention as A
+    from torchacc_b200 import _native as nat
+    A.set_attention_backend("native")
+    g = torch.Generator(device="cuda").manual_seed(7)
+    mk = lambda *shape: (torch.randn(*shape, device="cuda", generator=g) * 0.8).to(dtype)
+    q, k, v = mk(B, Sq, Hq, D), mk(B, Sk, Hk, D), mk(B, Sk, Hk, D)
+    q.requires_grad_(); k.requires_grad_(); v.requires_grad_()
+    slopes = (torch.rand(B, Hq, device="cuda", generator=g) * 0.3) if alibi else None
+    n0 = nat.LAUNCHES
+    out, lse, _ = A.flash_attn_func(q, k, v, causal=causal, window_size=window, alibi_slopes=slopes,
+                                    return_attn_probs=True)
+    assert nat.LAUNCHES > n0, "native attention kernel was not launched"
+    assert out.dtype == dtype and out.shape == q.shape
+    do = mk(B, Sq, Hq, D)
+    out.backward(do)
+    qf, kf, vf = (t.detach().float().requires_grad_() for t in (q, k, v))
+    ref, lse_ref = A.attention_reference(qf, kf, vf, None, causal, window, slopes)
+    ref.backward(do.float())
+    tol = 2e-2 if dtype == torch.bfloat16 else 6e-3
+    _check(out, ref, "out", tol, tol)
+    fin = torch.isfinite(lse_ref)
+    _check(lse[fin], lse_ref[fin], "lse", 1e-2, 1e-2)
+    _check(v.grad, vf.grad, "dv", tol, tol)
+    _check(k.grad, kf.grad, "dk", tol, tol)
+    _check(q.grad, qf.grad, "dq", tol, tol)
+
+
+@pytest.mark.parametrize("S", [4096, 8192])
+def test_flash_attn_long_sequence(S):
+    """the bench shape (B=2, H=32/8, D=128, causal) and twice its length: forward + backward vs the fp32 oracle on a
+    head subset (the oracle materialises [H, S, S])"""
+    from torchacc_b200.ops import attention as A
+    A.set_attention_backend("native")
+    B, Hq, Hk, D = 1, 8, 2, 128
+    g = torch.Generator(device="cuda").manual_seed(11)
+    mk = lambda *shape: (torch.randn(*shape, device="cuda", generator=g) * 0.7).bfloat16()
+    q, k, v = mk(B, S, Hq, D), mk(B, S, Hk, D), mk(B, S, Hk, D)
+    q.requires_grad_(); k.requires_grad_(); v.requires_grad_()
+    out = A.flash_attn_func(q, k, v, causal=True)
+    do = mk(B, S, Hq, D)
+    out.backward(do)
+    qf, kf, vf = (t.detach().float().requires_grad_() for t in (q, k, v))
+    ref, _ = A.attention_reference(qf, kf, vf, None, True, (-1, -1))
+    ref.backward(do.float())
+    _check(out, ref, "out")
+    _check(q.grad, qf.grad, "dq", 3e-2, 3e-2)
+    _check(k.grad, kf.grad, "dk", 3e-2, 3e-2)
+    _check(v.grad, vf.grad, "dv", 3e-2, 3e-2)

@@ -48,18 +48,21 @@ def _warn_once(key, msg):
 
 nat.register_signatures({
     "tb_flash_attn_fwd": ([nat.u64] * 7 + [nat.i32] * 6 + [nat.i64] * 4 + [nat.f32] + [nat.i32] * 3 +
-                          [nat.i64, nat.i64, nat.i32, nat.i32, nat.u64], nat.i32),
+                          [nat.i64, nat.i64, nat.i32, nat.i32, nat.u64, nat.i32, nat.u64, nat.i32], nat.i32),
     "tb_flash_attn_bwd": ([nat.u64] * 13 + [nat.i32] * 6 + [nat.i64] * 4 + [nat.f32] + [nat.i32] * 3 +
-                          [nat.i64] * 5 + [nat.i32, nat.u64], nat.i32),
+                          [nat.i64] * 5 + [nat.i32, nat.u64, nat.i32, nat.u64, nat.i32], nat.i32),
 })
 
 
-def native_supported(q, k, v, dropout_p, alibi_slopes) -> bool:
+def native_supported(q, k, v, dropout_p, alibi_slopes, pad_ok: bool = False) -> bool:
     L = nat.lib()
     if L is None or not hasattr(L, "tb_flash_attn_fwd"):
         return False
     D = q.shape[-1]
-    return (q.is_cuda and q.dtype == torch.bfloat16 and D in (64, 128) and dropout_p == 0.0 and alibi_slopes is None
+    # head dims other than 64 / 128 are zero-padded up to the next supported size by the callers (_pad_head_dim);
+    # ALiBi and fp16 are native; dropout is not
+    d_ok = D in (64, 128) or (pad_ok and D <= 128 and D % 8 == 0)
+    return (q.is_cuda and q.dtype in (torch.bfloat16, torch.float16) and d_ok and dropout_p == 0.0
             and q.stride(-1) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1)
 
 
@@ -114,9 +117,18 @@ def attention_reference(q, k, v, softmax_scale=None, causal=False, window_size=(
 # ------------------------------------------------------------------------------------------------------
 # Native launcher (tokens flattened; see csrc/attn/attn.h)
 # ------------------------------------------------------------------------------------------------------
-def _native_fwd(q3, k3, v3, cu_q, cu_k, B, Sq, Sk, scale, causal, window):
+def _alibi_args(alibi, Hq):
+    """(pointer, batch stride) of fp32 ALiBi slopes given as [Hq] or [B, Hq] (reference flash_attn.py:313-601)."""
+    if alibi is None:
+        return 0, 0
+    assert alibi.dtype == torch.float32 and alibi.is_contiguous() and alibi.shape[-1] == Hq
+    return alibi.data_ptr(), (Hq if alibi.dim() == 2 else 0)
+
+
+def _native_fwd(q3, k3, v3, cu_q, cu_k, B, Sq, Sk, scale, causal, window, alibi=None):
     """q3: [Tq, Hq, D] strided view (token stride arbitrary, head stride D); returns (o [Tq,Hq,D], lse [Hq,Tq])."""
     Tq, Hq, D = q3.shape
+    ap, abs_ = _alibi_args(alibi, Hq)
     Tk, Hk = k3.shape[0], k3.shape[1]
     o = torch.empty((Tq, Hq, D), dtype=q3.dtype, device=q3.device)
     lse = torch.empty((Hq, Tq), dtype=torch.float32, device=q3.device)
@@ -124,15 +136,17 @@ def _native_fwd(q3, k3, v3, cu_q, cu_k, B, Sq, Sk, scale, causal, window):
     nat.check(
         L.tb_flash_attn_fwd(q3.data_ptr(), k3.data_ptr(), v3.data_ptr(), o.data_ptr(), lse.data_ptr(), nat.ptr(cu_q),
                             nat.ptr(cu_k), B, Sq, Sk, Hq, Hk, D, q3.stride(0), k3.stride(0), v3.stride(0), o.stride(0),
-                            scale, int(causal), window[0], window[1], Tq, Tk, 0, nat.num_sms(), nat.stream()),
+                            scale, int(causal), window[0], window[1], Tq, Tk, 0, nat.num_sms(), nat.stream(),
+                            int(q3.dtype == torch.bfloat16), ap, abs_),
         "tb_flash_attn_fwd")
     nat.count_launch()
     return o, lse
 
 
 def _native_bwd(do3, q3, k3, v3, o3, lse, cu_q, cu_k, B, Sq, Sk, scale, causal, window, dq3, dk3, dv3,
-                deterministic=False):
+                deterministic=False, alibi=None):
     Tq, Hq, D = q3.shape
+    ap, abs_ = _alibi_args(alibi, Hq)
     Tk, Hk = k3.shape[0], k3.shape[1]
     dq_acc = torch.empty((Tq, Hq, D), dtype=torch.float32, device=q3.device)
     delta = torch.empty((Hq, Tq), dtype=torch.float32, device=q3.device)
@@ -142,7 +156,8 @@ def _native_bwd(do3, q3, k3, v3, o3, lse, cu_q, cu_k, B, Sq, Sk, scale, causal, 
                             lse.data_ptr(), dq3.data_ptr(), dk3.data_ptr(), dv3.data_ptr(), dq_acc.data_ptr(),
                             delta.data_ptr(), nat.ptr(cu_q), nat.ptr(cu_k), B, Sq, Sk, Hq, Hk, D, q3.stride(0),
                             k3.stride(0), v3.stride(0), do3.stride(0), scale, int(causal), window[0], window[1], Tq,
-                            Tk, dq3.stride(0), dk3.stride(0), dv3.stride(0), nat.num_sms(), nat.stream()),
+                            Tk, dq3.stride(0), dk3.stride(0), dv3.stride(0), nat.num_sms(), nat.stream(),
+                            int(q3.dtype == torch.bfloat16), ap, abs_),
         "tb_flash_attn_bwd")
     nat.count_launch(3)
 
@@ -151,9 +166,10 @@ class _FlashAttnFn(torch.autograd.Function):
     """Token-flattened attention.  q: [Tq,Hq,D], k/v: [Tk,Hk,D] (strided views allowed)."""
 
     @staticmethod
-    def forward(ctx, q3, k3, v3, cu_q, cu_k, B, Sq, Sk, scale, causal, window, deterministic):
-        o, lse = _native_fwd(q3, k3, v3, cu_q, cu_k, B, Sq, Sk, scale, causal, window)
+    def forward(ctx, q3, k3, v3, cu_q, cu_k, B, Sq, Sk, scale, causal, window, deterministic, alibi=None):
+        o, lse = _native_fwd(q3, k3, v3, cu_q, cu_k, B, Sq, Sk, scale, causal, window, alibi)
         ctx.save_for_backward(q3, k3, v3, o, lse, cu_q, cu_k)
+        ctx.alibi = alibi
         ctx.cfg = (B, Sq, Sk, scale, causal, window, deterministic)
         ctx.mark_non_differentiable(lse)
         return o, lse
@@ -166,8 +182,8 @@ class _FlashAttnFn(torch.autograd.Function):
         dq = torch.empty(q3.shape, dtype=q3.dtype, device=q3.device)
         dk = torch.empty(k3.shape, dtype=k3.dtype, device=k3.device)
         dv = torch.empty(v3.shape, dtype=v3.dtype, device=v3.device)
-        _native_bwd(do, q3, k3, v3, o, lse, cu_q, cu_k, B, Sq, Sk, scale, causal, window, dq, dk, dv, det)
-        return dq, dk, dv, None, None, None, None, None, None, None, None, None
+        _native_bwd(do, q3, k3, v3, o, lse, cu_q, cu_k, B, Sq, Sk, scale, causal, window, dq, dk, dv, det, ctx.alibi)
+        return dq, dk, dv, None, None, None, None, None, None, None, None, None, None
 
 
 class _FlashAttnQKVPackedFn(torch.autograd.Function):
@@ -208,12 +224,22 @@ class _FlashAttnQKVPackedFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------------
 # Dispatch helpers
 # ------------------------------------------------------------------------------------------------------
-def _pick_backend(q, k, v, dropout_p, alibi_slopes):
+def _pad_head_dim(*ts):
+    """Zero-pad the head dim to the next native size (64 / 128): zero columns change neither q k^T nor the first D
+    columns of P v, so the caller slices the output back (softmax scale stays 1/sqrt(original D))."""
+    D = ts[0].shape[-1]
+    Dp = 64 if D <= 64 else 128
+    if D == Dp:
+        return ts, D
+    return tuple(F.pad(t, (0, Dp - D)) for t in ts), D
+
+
+def _pick_backend(q, k, v, dropout_p, alibi_slopes, pad_ok: bool = False):
     b = _BACKEND
     if b == "reference" or not q.is_cuda:
         return "reference"
     if b in ("auto", "native"):
-        if native_supported(q, k, v, dropout_p, alibi_slopes):
+        if native_supported(q, k, v, dropout_p, alibi_slopes, pad_ok):
             return "native"
         if b == "native":
             _warn_once(("native-unsupported", q.shape[-1], dropout_p, alibi_slopes is None),
@@ -255,13 +281,16 @@ def flash_attn_func(q, k, v, dropout_p=0.0, softmax_scale=None, causal=False, wi
     Sk, Hk = k.shape[1], k.shape[2]
     scale = softmax_scale if softmax_scale is not None else 1.0 / math.sqrt(D)
     window = tuple(window_size)
-    backend = _pick_backend(q, k, v, dropout_p, alibi_slopes)
+    backend = _pick_backend(q, k, v, dropout_p, alibi_slopes, pad_ok=True)
     if backend == "native":
-        q3 = q.reshape(B * Sq, Hq, D) if q.is_contiguous() else q.contiguous().view(B * Sq, Hq, D)
-        k3 = k.reshape(B * Sk, Hk, D) if k.is_contiguous() else k.contiguous().view(B * Sk, Hk, D)
-        v3 = v.reshape(B * Sk, Hk, D) if v.is_contiguous() else v.contiguous().view(B * Sk, Hk, D)
-        o, lse = _FlashAttnFn.apply(q3, k3, v3, None, None, B, Sq, Sk, scale, causal, window, deterministic)
-        out = o.view(B, Sq, Hq, D)
+        (qp, kp, vp), D0 = _pad_head_dim(q, k, v)
+        Dp = qp.shape[-1]
+        q3 = qp.reshape(B * Sq, Hq, Dp) if qp.is_contiguous() else qp.contiguous().view(B * Sq, Hq, Dp)
+        k3 = kp.reshape(B * Sk, Hk, Dp) if kp.is_contiguous() else kp.contiguous().view(B * Sk, Hk, Dp)
+        v3 = vp.reshape(B * Sk, Hk, Dp) if vp.is_contiguous() else vp.contiguous().view(B * Sk, Hk, Dp)
+        alibi = alibi_slopes.float().contiguous() if alibi_slopes is not None else None
+        o, lse = _FlashAttnFn.apply(q3, k3, v3, None, None, B, Sq, Sk, scale, causal, window, deterministic, alibi)
+        out = o.view(B, Sq, Hq, Dp)[..., :D0]
         if return_attn_probs:
             return out, lse.view(Hq, B, Sq).transpose(0, 1).contiguous(), None
         return out
@@ -301,10 +330,12 @@ def flash_attn_qkvpacked_tokens(qkv, num_q_heads, num_kv_heads, head_dim, batch,
 
 def flash_attn_varlen_cu(q3, k3, v3, cu_q, cu_k, scale, causal, window, return_lse=False):
     """Packed sequences: q3 [Tq,Hq,D], k3/v3 [Tk,Hk,D], cu_* int32 [B+1]."""
-    backend = _pick_backend(q3, k3, v3, 0.0, None)
+    backend = _pick_backend(q3, k3, v3, 0.0, None, pad_ok=True)
     Bn = cu_q.numel() - 1
     if backend == "native":
-        o, lse = _FlashAttnFn.apply(q3, k3, v3, cu_q.int(), cu_k.int(), Bn, 0, 0, scale, causal, window, False)
+        (qp, kp, vp), D0 = _pad_head_dim(q3, k3, v3)
+        o, lse = _FlashAttnFn.apply(qp, kp, vp, cu_q.int(), cu_k.int(), Bn, 0, 0, scale, causal, window, False)
+        o = o[..., :D0]
         return (o, lse) if return_lse else o
     outs, lses = [], []
     cq, ck = cu_q.tolist(), cu_k.tolist()
