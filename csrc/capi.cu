@@ -32,44 +32,47 @@ TB_API int tb_device_info(int device, int* num_sms, int* cc_major, int* cc_minor
 // ---- GEMM -------------------------------------------------------------------------------------------
 TB_API int tb_gemm_bf16(uint64_t A, uint64_t B, uint64_t D, uint64_t bias, int M, int N, int K, long long lda,
                         long long ldb, long long ldd, int a_mn_major, int b_mn_major, int out_fp32, int accumulate,
-                        int cluster, int num_sms, uint64_t stream) {
+                        int cluster, int num_sms, uint64_t stream, int is_fp16) {
   return (int)tb::gemm_bf16(P<void>(A), P<void>(B), P<void>(D), P<void>(bias), M, N, K, lda, ldb, ldd,
                             a_mn_major != 0, b_mn_major != 0, out_fp32 != 0, accumulate != 0, cluster, num_sms,
-                            S(stream));
+                            S(stream), is_fp16 != 0);
 }
 
 TB_API int tb_gemm_sched_mode(int mode) { return tb::gemm_sched_mode(mode); }
 TB_API int tb_gemm_bf16_ex(uint64_t A, uint64_t B, uint64_t D, uint64_t bias, uint64_t C, int M, int N, int K,
                            long long lda, long long ldb, long long ldd, long long ldc, int a_mn_major, int b_mn_major,
-                           int out_fp32, int cluster, int num_sms, uint64_t stream) {
+                           int out_fp32, int cluster, int num_sms, uint64_t stream, int is_fp16) {
   return (int)tb::gemm_bf16_ex(P<void>(A), P<void>(B), P<void>(D), P<void>(bias), P<void>(C), M, N, K, lda, ldb, ldd, ldc,
-                               a_mn_major != 0, b_mn_major != 0, out_fp32 != 0, cluster, num_sms, S(stream));
+                               a_mn_major != 0, b_mn_major != 0, out_fp32 != 0, cluster, num_sms, S(stream),
+                               is_fp16 != 0);
 }
 
 // ---- norm / rope / activation -----------------------------------------------------------------------
 TB_API int tb_rmsnorm_fwd(uint64_t x, uint64_t res, uint64_t w, uint64_t y, uint64_t h_out, uint64_t rstd, int rows,
-                          int H, float eps, int num_sms, uint64_t stream) {
+                          int H, float eps, int num_sms, uint64_t stream, int is_bf16) {
   return (int)tb::rmsnorm_fwd(P<void>(x), P<void>(res), P<void>(w), P<void>(y), P<void>(h_out), P<float>(rstd), rows,
-                              H, eps, num_sms, S(stream));
+                              H, eps, num_sms, is_bf16 != 0, S(stream));
 }
 TB_API int tb_rmsnorm_bwd(uint64_t dy, uint64_t x, uint64_t w, uint64_t rstd, uint64_t dres, uint64_t dx, uint64_t dw,
-                          int dw_rows, int rows, int H, int num_sms, uint64_t stream) {
+                          int dw_rows, int rows, int H, int num_sms, uint64_t stream, int is_bf16) {
   return (int)tb::rmsnorm_bwd(P<void>(dy), P<void>(x), P<void>(w), P<float>(rstd), P<void>(dres), P<void>(dx),
-                              P<float>(dw), dw_rows, rows, H, num_sms, S(stream));
+                              P<float>(dw), dw_rows, rows, H, num_sms, is_bf16 != 0, S(stream));
 }
 TB_API int tb_rope_inplace(uint64_t x, uint64_t cos_t, uint64_t sin_t, uint64_t positions, long long T, int nheads,
-                           int D, long long token_stride, int seq_len, int backward, int num_sms, uint64_t stream) {
+                           int D, long long token_stride, int seq_len, int backward, int num_sms, uint64_t stream,
+                           int is_bf16) {
   return (int)tb::rope_inplace(P<void>(x), P<float>(cos_t), P<float>(sin_t), P<int>(positions), T, nheads, D,
-                               token_stride, seq_len, backward != 0, num_sms, S(stream));
+                               token_stride, seq_len, backward != 0, num_sms, is_bf16 != 0, S(stream));
 }
 TB_API int tb_swiglu_fwd(uint64_t g, uint64_t u, uint64_t h, long long T, int F, long long ldg, long long ldu,
-                         int num_sms, uint64_t stream) {
-  return (int)tb::swiglu_fwd(P<void>(g), P<void>(u), P<void>(h), T, F, ldg, ldu, num_sms, S(stream));
+                         int num_sms, uint64_t stream, int is_bf16) {
+  return (int)tb::swiglu_fwd(P<void>(g), P<void>(u), P<void>(h), T, F, ldg, ldu, num_sms, is_bf16 != 0, S(stream));
 }
 TB_API int tb_swiglu_bwd(uint64_t dh, uint64_t g, uint64_t u, uint64_t dg, uint64_t du, long long T, int F,
-                         long long ldg, long long ldu, long long lddg, long long lddu, int num_sms, uint64_t stream) {
+                         long long ldg, long long ldu, long long lddg, long long lddu, int num_sms, uint64_t stream,
+                         int is_bf16) {
   return (int)tb::swiglu_bwd(P<void>(dh), P<void>(g), P<void>(u), P<void>(dg), P<void>(du), T, F, ldg, ldu, lddg,
-                             lddu, num_sms, S(stream));
+                             lddu, num_sms, is_bf16 != 0, S(stream));
 }
 
 // ---- loss / optimizer -------------------------------------------------------------------------------

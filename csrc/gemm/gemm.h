@@ -6,7 +6,7 @@
 
 namespace tb {
 
-// D[M,N] (+)= A_op[M,K] * B_op[N,K]^T (+ bias).  bf16 inputs, fp32 accumulation in TMEM.
+// D[M,N] (+)= A_op[M,K] * B_op[N,K]^T (+ bias).  bf16 (or, with is_fp16, IEEE fp16) inputs, fp32 accumulation in TMEM.
 //   a_mn_major == false : A stored [M][K] (row pitch lda);  true : A stored [K][M]
 //   b_mn_major == false : B stored [N][K] (row pitch ldb);  true : B stored [K][N]
 //   out_fp32            : D is float32 instead of bf16
@@ -14,7 +14,7 @@ namespace tb {
 //   cluster             : 1 = one CTA per 128x256 tile, 2 = CTA pair per 256x256 tile (cta_group::2)
 cudaError_t gemm_bf16(const void* A, const void* B, void* D, const void* bias, int M, int N, int K, long long lda,
                       long long ldb, long long ldd, bool a_mn_major, bool b_mn_major, bool out_fp32, bool accumulate,
-                      int cluster, int num_sms, cudaStream_t stream);
+                      int cluster, int num_sms, cudaStream_t stream, bool is_fp16 = false);
 
 // Tile scheduling of the unfused GEMM: 1 = dynamic (one cluster per tile, claimed with cluster launch control; robust
 // against SMs that are busy with a concurrent kernel), 0 = static striping over a persistent grid.  mode < 0 queries.
@@ -24,7 +24,7 @@ int gemm_sched_mode(int mode);
 // Used to fuse the transformer residual add into the down-projection epilogue.
 cudaError_t gemm_bf16_ex(const void* A, const void* B, void* D, const void* bias, const void* C, int M, int N, int K,
                          long long lda, long long ldb, long long ldd, long long ldc, bool a_mn_major, bool b_mn_major,
-                         bool out_fp32, int cluster, int num_sms, cudaStream_t stream);
+                         bool out_fp32, int cluster, int num_sms, cudaStream_t stream, bool is_fp16 = false);
 
 // ---- fused tensor-parallel kernels (see the FuseArgs comment in gemm_bf16.cu) ----
 // all-gather -> GEMM: D[world*rows, N] = gather(A)[world*rows, K] * B_op^T.  `a_full` is this rank's symmetric

@@ -72,6 +72,7 @@ struct GemmArgs {
   long long ldc;   // a different C fuses a residual add into the epilogue (h + x W^T).
   int out_fp32;
   int num_m_tiles, num_n_tiles;
+  int fp16;        // operands, bias and 16-bit outputs are IEEE fp16 instead of bf16 (same tiles, other format bits)
   int dynamic;     // 1: grid = one cluster per tile, tiles are claimed with cluster-launch-control (see kernel comment)
   FuseArgs fuse;
   CarryArgs carry;  // slices of pending FSDP collectives moved by warp 3 of every CTA while the tiles run (fused/carry.cuh)
@@ -388,6 +389,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp_idx == 1) {
     // ================================ MMA issuer ================================
     if (is_leader && lane == 0) {
+      // a/b format bits [7,10) / [10,13): 1 = bf16, 0 = fp16
+      const uint32_t idesc = args.fp16 ? (kIdesc & ~((7u << 7) | (7u << 10))) : kIdesc;
       int it = 0, lt = 0;
       int t = cluster_id;
       for (bool more = t < num_tiles; more; more = advance(t, true), ++lt) {
@@ -408,7 +411,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                                        : desc_mnmajor_sw128(smem_a(s), k, 8192);
             const uint64_t db = (kBMajor == Major::K) ? desc_kmajor_sw128(smem_b(s), k)
                                                        : desc_mnmajor_sw128(smem_b(s), k, 8192);
-            umma_ss_f16<kCluster>(tmem_d, da, db, kIdesc, (kb | k) != 0);
+            umma_ss_f16<kCluster>(tmem_d, da, db, idesc, (kb | k) != 0);
           }
           // Release the smem slot once the MMAs that read it retire.
           if constexpr (kCluster == 2) umma_commit_2sm(empty_bar(s), 0x3);
@@ -431,6 +434,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp_idx >= 4) {
     // ================================ Epilogue ================================
     const uint32_t q = warp_idx & 3;  // TMEM lane quarter this warp may read
+    const bool f16 = args.fp16 != 0;
+    auto unpk = [&](uint32_t u) { return f16 ? unpack_f16x2(u) : unpack_bf16x2(u); };
+    auto pk = [&](float a, float b) { return f16 ? pack_f16x2(a, b) : pack_bf16x2(a, b); };
+    auto ld1 = [&](const __nv_bfloat16* p) {
+      return f16 ? __half2float(*reinterpret_cast<const __half*>(p)) : __bfloat162float(*p);
+    };
+    auto st1 = [&](__nv_bfloat16* p, float v) {
+      if (f16) *reinterpret_cast<__half*>(p) = __float2half_rn(v); else *p = __float2bfloat16(v);
+    };
     const uint32_t tempty_leader =
         (kCluster == 2) ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);  // barrier lives in the leader CTA
     int lt = 0;
@@ -522,13 +534,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 b = __ldg(bp + j);
-              float2 f0 = unpack_bf16x2(b.x), f1 = unpack_bf16x2(b.y), f2 = unpack_bf16x2(b.z), f3 = unpack_bf16x2(b.w);
+              float2 f0 = unpk(b.x), f1 = unpk(b.y), f2 = unpk(b.z), f3 = unpk(b.w);
               v[8 * j + 0] += f0.x; v[8 * j + 1] += f0.y; v[8 * j + 2] += f1.x; v[8 * j + 3] += f1.y;
               v[8 * j + 4] += f2.x; v[8 * j + 5] += f2.y; v[8 * j + 6] += f3.x; v[8 * j + 7] += f3.y;
             }
           } else {
             for (int j = 0; j < 32; ++j)
-              if (gcol + j < args.N) v[j] += __bfloat162float(args.bias[gcol + j]);
+              if (gcol + j < args.N) v[j] += ld1(args.bias + gcol + j);
           }
         }
         if (args.out_fp32) {
@@ -561,21 +573,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int j = 0; j < 4; ++j) {
               if (cp) {
                 uint4 old = c4[j];
-                float2 f0 = unpack_bf16x2(old.x), f1 = unpack_bf16x2(old.y), f2 = unpack_bf16x2(old.z), f3 = unpack_bf16x2(old.w);
+                float2 f0 = unpk(old.x), f1 = unpk(old.y), f2 = unpk(old.z), f3 = unpk(old.w);
                 v[8 * j + 0] += f0.x; v[8 * j + 1] += f0.y; v[8 * j + 2] += f1.x; v[8 * j + 3] += f1.y;
                 v[8 * j + 4] += f2.x; v[8 * j + 5] += f2.y; v[8 * j + 6] += f3.x; v[8 * j + 7] += f3.y;
               }
               uint4 o;
-              o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-              o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-              o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              o.x = pk(v[8 * j + 0], v[8 * j + 1]);
+              o.y = pk(v[8 * j + 2], v[8 * j + 3]);
+              o.z = pk(v[8 * j + 4], v[8 * j + 5]);
+              o.w = pk(v[8 * j + 6], v[8 * j + 7]);
               d4[j] = o;
             }
           } else {
             for (int j = 0; j < 32; ++j)
-              if (gcol + j < args.N)
-                dp[j] = __float2bfloat16(v[j] + (cp ? __bfloat162float(cp[j]) : 0.f));
+              if (gcol + j < args.N) st1(dp + j, v[j] + (cp ? ld1(cp + j) : 0.f));
           }
         }
       }
@@ -664,6 +675,7 @@ static bool fill_common(GemmArgs& args, void* D, const void* bias, int M, int N,
   args.num_m_tiles = (M + tile_m - 1) / tile_m;
   args.num_n_tiles = (N + kBlockN - 1) / kBlockN;
   args.dynamic = gemm_sched_mode(-1);
+  args.fp16 = 0;
   memset(&args.fuse, 0, sizeof(args.fuse));
   memset(&args.carry, 0, sizeof(args.carry));
   return true;
@@ -671,14 +683,14 @@ static bool fill_common(GemmArgs& args, void* D, const void* bias, int M, int N,
 
 cudaError_t gemm_bf16(const void* A, const void* B, void* D, const void* bias, int M, int N, int K, long long lda,
                       long long ldb, long long ldd, bool a_mn_major, bool b_mn_major, bool out_fp32, bool accumulate,
-                      int cluster, int num_sms, cudaStream_t stream) {
+                      int cluster, int num_sms, cudaStream_t stream, bool is_fp16) {
   return gemm_bf16_ex(A, B, D, bias, accumulate ? D : nullptr, M, N, K, lda, ldb, ldd, ldd, a_mn_major, b_mn_major,
-                      out_fp32, cluster, num_sms, stream);
+                      out_fp32, cluster, num_sms, stream, is_fp16);
 }
 
 cudaError_t gemm_bf16_ex(const void* A, const void* B, void* D, const void* bias, const void* C, int M, int N, int K,
                          long long lda, long long ldb, long long ldd, long long ldc, bool a_mn_major, bool b_mn_major,
-                         bool out_fp32, int cluster, int num_sms, cudaStream_t stream) {
+                         bool out_fp32, int cluster, int num_sms, cudaStream_t stream, bool is_fp16) {
   if (M <= 0 || N <= 0) return cudaSuccess;
   if (K <= 0) return cudaErrorInvalidValue;
   if (cluster != 1 && cluster != 2) return cudaErrorInvalidValue;
@@ -694,6 +706,7 @@ cudaError_t gemm_bf16_ex(const void* A, const void* B, void* D, const void* bias
   }
   GemmArgs args;
   fill_common(args, D, bias, M, N, K, ldd, out_fp32, C, ldc, cluster);
+  args.fp16 = is_fp16 ? 1 : 0;
   // pending FSDP collectives ride along: bytes proportional to this GEMM's FLOPs (static scheduling only -- under
   // dynamic scheduling warp 3 is the tile scheduler and collectives run as their own kernels)
   if (!args.dynamic) carry_take(2.0 * (double)M * (double)N * (double)K, &args.carry);

@@ -15,14 +15,17 @@ struct alignas(16) bf16x8 {
   uint4 u;
 };
 
+// 8 x 16-bit floats (bf16 or fp16, kernel template parameter) <-> 8 floats
+template <bool kBf16>
 TB_DEVICE void unpack8(const uint4& u, float (&f)[8]) {
-  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  float2 a = unpack_h2<kBf16>(u.x), b = unpack_h2<kBf16>(u.y), c = unpack_h2<kBf16>(u.z), d = unpack_h2<kBf16>(u.w);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
+template <bool kBf16>
 TB_DEVICE uint4 pack8(const float (&f)[8]) {
   uint4 u;
-  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
-  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  u.x = pack_h2<kBf16>(f[0], f[1]); u.y = pack_h2<kBf16>(f[2], f[3]);
+  u.z = pack_h2<kBf16>(f[4], f[5]); u.w = pack_h2<kBf16>(f[6], f[7]);
   return u;
 }
 
@@ -41,7 +44,7 @@ TB_DEVICE float block_reduce_sum(float v, float* red) {
 // ---------------------------------------------------------------------------------------------------
 // RMSNorm forward.  y = (x [+ res]) * rstd * w ;  optionally writes h = x + res (the new residual stream).
 // ---------------------------------------------------------------------------------------------------
-template <int kVpt>
+template <int kVpt, bool kBf16>
 __global__ void __launch_bounds__(kNormThreads)
 rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                    const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y,
@@ -52,7 +55,7 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
 #pragma unroll
   for (int i = 0; i < kVpt; ++i) {
     const int v = threadIdx.x + i * kNormThreads;
-    if (v < nvec) unpack8(__ldg(reinterpret_cast<const uint4*>(w) + v), wv[i]);
+    if (v < nvec) unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(w) + v), wv[i]);
   }
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * H);
@@ -63,15 +66,15 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
     for (int i = 0; i < kVpt; ++i) {
       const int v = threadIdx.x + i * kNormThreads;
       if (v < nvec) {
-        unpack8(xr[v], xv[i]);
+        unpack8<kBf16>(xr[v], xv[i]);
         if (rr) {
           float rv[8];
-          unpack8(rr[v], rv);
+          unpack8<kBf16>(rr[v], rv);
 #pragma unroll
           for (int j = 0; j < 8; ++j) xv[i][j] += rv[j];
-          uint4 hp = pack8(xv[i]);
+          uint4 hp = pack8<kBf16>(xv[i]);
           if (h_out) reinterpret_cast<uint4*>(h_out + (size_t)row * H)[v] = hp;
-          unpack8(hp, xv[i]);  // normalise exactly what the residual stream stores (bf16-rounded)
+          unpack8<kBf16>(hp, xv[i]);  // normalise exactly what the residual stream stores (bf16-rounded)
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) ss += xv[i][j] * xv[i][j];
@@ -87,7 +90,7 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = xv[i][j] * rstd * wv[i][j];
-        reinterpret_cast<uint4*>(y + (size_t)row * H)[v] = pack8(o);
+        reinterpret_cast<uint4*>(y + (size_t)row * H)[v] = pack8<kBf16>(o);
       }
     }
   }
@@ -97,7 +100,7 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
 // row blockIdx.x of dw_partial[gridDim.x, H] (fp32, no atomics; the caller sums the rows).
 // The next row's x / dy / dres are prefetched as raw 16-byte vectors before the current row's block reduction, so two
 // rows of loads are in flight per CTA and the reduction latency is hidden.
-template <int kVpt, int kThreads>
+template <int kVpt, int kThreads, bool kBf16>
 __global__ void __launch_bounds__(kThreads, (kVpt == 1) ? (1024 / kThreads) : 1)
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                    const __nv_bfloat16* __restrict__ w, const float* __restrict__ rstd,
@@ -109,7 +112,7 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
 #pragma unroll
   for (int i = 0; i < kVpt; ++i) {
     const int v = threadIdx.x + i * kThreads;
-    if (v < nvec) unpack8(__ldg(reinterpret_cast<const uint4*>(w) + v), wv[i]);
+    if (v < nvec) unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(w) + v), wv[i]);
 #pragma unroll
     for (int j = 0; j < 8; ++j) dwv[i][j] = 0.f;
   }
@@ -143,8 +146,8 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
       const int v = threadIdx.x + i * kThreads;
       if (v < nvec) {
         float g[8];
-        unpack8(xc[i], xh[i]);
-        unpack8(gc[i], g);
+        unpack8<kBf16>(xc[i], xh[i]);
+        unpack8<kBf16>(gc[i], g);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xh[i][j] *= rs;
@@ -164,11 +167,11 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
         for (int j = 0; j < 8; ++j) o[j] = rs * (gw[i][j] - xh[i][j] * dot);
         if (dres) {
           float r[8];
-          unpack8(rc[i], r);
+          unpack8<kBf16>(rc[i], r);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] += r[j];
         }
-        __stcs(reinterpret_cast<uint4*>(dx + (size_t)row * H) + v, pack8(o));
+        __stcs(reinterpret_cast<uint4*>(dx + (size_t)row * H) + v, pack8<kBf16>(o));
       }
     }
   }
@@ -186,22 +189,24 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
 }
 
 cudaError_t rmsnorm_fwd(const void* x, const void* res, const void* w, void* y, void* h_out, float* rstd, int rows,
-                        int H, float eps, int num_sms, cudaStream_t stream) {
+                        int H, float eps, int num_sms, bool is_bf16, cudaStream_t stream) {
   if (rows == 0) return cudaSuccess;
   if (H % 8 != 0 || H > kNormThreads * 8 * kMaxVec) return cudaErrorInvalidValue;
   int grid = rows < num_sms * 8 ? rows : num_sms * 8;
   const int vpt = (H / 8 + kNormThreads - 1) / kNormThreads;
-#define TB_LAUNCH(V)                                                                                            \
-  rmsnorm_fwd_kernel<V><<<grid, kNormThreads, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res,  \
-                                                           (const __nv_bfloat16*)w, (__nv_bfloat16*)y,          \
-                                                           (__nv_bfloat16*)h_out, rstd, rows, H, eps)
+#define TB_LAUNCH2(V, BF)                                                                                          \
+  rmsnorm_fwd_kernel<V, BF><<<grid, kNormThreads, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res, \
+                                                               (const __nv_bfloat16*)w, (__nv_bfloat16*)y,         \
+                                                               (__nv_bfloat16*)h_out, rstd, rows, H, eps)
+#define TB_LAUNCH(V) do { if (is_bf16) TB_LAUNCH2(V, true); else TB_LAUNCH2(V, false); } while (0)
   if (vpt <= 1) TB_LAUNCH(1); else if (vpt <= 2) TB_LAUNCH(2); else if (vpt <= 4) TB_LAUNCH(4); else TB_LAUNCH(8);
 #undef TB_LAUNCH
+#undef TB_LAUNCH2
   return cudaGetLastError();
 }
 
 cudaError_t rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx,
-                        float* dw, int dw_rows, int rows, int H, int num_sms, cudaStream_t stream) {
+                        float* dw, int dw_rows, int rows, int H, int num_sms, bool is_bf16, cudaStream_t stream) {
   if (rows == 0) return cudaSuccess;
   if (H % 8 != 0 || H > kNormThreads * 8 * kMaxVec) return cudaErrorInvalidValue;
   // dw is a [dw_rows, H] fp32 partial-sum buffer: exactly dw_rows CTAs run and each writes its own row
@@ -213,16 +218,18 @@ cudaError_t rmsnorm_bwd(const void* dy, const void* x, const void* w, const floa
   const bool wide = nvec >= 512;
   const int threads = wide ? 512 : 256;
   const int vpt = (nvec + threads - 1) / threads;
-#define TB_LAUNCH(V, T)                                                                                         \
-  rmsnorm_bwd_kernel<V, T><<<grid, T, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,            \
-                                                    (const __nv_bfloat16*)w, rstd, (const __nv_bfloat16*)dres,   \
-                                                    (__nv_bfloat16*)dx, dw, rows, H)
+#define TB_LAUNCH2(V, T, BF)                                                                                     \
+  rmsnorm_bwd_kernel<V, T, BF><<<grid, T, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,          \
+                                                        (const __nv_bfloat16*)w, rstd, (const __nv_bfloat16*)dres, \
+                                                        (__nv_bfloat16*)dx, dw, rows, H)
+#define TB_LAUNCH(V, T) do { if (is_bf16) TB_LAUNCH2(V, T, true); else TB_LAUNCH2(V, T, false); } while (0)
   if (wide) {
     if (vpt <= 1) TB_LAUNCH(1, 512); else if (vpt <= 2) TB_LAUNCH(2, 512); else TB_LAUNCH(4, 512);
   } else {
     if (vpt <= 1) TB_LAUNCH(1, 256); else TB_LAUNCH(2, 256);
   }
 #undef TB_LAUNCH
+#undef TB_LAUNCH2
   return cudaGetLastError();
 }
 
@@ -231,6 +238,7 @@ cudaError_t rmsnorm_bwd(const void* dy, const void* x, const void* w, const floa
 //   out[:D/2] = x1*cos - x2*sin ; out[D/2:] = x2*cos + x1*sin        (backward: sin -> -sin)
 // cos/sin tables are fp32 [max_pos, D/2]; position of token t is positions[t] or (t % seq_len).
 // ---------------------------------------------------------------------------------------------------
+template <bool kBf16>
 __global__ void __launch_bounds__(256)
 rope_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ cos_t, const float* __restrict__ sin_t,
             const int* __restrict__ positions, long long T, int nheads, int D, long long ts, int seq_len,
@@ -249,8 +257,8 @@ rope_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ cos_t, cons
     uint4 u1 = *reinterpret_cast<uint4*>(base);
     uint4 u2 = *reinterpret_cast<uint4*>(base + half);
     float a[8], b[8], c[8], s[8];
-    unpack8(u1, a);
-    unpack8(u2, b);
+    unpack8<kBf16>(u1, a);
+    unpack8<kBf16>(u2, b);
     const float4* cp = reinterpret_cast<const float4*>(cos_t + (size_t)pos * half + v * 8);
     const float4* sp = reinterpret_cast<const float4*>(sin_t + (size_t)pos * half + v * 8);
     float4 c0 = __ldg(cp), c1 = __ldg(cp + 1), s0 = __ldg(sp), s1 = __ldg(sp + 1);
@@ -263,21 +271,25 @@ rope_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ cos_t, cons
       o1[j] = a[j] * c[j] - b[j] * sn;
       o2[j] = b[j] * c[j] + a[j] * sn;
     }
-    *reinterpret_cast<uint4*>(base) = pack8(o1);
-    *reinterpret_cast<uint4*>(base + half) = pack8(o2);
+    *reinterpret_cast<uint4*>(base) = pack8<kBf16>(o1);
+    *reinterpret_cast<uint4*>(base + half) = pack8<kBf16>(o2);
   }
 }
 
 cudaError_t rope_inplace(void* x, const float* cos_t, const float* sin_t, const int* positions, long long T,
                          int nheads, int D, long long token_stride, int seq_len, bool backward, int num_sms,
-                         cudaStream_t stream) {
+                         bool is_bf16, cudaStream_t stream) {
   if (T == 0 || nheads == 0) return cudaSuccess;
   if (D % 16 != 0 || token_stride % 8 != 0) return cudaErrorInvalidValue;
   long long total = T * nheads * (D / 16);
   long long blocks = (total + 255) / 256;
   int grid = (int)(blocks < (long long)num_sms * 16 ? blocks : (long long)num_sms * 16);
-  rope_kernel<<<grid, 256, 0, stream>>>((__nv_bfloat16*)x, cos_t, sin_t, positions, T, nheads, D, token_stride,
-                                         seq_len, backward ? -1.f : 1.f);
+  if (is_bf16)
+    rope_kernel<true><<<grid, 256, 0, stream>>>((__nv_bfloat16*)x, cos_t, sin_t, positions, T, nheads, D, token_stride,
+                                                 seq_len, backward ? -1.f : 1.f);
+  else
+    rope_kernel<false><<<grid, 256, 0, stream>>>((__nv_bfloat16*)x, cos_t, sin_t, positions, T, nheads, D,
+                                                  token_stride, seq_len, backward ? -1.f : 1.f);
   return cudaGetLastError();
 }
 
@@ -296,6 +308,7 @@ TB_DEVICE float fast_sigmoid(float x) {
 
 // One CTA walks whole rows (no per-element index division); two independent 16-byte vector pairs per thread and
 // iteration keep 4 loads in flight per thread.
+template <bool kBf16>
 __global__ void __launch_bounds__(256)
 swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ g_, const __nv_bfloat16* __restrict__ u_,
                   __nv_bfloat16* __restrict__ h, long long T, int F, long long ldg, long long ldu) {
@@ -311,20 +324,21 @@ swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ g_, const __nv_bfloat16* __r
       uint4 gr1 = gr0, ur1 = ur0;
       if (has1) { gr1 = __ldcs(gp + v1); ur1 = __ldcs(up + v1); }
       float g[8], u[8], o[8];
-      unpack8(gr0, g); unpack8(ur0, u);
+      unpack8<kBf16>(gr0, g); unpack8<kBf16>(ur0, u);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = g[j] * fast_sigmoid(g[j]) * u[j];
-      hp[v] = pack8(o);
+      hp[v] = pack8<kBf16>(o);
       if (has1) {
-        unpack8(gr1, g); unpack8(ur1, u);
+        unpack8<kBf16>(gr1, g); unpack8<kBf16>(ur1, u);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = g[j] * fast_sigmoid(g[j]) * u[j];
-        hp[v1] = pack8(o);
+        hp[v1] = pack8<kBf16>(o);
       }
     }
   }
 }
 
+template <bool kBf16>
 __global__ void __launch_bounds__(256)
 swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ g_,
                   const __nv_bfloat16* __restrict__ u_, __nv_bfloat16* __restrict__ dg_,
@@ -344,7 +358,7 @@ swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __r
       uint4 gr1 = gr0, ur1 = ur0, dr1 = dr0;
       if (has1) { gr1 = __ldcs(gp + v1); ur1 = __ldcs(up + v1); dr1 = __ldcs(dp + v1); }
       float g[8], u[8], d[8], dg[8], du[8];
-      unpack8(gr0, g); unpack8(ur0, u); unpack8(dr0, d);
+      unpack8<kBf16>(gr0, g); unpack8<kBf16>(ur0, u); unpack8<kBf16>(dr0, d);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float sg = fast_sigmoid(g[j]);
@@ -352,10 +366,10 @@ swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __r
         du[j] = d[j] * silu;
         dg[j] = d[j] * u[j] * (sg + silu * (1.f - sg));
       }
-      dgp[v] = pack8(dg);
-      dup[v] = pack8(du);
+      dgp[v] = pack8<kBf16>(dg);
+      dup[v] = pack8<kBf16>(du);
       if (has1) {
-        unpack8(gr1, g); unpack8(ur1, u); unpack8(dr1, d);
+        unpack8<kBf16>(gr1, g); unpack8<kBf16>(ur1, u); unpack8<kBf16>(dr1, d);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float sg = fast_sigmoid(g[j]);
@@ -363,32 +377,41 @@ swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __r
           du[j] = d[j] * silu;
           dg[j] = d[j] * u[j] * (sg + silu * (1.f - sg));
         }
-        dgp[v1] = pack8(dg);
-        dup[v1] = pack8(du);
+        dgp[v1] = pack8<kBf16>(dg);
+        dup[v1] = pack8<kBf16>(du);
       }
     }
   }
 }
 
 cudaError_t swiglu_fwd(const void* g, const void* u, void* h, long long T, int F, long long ldg, long long ldu,
-                       int num_sms, cudaStream_t stream) {
+                       int num_sms, bool is_bf16, cudaStream_t stream) {
   if (T == 0) return cudaSuccess;
   if (F % 8 != 0 || ldg % 8 != 0 || ldu % 8 != 0) return cudaErrorInvalidValue;
   int grid = (int)(T < (long long)num_sms * 8 ? T : (long long)num_sms * 8);
-  swiglu_fwd_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)u, (__nv_bfloat16*)h, T,
-                                               F, ldg, ldu);
+  if (is_bf16)
+    swiglu_fwd_kernel<true><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)u,
+                                                       (__nv_bfloat16*)h, T, F, ldg, ldu);
+  else
+    swiglu_fwd_kernel<false><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)u,
+                                                        (__nv_bfloat16*)h, T, F, ldg, ldu);
   return cudaGetLastError();
 }
 
 cudaError_t swiglu_bwd(const void* dh, const void* g, const void* u, void* dg, void* du, long long T, int F,
-                       long long ldg, long long ldu, long long lddg, long long lddu, int num_sms,
+                       long long ldg, long long ldu, long long lddg, long long lddu, int num_sms, bool is_bf16,
                        cudaStream_t stream) {
   if (T == 0) return cudaSuccess;
   if (F % 8 != 0 || ldg % 8 != 0 || ldu % 8 != 0 || lddg % 8 != 0 || lddu % 8 != 0) return cudaErrorInvalidValue;
   int grid = (int)(T < (long long)num_sms * 8 ? T : (long long)num_sms * 8);
-  swiglu_bwd_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)dh, (const __nv_bfloat16*)g,
-                                               (const __nv_bfloat16*)u, (__nv_bfloat16*)dg, (__nv_bfloat16*)du, T, F,
-                                               ldg, ldu, lddg, lddu);
+  if (is_bf16)
+    swiglu_bwd_kernel<true><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)dh, (const __nv_bfloat16*)g,
+                                                       (const __nv_bfloat16*)u, (__nv_bfloat16*)dg,
+                                                       (__nv_bfloat16*)du, T, F, ldg, ldu, lddg, lddu);
+  else
+    swiglu_bwd_kernel<false><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)dh, (const __nv_bfloat16*)g,
+                                                        (const __nv_bfloat16*)u, (__nv_bfloat16*)dg,
+                                                        (__nv_bfloat16*)du, T, F, ldg, ldu, lddg, lddu);
   return cudaGetLastError();
 }
 

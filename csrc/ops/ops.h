@@ -1,3 +1,4 @@
+// (16-bit kernels take `is_bf16`: false = IEEE fp16 -- reference benchmarks run both, benchmarks/run.sh:8-48)
 // C++ entry points of the bandwidth-bound op kernels (raw pointers + stream; wrapped by csrc/capi.cpp).
 #pragma once
 #include <cuda_runtime.h>
@@ -5,16 +6,17 @@
 namespace tb {
 
 cudaError_t rmsnorm_fwd(const void* x, const void* res, const void* w, void* y, void* h_out, float* rstd, int rows,
-                        int H, float eps, int num_sms, cudaStream_t stream);
+                        int H, float eps, int num_sms, bool is_bf16, cudaStream_t stream);
 cudaError_t rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx,
-                        float* dw_partial, int dw_rows, int rows, int H, int num_sms, cudaStream_t stream);
+                        float* dw_partial, int dw_rows, int rows, int H, int num_sms, bool is_bf16,
+                        cudaStream_t stream);
 cudaError_t rope_inplace(void* x, const float* cos_t, const float* sin_t, const int* positions, long long T,
                          int nheads, int D, long long token_stride, int seq_len, bool backward, int num_sms,
-                         cudaStream_t stream);
+                         bool is_bf16, cudaStream_t stream);
 cudaError_t swiglu_fwd(const void* g, const void* u, void* h, long long T, int F, long long ldg, long long ldu,
-                       int num_sms, cudaStream_t stream);
+                       int num_sms, bool is_bf16, cudaStream_t stream);
 cudaError_t swiglu_bwd(const void* dh, const void* g, const void* u, void* dg, void* du, long long T, int F,
-                       long long ldg, long long ldu, long long lddg, long long lddu, int num_sms,
+                       long long ldg, long long ldu, long long lddg, long long lddu, int num_sms, bool is_bf16,
                        cudaStream_t stream);
 cudaError_t cross_entropy_fwd_bwd(void* logits, const long long* labels, float* loss_rows, float* lse_rows, int n,
                                   int V, long long ld, int ignore_index, const float* scale_ptr, float scale_val,

@@ -368,3 +368,51 @@ def test_fp8_linear_fwd_bwd_close_to_bf16():
     for a, b, what in ((y1, y0, "y"), (x.grad, gx0, "dx"), (w.grad, gw0, "dw")):
         rel = (a.float() - b.float()).norm() / b.float().norm()
         assert rel < 0.06, (what, float(rel))
+
+
+# ---- fp16 operands on the native kernels (reference benchmark matrix is {bf16, fp16}: benchmarks/run.sh:8-48) -----------
+def test_fp16_native_ops_match_fp32_reference():
+    from torchacc_b200 import _native as nat
+    from torchacc_b200.ops import rmsnorm
+    from torchacc_b200.ops.swiglu import swiglu_separate
+    from torchacc_b200.ops.linear import linear
+    torch.manual_seed(0)
+    dev = _dev()
+    T, K, N = 512, 1024, 768
+    x = (torch.randn(T, K, device=dev) * 0.5).half().requires_grad_()
+    w = (torch.randn(N, K, device=dev) * 0.05).half().requires_grad_()
+    b = torch.randn(N, device=dev).half().requires_grad_()
+    n0 = nat.LAUNCHES
+    y = linear(x, w, b)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    assert nat.LAUNCHES - n0 >= 3 and y.dtype == torch.float16
+    xf, wf, bf = (t.detach().float().requires_grad_() for t in (x, w, b))
+    yr = F.linear(xf, wf, bf)
+    yr.backward(dy.float())
+    _close(y, yr, 4e-3, 4e-3 * float(yr.abs().max()), "fp16 linear fwd")
+    _close(x.grad, xf.grad, 4e-3, 4e-3 * float(xf.grad.abs().max()), "fp16 dgrad")
+    _close(w.grad, wf.grad, 4e-3, 4e-3 * float(wf.grad.abs().max()), "fp16 wgrad")
+    # rmsnorm + residual, swiglu
+    h = torch.randn(T, K, device=dev).half().requires_grad_()
+    res = torch.randn(T, K, device=dev).half()
+    g = (torch.rand(K, device=dev) + 0.5).half().requires_grad_()
+    n0 = nat.LAUNCHES
+    yn, hn = rmsnorm(h, g, 1e-5, residual=res)
+    yn.float().square().sum().backward()
+    assert nat.LAUNCHES - n0 >= 2 and yn.dtype == torch.float16
+    hf, gf = h.detach().float().requires_grad_(), g.detach().float().requires_grad_()
+    s = hf + res.float()
+    yr = s * torch.rsqrt(s.pow(2).mean(-1, keepdim=True) + 1e-5) * gf
+    yr.square().sum().backward()
+    _close(yn, yr, 1e-2, 1e-2, "fp16 rmsnorm")        # the kernel normalises the fp16-rounded residual stream
+    _close(h.grad, hf.grad, 3e-2, 3e-2 * float(hf.grad.abs().max()), "fp16 rmsnorm dx")
+    gate, up = torch.randn(T, N, device=dev).half().requires_grad_(), torch.randn(T, N, device=dev).half().requires_grad_()
+    n0 = nat.LAUNCHES
+    o = swiglu_separate(gate, up)
+    o.float().sum().backward()
+    assert nat.LAUNCHES - n0 >= 2 and o.dtype == torch.float16
+    gr, ur = gate.detach().float().requires_grad_(), up.detach().float().requires_grad_()
+    (F.silu(gr) * ur).sum().backward()
+    _close(o, F.silu(gr) * ur, 4e-3, 4e-3, "fp16 swiglu")
+    _close(gate.grad, gr.grad, 6e-3, 6e-3, "fp16 swiglu dgate")

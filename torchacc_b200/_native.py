@@ -22,14 +22,15 @@ u64, i32, i64, f32 = ctypes.c_uint64, ctypes.c_int, ctypes.c_longlong, ctypes.c_
 _SIGS = {
     "tb_abi_version": ([], i32),
     "tb_device_info": ([i32, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i64)], i32),
-    "tb_gemm_bf16": ([u64, u64, u64, u64, i32, i32, i32, i64, i64, i64, i32, i32, i32, i32, i32, i32, u64], i32),
+    "tb_gemm_bf16": ([u64, u64, u64, u64, i32, i32, i32, i64, i64, i64, i32, i32, i32, i32, i32, i32, u64, i32], i32),
     "tb_gemm_sched_mode": ([i32], i32),
-    "tb_gemm_bf16_ex": ([u64, u64, u64, u64, u64, i32, i32, i32, i64, i64, i64, i64, i32, i32, i32, i32, i32, u64], i32),
-    "tb_rmsnorm_fwd": ([u64, u64, u64, u64, u64, u64, i32, i32, f32, i32, u64], i32),
-    "tb_rmsnorm_bwd": ([u64, u64, u64, u64, u64, u64, u64, i32, i32, i32, i32, u64], i32),
-    "tb_rope_inplace": ([u64, u64, u64, u64, i64, i32, i32, i64, i32, i32, i32, u64], i32),
-    "tb_swiglu_fwd": ([u64, u64, u64, i64, i32, i64, i64, i32, u64], i32),
-    "tb_swiglu_bwd": ([u64, u64, u64, u64, u64, i64, i32, i64, i64, i64, i64, i32, u64], i32),
+    "tb_gemm_bf16_ex": ([u64, u64, u64, u64, u64, i32, i32, i32, i64, i64, i64, i64, i32, i32, i32, i32, i32, u64, i32],
+                        i32),
+    "tb_rmsnorm_fwd": ([u64, u64, u64, u64, u64, u64, i32, i32, f32, i32, u64, i32], i32),
+    "tb_rmsnorm_bwd": ([u64, u64, u64, u64, u64, u64, u64, i32, i32, i32, i32, u64, i32], i32),
+    "tb_rope_inplace": ([u64, u64, u64, u64, i64, i32, i32, i64, i32, i32, i32, u64, i32], i32),
+    "tb_swiglu_fwd": ([u64, u64, u64, i64, i32, i64, i64, i32, u64, i32], i32),
+    "tb_swiglu_bwd": ([u64, u64, u64, u64, u64, i64, i32, i64, i64, i64, i64, i32, u64, i32], i32),
     "tb_cross_entropy": ([u64, u64, u64, u64, i32, i32, i64, i32, u64, f32, i32, u64], i32),
     "tb_adamw_flat": ([u64, u64, i32, u64, u64, u64, i64, f32, f32, f32, f32, f32, i32, u64, u64, i32, u64], i32),
     "tb_sqnorm_accumulate": ([u64, i32, i64, u64, f32, i32, u64], i32),
@@ -136,6 +137,18 @@ def num_sms() -> int:
 
 def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+_HALF = (torch.bfloat16, torch.float16)
+
+
+def is_half(*ts) -> bool:
+    """All tensors share one 16-bit float dtype (the native kernels are templated on bf16 / fp16)."""
+    return all(t.dtype == ts[0].dtype for t in ts) and ts[0].dtype in _HALF
+
+
+def bf16_flag(t) -> int:
+    return int(t.dtype == torch.bfloat16)
 
 
 def set_gemm_scheduler(dynamic: bool) -> None:

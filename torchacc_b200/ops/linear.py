@@ -23,7 +23,7 @@ _CLUSTER = int(os.environ.get("TORCHACC_B200_GEMM_CLUSTER", "2"))
 
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_major: bool = False,
          out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, accumulate: bool = False,
-         out_dtype: torch.dtype = torch.bfloat16, addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+         out_dtype: Optional[torch.dtype] = None, addend: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``D[M,N] (+)= A_op[M,K] @ B_op[N,K]^T (+ bias) (+ addend)`` on 2-D bf16 tensors (last dim contiguous).
 
     ``a`` is ``[M,K]`` (or ``[K,M]`` when ``a_mn_major``); ``b`` is ``[N,K]`` (or ``[K,N]`` when ``b_mn_major``).
@@ -42,7 +42,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
     assert K == Kb, f"reduction dims differ: {K} vs {Kb}"
     if out is None:
         assert not accumulate
-        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+        out = torch.empty((M, N), dtype=out_dtype or (a.dtype if a.dtype != torch.float32 else torch.bfloat16),
+                          device=a.device)
     assert not (accumulate and addend is not None)
     if not nat.use_native(a, b):
         A = a.t() if a_mn_major else a
@@ -57,12 +58,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
         else:
             out.copy_(r.to(out.dtype))
         return out
-    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16, "native GEMM is bf16 x bf16"
+    assert a.dtype == b.dtype and a.dtype in (torch.bfloat16, torch.float16), "native GEMM: bf16 x bf16 or fp16 x fp16"
+    f16 = int(a.dtype == torch.float16)
+    assert out.dtype in (a.dtype, torch.float32)
     assert a.stride(1) == 1 and b.stride(1) == 1 and out.stride(1) == 1
     assert a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0, "row pitch must be a multiple of 16 bytes (TMA)"
-    assert out.dtype in (torch.bfloat16, torch.float32)
     if bias is not None:
-        assert bias.dtype == torch.bfloat16 and bias.is_contiguous()
+        assert bias.dtype == a.dtype and bias.is_contiguous()
     L = nat.require()
     if addend is not None:
         assert addend.dtype == out.dtype and addend.shape == out.shape and addend.stride(1) == 1 \
@@ -70,13 +72,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
         nat.check(
             L.tb_gemm_bf16_ex(a.data_ptr(), b.data_ptr(), out.data_ptr(), nat.ptr(bias), addend.data_ptr(), M, N, K,
                               a.stride(0), b.stride(0), out.stride(0), addend.stride(0), int(a_mn_major),
-                              int(b_mn_major), int(out.dtype == torch.float32), _CLUSTER, nat.num_sms(), nat.stream()),
+                              int(b_mn_major), int(out.dtype == torch.float32), _CLUSTER, nat.num_sms(), nat.stream(),
+                              f16),
             "tb_gemm_bf16_ex")
     else:
         nat.check(
             L.tb_gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), nat.ptr(bias), M, N, K, a.stride(0), b.stride(0),
                            out.stride(0), int(a_mn_major), int(b_mn_major), int(out.dtype == torch.float32),
-                           int(accumulate), _CLUSTER, nat.num_sms(), nat.stream()), "tb_gemm_bf16")
+                           int(accumulate), _CLUSTER, nat.num_sms(), nat.stream(), f16), "tb_gemm_bf16")
     nat.count_launch()
     return out
 
@@ -135,7 +138,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
            residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Drop-in for ``F.linear`` (bf16 CUDA tensors go through the tcgen05 GEMM).  ``residual`` (same shape as the
     result) is added inside the GEMM epilogue: ``x @ w.T + bias + residual`` without a separate elementwise pass."""
-    if x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and nat.use_native(x, w):
+    if x.is_cuda and nat.is_half(x, w) and nat.use_native(x, w):
         from . import fp8
         if fp8.enabled() and fp8.eligible(x.reshape(-1, x.shape[-1]), w):
             return fp8.fp8_linear(x, w, bias, residual)          # compute.fp8: block-scaled e4m3 GEMMs (ops/fp8.py)

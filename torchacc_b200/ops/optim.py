@@ -110,13 +110,17 @@ class FusedAdamW(torch.optim.Optimizer):
                 if (p.dtype == torch.float32 and nat.use_native(p, g) and p.is_contiguous() and g.is_contiguous()
                         and g.dtype in (torch.bfloat16, torch.float32)):
                     L = nat.require()
+                    lp_native = lp if (lp is not None and lp.dtype == torch.bfloat16) else None   # kernel writes bf16
                     nat.check(
                         L.tb_adamw_flat(p.data_ptr(), g.data_ptr(), int(g.dtype == torch.bfloat16),
-                                        st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), nat.ptr(lp), p.numel(),
+                                        st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), nat.ptr(lp_native),
+                                        p.numel(),
                                         group["lr"], b1, b2, group["eps"], group["weight_decay"], st["step"],
                                         nat.ptr(self.grad_scale), nat.ptr(self.found_inf), nat.num_sms(),
                                         nat.stream()), "tb_adamw_flat")
                     nat.count_launch()
+                    if lp is not None and lp_native is None:
+                        lp.copy_(p.data.view_as(lp))           # fp16 compute copy: separate cast
                 else:
                     self._reference_update(p, g, st, group, lp)
                 unit = getattr(p, "_tb_unit", None)

@@ -35,7 +35,7 @@ class _RMSNormFn(torch.autograd.Function):
         nat.check(
             L.tb_rmsnorm_fwd(x2.data_ptr(), nat.ptr(r2), w.data_ptr(), y.data_ptr(),
                              h.data_ptr() if r2 is not None else 0, rstd.data_ptr(), rows, H, eps, nat.num_sms(),
-                             nat.stream()), "tb_rmsnorm_fwd")
+                             nat.stream(), nat.bf16_flag(x)), "tb_rmsnorm_fwd")
         nat.count_launch()
         ctx.save_for_backward(h.view(-1, H) if r2 is not None else h, w, rstd)
         ctx.has_res = r2 is not None
@@ -61,7 +61,8 @@ class _RMSNormFn(torch.autograd.Function):
         L = nat.require()
         nat.check(
             L.tb_rmsnorm_bwd(dy2.data_ptr(), h.data_ptr(), w.data_ptr(), rstd.data_ptr(), nat.ptr(dres),
-                             dx.data_ptr(), dw_part.data_ptr(), parts, rows, H, nat.num_sms(), nat.stream()),
+                             dx.data_ptr(), dw_part.data_ptr(), parts, rows, H, nat.num_sms(), nat.stream(),
+                             nat.bf16_flag(h)),
             "tb_rmsnorm_bwd")
         nat.count_launch()
         return dx, dw_part.sum(0).to(w.dtype), (dx if ctx.has_res else None), None, None
@@ -73,7 +74,7 @@ def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-6, residual: 
     ``y = rmsnorm(h) * weight``.  With ``passthrough`` (and no residual) ``h`` is ``x`` itself routed through the
     op, so a consumer of the skip branch sends its gradient into the fused backward kernel instead of a separate
     autograd accumulation pass."""
-    if x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and nat.use_native(x, weight) \
+    if nat.is_half(x, weight) and (residual is None or residual.dtype == x.dtype) and nat.use_native(x, weight) \
             and x.shape[-1] % 8 == 0 and x.shape[-1] <= 16384:
         return _RMSNormFn.apply(x, weight, residual, eps, passthrough)
     y, h = rmsnorm_ref(x, weight, eps, residual)

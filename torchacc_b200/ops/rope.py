@@ -45,12 +45,13 @@ def _rope_ref(x, cos, sin, positions, sign):
 def _apply_inplace(x3: torch.Tensor, cos, sin, positions, seq_len: int, backward: bool):
     """x3: [T, nheads, D] view with stride (ts, D, 1)."""
     T, nh, D = x3.shape
-    if nat.use_native(x3) and x3.dtype == torch.bfloat16 and D % 16 == 0 and x3.stride(2) == 1 \
+    if nat.use_native(x3) and nat.is_half(x3) and D % 16 == 0 and x3.stride(2) == 1 \
             and x3.stride(1) == D and x3.stride(0) % 8 == 0:
         L = nat.require()
         nat.check(
             L.tb_rope_inplace(x3.data_ptr(), cos.data_ptr(), sin.data_ptr(), nat.ptr(positions), T, nh, D,
-                              x3.stride(0), seq_len, int(backward), nat.num_sms(), nat.stream()), "tb_rope_inplace")
+                              x3.stride(0), seq_len, int(backward), nat.num_sms(), nat.stream(),
+                              nat.bf16_flag(x3)), "tb_rope_inplace")
         nat.count_launch()
     else:
         pos = positions

@@ -28,7 +28,7 @@ class _SwiGLUFn(torch.autograd.Function):
         h = torch.empty((*g.shape[:-1], Fdim), dtype=g.dtype, device=g.device)
         L = nat.require()
         nat.check(L.tb_swiglu_fwd(g2.data_ptr(), u2.data_ptr(), h.data_ptr(), T, Fdim, g2.stride(0), u2.stride(0),
-                                  nat.num_sms(), nat.stream()), "tb_swiglu_fwd")
+                                  nat.num_sms(), nat.stream(), nat.bf16_flag(g2)), "tb_swiglu_fwd")
         nat.count_launch()
         ctx.save_for_backward(g2, u2)
         ctx.shape = g.shape
@@ -44,14 +44,15 @@ class _SwiGLUFn(torch.autograd.Function):
         L = nat.require()
         nat.check(
             L.tb_swiglu_bwd(dh2.data_ptr(), g2.data_ptr(), u2.data_ptr(), dg.data_ptr(), du.data_ptr(), T, Fdim,
-                            g2.stride(0), u2.stride(0), dgu.stride(0), dgu.stride(0), nat.num_sms(), nat.stream()),
+                            g2.stride(0), u2.stride(0), dgu.stride(0), dgu.stride(0), nat.num_sms(), nat.stream(),
+                            nat.bf16_flag(g2)),
             "tb_swiglu_bwd")
         nat.count_launch()
         return dg.view(ctx.shape), du.view(ctx.shape)
 
 
 def swiglu_separate(g: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
-    if g.dtype == torch.bfloat16 and u.dtype == torch.bfloat16 and nat.use_native(g, u) and g.shape[-1] % 8 == 0:
+    if nat.is_half(g, u) and nat.use_native(g, u) and g.shape[-1] % 8 == 0:
         return _SwiGLUFn.apply(g, u)
     return (F.silu(g.float()) * u.float()).to(g.dtype)
 
@@ -67,7 +68,7 @@ class _SwiGLUFusedFn(torch.autograd.Function):
         h = torch.empty((*gu.shape[:-1], Fdim), dtype=gu.dtype, device=gu.device)
         L = nat.require()
         nat.check(L.tb_swiglu_fwd(gu2.data_ptr(), gu2.data_ptr() + 2 * Fdim, h.data_ptr(), T, Fdim, gu2.stride(0),
-                                  gu2.stride(0), nat.num_sms(), nat.stream()), "tb_swiglu_fwd")
+                                  gu2.stride(0), nat.num_sms(), nat.stream(), nat.bf16_flag(gu2)), "tb_swiglu_fwd")
         nat.count_launch()
         ctx.save_for_backward(gu2)
         ctx.shape = gu.shape
@@ -84,7 +85,7 @@ class _SwiGLUFusedFn(torch.autograd.Function):
         nat.check(
             L.tb_swiglu_bwd(dh2.data_ptr(), gu2.data_ptr(), gu2.data_ptr() + 2 * Fdim, dgu.data_ptr(),
                             dgu.data_ptr() + 2 * Fdim, T, Fdim, gu2.stride(0), gu2.stride(0), ld, ld, nat.num_sms(),
-                            nat.stream()), "tb_swiglu_bwd")
+                            nat.stream(), nat.bf16_flag(gu2)), "tb_swiglu_bwd")
         nat.count_launch()
         return dgu
 
@@ -92,6 +93,6 @@ class _SwiGLUFusedFn(torch.autograd.Function):
 def swiglu(gu: torch.Tensor) -> torch.Tensor:
     """gu: [..., 2F] with gate in the first half and up in the second half."""
     Fdim = gu.shape[-1] // 2
-    if gu.dtype == torch.bfloat16 and nat.use_native(gu) and Fdim % 8 == 0:
+    if nat.is_half(gu) and nat.use_native(gu) and Fdim % 8 == 0:
         return _SwiGLUFusedFn.apply(gu)
     return (F.silu(gu[..., :Fdim].float()) * gu[..., Fdim:].float()).to(gu.dtype)
