@@ -36,7 +36,14 @@ nat.register_signatures({
                             nat.i32, nat.i32, ctypes.c_uint32, nat.u64, nat.i32, nat.u64], nat.i32),
 })
 
+# Channel map of a domain's signal pad (64 channels x 16 slots): 0-3 first SymmCollectives instance (all-gather,
+# reduce-scatter, all-reduce, all-to-all), 4-7 carried collectives (parallel/carry.py), 8-9 fused TP GEMMs, 16+4k..19+4k
+# the k-th further SymmCollectives instance.  The device protocol requires the collectives of ONE channel to run in the
+# same order on every rank; two users that issue from different streams (the engine's gradient all-reduce on its
+# reduce stream, ring attention's reduce-scatter on the compute stream) therefore get their own channel block
+# (found with the bounded spins on 8 GPUs in round 2: profiles/ring_cp8_deadlock_r2.txt).
 CH_ALL_GATHER, CH_REDUCE_SCATTER, CH_ALL_REDUCE, CH_ALL_TO_ALL, CH_USER0 = 0, 1, 2, 3, 8
+_FIRST_EXTRA_BLOCK, _MAX_BLOCKS = 16, 12
 _PAD_BYTES = 64 * 16 * 4
 
 
@@ -95,6 +102,7 @@ class SymmDomain:
         self.pad_ptrs = self.pad.peer_ptrs
         self.counters = torch.zeros(64, dtype=torch.int32, device=device)
         self.epochs = [0] * 64
+        self._blocks = 0
         dist.barrier(group=group, device_ids=[device.index])
 
     @classmethod
@@ -121,6 +129,16 @@ class SymmDomain:
             if b.contains(t):
                 return b
         return None
+
+    def channel_block(self) -> int:
+        """Base channel of a fresh block of 4 (collective: every rank creates its instances in the same order)."""
+        k = self._blocks
+        self._blocks += 1
+        if k == 0:
+            return 0
+        # blocks are recycled round-robin past the 12th extra instance (long test sessions re-create engines; only
+        # instances that are active at the same time on different streams must not share a block)
+        return _FIRST_EXTRA_BLOCK + 4 * ((k - 1) % _MAX_BLOCKS)
 
     def next_epoch(self, ch: int) -> int:
         self.epochs[ch] += 1
@@ -150,6 +168,7 @@ class SymmCollectives(Collectives):
         self.domain = SymmDomain.get(group, device)
         self.nccl = NcclCollectives(group, world, rank)
         self._staging: Dict[tuple, torch.Tensor] = {}
+        self.ch0 = self.domain.channel_block()          # this instance's channels: ch0 + {AG, RS, AR, A2A}
 
     # buffers the engines hand to all_gather / reduce_scatter should come from here
     def alloc(self, numel: int, dtype: torch.dtype, device=None) -> torch.Tensor:
@@ -175,7 +194,7 @@ class SymmCollectives(Collectives):
         L = nat.require()
         nat.check(
             L.tb_symm_all_gather(buf.peer_ptrs, d.pad_ptrs, off, full.data_ptr(), nbytes, d.rank, d.world,
-                                 CH_ALL_GATHER, d.next_epoch(CH_ALL_GATHER), d.counter_ptr(CH_ALL_GATHER),
+                                 self.ch0 + CH_ALL_GATHER, d.next_epoch(self.ch0 + CH_ALL_GATHER), d.counter_ptr(self.ch0 + CH_ALL_GATHER),
                                  nat.num_sms(), nat.stream()), "tb_symm_all_gather")
         nat.count_launch()
 
@@ -196,8 +215,8 @@ class SymmCollectives(Collectives):
         nat.check(
             L.tb_symm_reduce_scatter(buf.peer_ptrs, d.pad_ptrs, off, out.data_ptr(), n,
                                      int(full.dtype == torch.bfloat16), int(out.dtype == torch.float32), scale, d.rank,
-                                     d.world, CH_REDUCE_SCATTER, d.next_epoch(CH_REDUCE_SCATTER),
-                                     d.counter_ptr(CH_REDUCE_SCATTER), nat.num_sms(), nat.stream()),
+                                     d.world, self.ch0 + CH_REDUCE_SCATTER, d.next_epoch(self.ch0 + CH_REDUCE_SCATTER),
+                                     d.counter_ptr(self.ch0 + CH_REDUCE_SCATTER), nat.num_sms(), nat.stream()),
             "tb_symm_reduce_scatter")
         nat.count_launch()
 
@@ -220,8 +239,9 @@ class SymmCollectives(Collectives):
             L = nat.require()
             nat.check(
                 L.tb_symm_all_gather(buf.peer_ptrs, d.pad_ptrs, st.data_ptr() - buf.ptr, gathered.data_ptr(), m * es,
-                                     d.rank, d.world, CH_ALL_REDUCE, d.next_epoch(CH_ALL_REDUCE),
-                                     d.counter_ptr(CH_ALL_REDUCE), nat.num_sms(), nat.stream()), "tb_symm_all_gather")
+                                     d.rank, d.world, self.ch0 + CH_ALL_REDUCE, d.next_epoch(self.ch0 + CH_ALL_REDUCE),
+                                     d.counter_ptr(self.ch0 + CH_ALL_REDUCE), nat.num_sms(), nat.stream()),
+                "tb_symm_all_gather")
             nat.count_launch()
             red = gathered.view(self.world, m)[:, :n].float().sum(0)
             if scale != 1.0:
@@ -254,6 +274,7 @@ class SymmCollectives(Collectives):
         L = nat.require()
         nat.check(
             L.tb_symm_all_to_all(buf.peer_ptrs, d.pad_ptrs, inp.data_ptr() - buf.ptr, out.data_ptr(),
-                                 n // self.world * es, d.rank, d.world, CH_ALL_TO_ALL, d.next_epoch(CH_ALL_TO_ALL),
-                                 d.counter_ptr(CH_ALL_TO_ALL), nat.num_sms(), nat.stream()), "tb_symm_all_to_all")
+                                 n // self.world * es, d.rank, d.world, self.ch0 + CH_ALL_TO_ALL,
+                                 d.next_epoch(self.ch0 + CH_ALL_TO_ALL), d.counter_ptr(self.ch0 + CH_ALL_TO_ALL),
+                                 nat.num_sms(), nat.stream()), "tb_symm_all_to_all")
         nat.count_launch()
