@@ -176,6 +176,13 @@ def make_carry(coll, device: torch.device) -> Optional[CarryRuntime]:
     import os
     if device.type != "cuda" or not hasattr(coll, "domain") or not available():
         return None
-    if os.environ.get("TORCHACC_B200_CARRY", "1") == "0":
+    mode = os.environ.get("TORCHACC_B200_CARRY", "auto")
+    if mode == "0":
+        return None
+    if mode == "auto" and coll.domain.world > 2:
+        # measured (profiles/carry_n8_r2.txt): carried collectives win at 2 GPUs (502-507 vs 510-512 ms / step) and
+        # lose at 8 (528-565 vs 511-515 ms): with 8 ranks a reduce stage is eight 1 KB bulk loads and every GEMM CTA's
+        # copy warp fans in from 7 peers.  Until the copy role uses larger per-peer stages the stand-alone TMA
+        # collectives (side streams, communication windows) stay the default beyond 2 ranks; TORCHACC_B200_CARRY=1 forces it.
         return None
     return CarryRuntime(coll, device)
