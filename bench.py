@@ -502,7 +502,7 @@ def run_torch_fsdp(a):
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29533")
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
-    model, hf = hf_llama(a, torch, device, world)
+    model, hf = hf_llama(a, torch, device, 1)          # built on the GPU (32 GB fp32), FSDP shards it from there
     for m in model.modules():
         if type(getattr(m, "act_fn", None)).__name__ == "SiLUActivation":
             m.act_fn = torch.nn.SiLU()
