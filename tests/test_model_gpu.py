@@ -84,3 +84,53 @@ def test_grad_accumulation_matches_single_batch():
     g1, g2 = run(False), run(True)
     rel = (g1 - g2).norm() / g1.norm()
     assert rel < 5e-2, float(rel)
+
+
+def test_hf_llama_through_accelerate_uses_native_attention_and_rope():
+    """accelerate(HF LlamaForCausalLM): linears, RMSNorm, SwiGLU, RoPE, attention and the loss run on the native kernels
+    (round-1 review: the HF path fell back to the flash-attn library and HF's elementwise RoPE) and the loss / its
+    trajectory match the un-patched HF model."""
+    import copy
+    transformers = pytest.importorskip("transformers")
+    import torchacc_b200 as ta
+    from torchacc_b200 import _native as nat
+    from torchacc_b200.utils.patch import unpatch_all
+    from transformers import LlamaConfig, LlamaForCausalLM
+    dev = torch.device("cuda", 0)
+    cfg = LlamaConfig(vocab_size=2048, hidden_size=512, intermediate_size=1024, num_hidden_layers=2,
+                      num_attention_heads=8, num_key_value_heads=2, max_position_embeddings=512, rms_norm_eps=1e-5,
+                      tie_word_embeddings=False, attn_implementation="sdpa", use_cache=False)
+    torch.manual_seed(0)
+    ref = LlamaForCausalLM(cfg).to(dev, torch.bfloat16)
+    ours = copy.deepcopy(ref)
+    ids = torch.randint(0, 2048, (2, 256), device=dev)
+    ref_loss = ref(input_ids=ids, labels=ids).loss
+    from transformers.models.llama import modeling_llama as ml
+    saved = [(c, c.forward) for c in (ml.LlamaRMSNorm, ml.LlamaMLP, ml.LlamaForCausalLM)]
+    try:
+        ours.config._attn_implementation = "flash_attention_2"       # HF dispatches to the patched interface
+        c = ta.Config()
+        c.compute.bf16 = True
+        c.dist.fsdp.wrap_layer_cls = {"LlamaDecoderLayer"}
+        model = ta.accelerate(ours, config=c)
+        assert ml.apply_rotary_pos_emb.__name__ == "hf_apply_rotary_pos_emb"
+        n0 = nat.LAUNCHES
+        out = model(input_ids=ids, labels=ids)
+        launches = nat.LAUNCHES - n0
+        assert launches >= 2 * (4 + 2 + 2 + 1 + 1) + 2, launches       # linears + norms + rope + attention + swiglu per layer
+        assert abs(float(out.loss) - float(ref_loss)) < 5e-2, (float(out.loss), float(ref_loss))
+        opt = ta.optim.FusedAdamW(model.parameters(), lr=2e-3)
+        losses = []
+        for _ in range(6):
+            l = model(input_ids=ids, labels=ids).loss
+            l.backward()
+            opt.step()
+            opt.zero_grad()
+            losses.append(float(l))
+        assert losses[-1] < losses[0] - 0.5, losses
+    finally:
+        for cls, f in saved:
+            cls.forward = f
+            if hasattr(cls, "_tb_lce_patched"):
+                del cls._tb_lce_patched
+        unpatch_all()

@@ -31,6 +31,35 @@ def mlp_forward(self, x):
     return linear(swiglu_separate(g, u), self.down_proj.weight, self.down_proj.bias)
 
 
+def hf_apply_rotary_pos_emb(q, k, cos, sin, position_ids=None, unsqueeze_dim=1):
+    """Drop-in for HF ``apply_rotary_pos_emb`` (q/k: [B, H, S, D] views of the [B, S, H, D] projections, cos/sin:
+    [B, S, D] with duplicated halves): one in-place rotate-half kernel per tensor instead of ~10 elementwise / cat
+    launches per layer (reference liger.py:69-70 swaps in liger's Triton RoPE here)."""
+    from .rope import _RopeFn, _rope_ref  # noqa: F401
+    ok = (q.is_cuda and q.dim() == 4 and cos.dim() == 3 and unsqueeze_dim == 1 and q.dtype in (torch.bfloat16, torch.float16)
+          and q.shape[-1] % 16 == 0 and q.transpose(1, 2).is_contiguous() and k.transpose(1, 2).is_contiguous())
+    if not ok:
+        orig = _HF_ROPE_ORIG[0]
+        import inspect
+        if "position_ids" in inspect.signature(orig).parameters:       # transformers < 4.5x
+            return orig(q, k, cos, sin, position_ids, unsqueeze_dim)
+        return orig(q, k, cos, sin, unsqueeze_dim=unsqueeze_dim)
+    B, H, S, D = q.shape
+    half = D // 2
+    cos_t = cos[..., :half].float().reshape(-1, half).contiguous()
+    sin_t = sin[..., :half].float().reshape(-1, half).contiguous()
+    if cos_t.shape[0] != B * S:                                    # broadcast batch dim of the tables
+        cos_t = cos_t.reshape(-1, S, half).expand(B, S, half).reshape(B * S, half).contiguous()
+        sin_t = sin_t.reshape(-1, S, half).expand(B, S, half).reshape(B * S, half).contiguous()
+    q3 = q.transpose(1, 2).reshape(B * S, H, D)
+    k3 = k.transpose(1, 2).reshape(B * S, k.shape[1], D)
+    q3, k3 = _RopeFn.apply(q3, k3, cos_t, sin_t, None, B * S)     # row t of the tables belongs to token t
+    return q3.view(B, S, H, D).transpose(1, 2), k3.view(B, S, k.shape[1], D).transpose(1, 2)
+
+
+_HF_ROPE_ORIG = []
+
+
 def linear_forward(self, x):
     return linear(x, self.weight, self.bias)
 
@@ -76,6 +105,8 @@ def apply_liger_kernel_to_llama(rope: bool = True, cross_entropy: bool = False, 
     does not see; attention itself is redirected by ``utils.patch.patch_fa`` so the flag is accepted and ignored."""
     from transformers.models.llama import modeling_llama
     _patch_family(modeling_llama, "Llama", rms_norm, swiglu, fused_linear_cross_entropy)
+    if rope:
+        _patch_rope(modeling_llama)
 
 
 def apply_liger_kernel_to_qwen2(rope: bool = True, cross_entropy: bool = False, fused_linear_cross_entropy: bool = True,
@@ -83,6 +114,18 @@ def apply_liger_kernel_to_qwen2(rope: bool = True, cross_entropy: bool = False, 
     """Reference liger.py:86-130."""
     from transformers.models.qwen2 import modeling_qwen2
     _patch_family(modeling_qwen2, "Qwen2", rms_norm, swiglu, fused_linear_cross_entropy)
+    if rope:
+        _patch_rope(modeling_qwen2)
+
+
+def _patch_rope(modeling) -> None:
+    from ..utils.patch import _patch_function
+    orig = getattr(modeling, "apply_rotary_pos_emb", None)
+    if orig is None or orig is hf_apply_rotary_pos_emb:
+        return
+    if not _HF_ROPE_ORIG:
+        _HF_ROPE_ORIG.append(orig)
+    _patch_function(modeling, "apply_rotary_pos_emb", hf_apply_rotary_pos_emb, required_params=("q", "k", "cos", "sin"))
 
 
 def patch_linears(model: nn.Module) -> int:
@@ -116,5 +159,10 @@ def apply_liger_kernel(model: Optional[nn.Module] = None) -> None:
                 fn()
             except Exception as e:  # pragma: no cover - depends on the installed transformers
                 logger.debug("kernel patch %s skipped: %s", fn.__name__, e)
+        if wanted:
+            # HF attention call sites (flash_attention_2 / the attention-interface registry) -> our tcgen05 kernels; the
+            # reference does this at import time (torchacc/__init__.py:135), here it happens when a model needs it
+            from ..utils.patch import patch_fa
+            patch_fa()
     if model is not None and not type(model).__module__.startswith("torchacc_b200"):
         patch_linears(model)
