@@ -35,7 +35,7 @@ def hf_apply_rotary_pos_emb(q, k, cos, sin, position_ids=None, unsqueeze_dim=1):
     """Drop-in for HF ``apply_rotary_pos_emb`` (q/k: [B, H, S, D] views of the [B, S, H, D] projections, cos/sin:
     [B, S, D] with duplicated halves): one in-place rotate-half kernel per tensor instead of ~10 elementwise / cat
     launches per layer (reference liger.py:69-70 swaps in liger's Triton RoPE here)."""
-    from .rope import _RopeFn, _rope_ref  # noqa: F401
+    from .rope import _RopeOneFn
     ok = (q.is_cuda and q.dim() == 4 and cos.dim() == 3 and unsqueeze_dim == 1 and q.dtype in (torch.bfloat16, torch.float16)
           and q.shape[-1] % 16 == 0 and q.transpose(1, 2).is_contiguous() and k.transpose(1, 2).is_contiguous())
     if not ok:
@@ -53,7 +53,8 @@ def hf_apply_rotary_pos_emb(q, k, cos, sin, position_ids=None, unsqueeze_dim=1):
         sin_t = sin_t.reshape(-1, S, half).expand(B, S, half).reshape(B * S, half).contiguous()
     q3 = q.transpose(1, 2).reshape(B * S, H, D)
     k3 = k.transpose(1, 2).reshape(B * S, k.shape[1], D)
-    q3, k3 = _RopeFn.apply(q3, k3, cos_t, sin_t, None, B * S)     # row t of the tables belongs to token t
+    q3 = _RopeOneFn.apply(q3, cos_t, sin_t, None, B * S)           # row t of the tables belongs to token t
+    k3 = _RopeOneFn.apply(k3, cos_t, sin_t, None, B * S)
     return q3.view(B, S, H, D).transpose(1, 2), k3.view(B, S, k.shape[1], D).transpose(1, 2)
 
 

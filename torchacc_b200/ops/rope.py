@@ -86,6 +86,30 @@ class _RopeFn(torch.autograd.Function):
         return dq, dk, None, None, None, None
 
 
+class _RopeOneFn(torch.autograd.Function):
+    """In-place RoPE on ONE tensor that may be a view of another tensor (autograd allows an in-place custom Function on
+    a view only when it returns a single tensor -- the HF attention modules hand over views of their projections)."""
+
+    @staticmethod
+    def forward(ctx, x, cos, sin, positions, seq_len):
+        _apply_inplace(x, cos, sin, positions, seq_len, False)
+        ctx.mark_dirty(x)
+        ctx.save_for_backward(cos, sin, positions) if positions is not None else ctx.save_for_backward(cos, sin)
+        ctx.has_pos = positions is not None
+        ctx.seq_len = seq_len
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        if ctx.has_pos:
+            cos, sin, positions = ctx.saved_tensors
+        else:
+            (cos, sin), positions = ctx.saved_tensors, None
+        dx = dx.clone(memory_format=torch.contiguous_format)
+        _apply_inplace(dx, cos, sin, positions, ctx.seq_len, True)
+        return dx, None, None, None, None
+
+
 def apply_rope(q: torch.Tensor, k: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor,
                positions: Optional[torch.Tensor] = None, seq_len: Optional[int] = None):
     """q: [T, Hq, D], k: [T, Hk, D] (token-major, may be strided views).  Returns rotated (q, k); the inputs are
