@@ -227,3 +227,8 @@ TB_API int tb_gemm_mxfp8(uint64_t A, uint64_t sfa, uint64_t B, uint64_t sfb, uin
   return (int)tb::gemm_mxfp8(P<void>(A), P<void>(sfa), P<void>(B), P<void>(sfb), P<void>(D), P<void>(C), M, N, K, lda, ldb,
                              ldd, ldc, out_fp32 != 0, num_sms, S(stream));
 }
+TB_API int tb_gemm_swiglu(uint64_t A, uint64_t Wgu, uint64_t H, uint64_t GU, int M, int F, int K, long long lda,
+                          long long ldb, long long ldh, long long ldgu, int num_sms, uint64_t stream, int is_fp16) {
+  return (int)tb::gemm_swiglu_bf16(P<void>(A), P<void>(Wgu), P<void>(H), P<void>(GU), M, F, K, lda, ldb, ldh, ldgu, num_sms,
+                                   S(stream), is_fp16 != 0);
+}

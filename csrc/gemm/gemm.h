@@ -26,6 +26,12 @@ cudaError_t gemm_bf16_ex(const void* A, const void* B, void* D, const void* bias
                          long long lda, long long ldb, long long ldd, long long ldc, bool a_mn_major, bool b_mn_major,
                          bool out_fp32, int cluster, int num_sms, cudaStream_t stream, bool is_fp16 = false);
 
+// gate|up projection with the SwiGLU activation in the epilogue: H[M][F] = silu(A Wg^T) * (A Wu^T), W_gu = [Wg; Wu]
+// stored [2F][K]; GU (optional, [M][2F]) receives the pre-activation for the backward pass.  F % 128 == 0.
+cudaError_t gemm_swiglu_bf16(const void* A, const void* Wgu, void* H, void* GU, int M, int F, int K, long long lda,
+                             long long ldb, long long ldh, long long ldgu, int num_sms, cudaStream_t stream,
+                             bool is_fp16 = false);
+
 // ---- fused tensor-parallel kernels (see the FuseArgs comment in gemm_bf16.cu) ----
 // all-gather -> GEMM: D[world*rows, N] = gather(A)[world*rows, K] * B_op^T.  `a_full` is this rank's symmetric
 // gathered buffer whose own row block is already filled; `peer_a_full[r]` is rank r's mapping of the same buffer.

@@ -72,6 +72,13 @@ struct GemmArgs {
   long long ldc;   // a different C fuses a residual add into the epilogue (h + x W^T).
   int out_fp32;
   int num_m_tiles, num_n_tiles;
+  // SwiGLU epilogue (gate|up projection, cta_group::2 only): B is W_gu [2F][K]; CTA 0 of a pair stages 128 gate rows,
+  // CTA 1 the matching 128 up rows, so accumulator columns [0,128) / [128,256) are gate / up of the SAME 128 output
+  // columns and the epilogue writes h = silu(g) * u [M][F] directly (and g|u [M][2F] only when the backward needs it).
+  int swiglu;      // 0 / 1
+  int swiglu_F;    // F = intermediate size
+  void* gu_out;    // optional [M][2F] pre-activation (nullptr: not materialised)
+  long long ldgu;
   int fp16;        // operands, bias and 16-bit outputs are IEEE fp16 instead of bf16 (same tiles, other format bits)
   int dynamic;     // 1: grid = one cluster per tile, tiles are claimed with cluster-launch-control (see kernel comment)
   FuseArgs fuse;
@@ -353,7 +360,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         int tm, tn, shard;
         coords(t, tm, tn, shard);
         const int m0 = tm * (int)kUmmaM + (int)cta_rank * kBlockMCta;
-        const int n0 = tn * kBlockN + (int)cta_rank * kLoadN;
+        const int n0 = (kFuse == 0 && args.swiglu) ? tn * kLoadN + (int)cta_rank * args.swiglu_F
+                                                   : tn * kBlockN + (int)cta_rank * kLoadN;
         if constexpr (kFuse == 1) {
           if (shard != args.fuse.rank) {   // wait until the copy clusters have landed this source rank's rows
             spin_until_count(args.fuse.flags + shard, args.fuse.flag_target, args.fuse.rank, shard,
@@ -516,6 +524,61 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         continue;
       }
+      if constexpr (kFuse == 0 && kCluster == 2) {
+        if (args.swiglu) {
+          const int oc0 = tn * 128;     // output columns of this tile
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            __syncwarp();
+            uint32_t rg[32], ru[32];
+            tmem_ld_32x32b_x32(tmem_base + ((q * 32u) << 16) + as * kBlockN + c * 32, rg);
+            tmem_ld_32x32b_x32(tmem_base + ((q * 32u) << 16) + as * kBlockN + 128 + c * 32, ru);
+            tmem_ld_wait();
+            const int gcol = oc0 + c * 32;
+            if (!row_ok || gcol >= args.swiglu_F) continue;
+            __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(args.D) + grow * args.ldd + gcol;
+            uint4* h4 = reinterpret_cast<uint4*>(hp);
+            float hv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float g = __uint_as_float(rg[j]), u = __uint_as_float(ru[j]);
+              float t;
+              asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * g));     // sigmoid(g) = 0.5 + 0.5 tanh(g / 2)
+              hv[j] = g * fmaf(0.5f, t, 0.5f) * u;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pk(hv[8 * j + 0], hv[8 * j + 1]); o.y = pk(hv[8 * j + 2], hv[8 * j + 3]);
+              o.z = pk(hv[8 * j + 4], hv[8 * j + 5]); o.w = pk(hv[8 * j + 6], hv[8 * j + 7]);
+              h4[j] = o;
+            }
+            if (args.gu_out != nullptr) {
+              __nv_bfloat16* gp = reinterpret_cast<__nv_bfloat16*>(args.gu_out) + grow * args.ldgu + gcol;
+              uint4* g4 = reinterpret_cast<uint4*>(gp);
+              uint4* u4 = reinterpret_cast<uint4*>(gp + args.swiglu_F);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 a, b;
+                a.x = pk(__uint_as_float(rg[8 * j + 0]), __uint_as_float(rg[8 * j + 1]));
+                a.y = pk(__uint_as_float(rg[8 * j + 2]), __uint_as_float(rg[8 * j + 3]));
+                a.z = pk(__uint_as_float(rg[8 * j + 4]), __uint_as_float(rg[8 * j + 5]));
+                a.w = pk(__uint_as_float(rg[8 * j + 6]), __uint_as_float(rg[8 * j + 7]));
+                b.x = pk(__uint_as_float(ru[8 * j + 0]), __uint_as_float(ru[8 * j + 1]));
+                b.y = pk(__uint_as_float(ru[8 * j + 2]), __uint_as_float(ru[8 * j + 3]));
+                b.z = pk(__uint_as_float(ru[8 * j + 4]), __uint_as_float(ru[8 * j + 5]));
+                b.w = pk(__uint_as_float(ru[8 * j + 6]), __uint_as_float(ru[8 * j + 7]));
+                g4[j] = a;
+                u4[j] = b;
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_leader + 8u * as);
+          continue;
+        }
+      }
 #pragma unroll 1
       for (int c = 0; c < kBlockN / 32; ++c) {
         __syncwarp();  // tcgen05.ld is warp-collective (.sync.aligned): reconverge after the guarded stores
@@ -676,6 +739,7 @@ static bool fill_common(GemmArgs& args, void* D, const void* bias, int M, int N,
   args.num_n_tiles = (N + kBlockN - 1) / kBlockN;
   args.dynamic = gemm_sched_mode(-1);
   args.fp16 = 0;
+  args.swiglu = 0; args.swiglu_F = 0; args.gu_out = nullptr; args.ldgu = 0;
   memset(&args.fuse, 0, sizeof(args.fuse));
   memset(&args.carry, 0, sizeof(args.carry));
   return true;
@@ -724,6 +788,30 @@ cudaError_t gemm_bf16_ex(const void* A, const void* B, void* D, const void* bias
     TB_DISPATCH(1, Major::MN, Major::MN);
   }
 #undef TB_DISPATCH
+}
+
+// h[M][F] = silu(x Wg^T) * (x Wu^T) with W_gu = [Wg; Wu] ([2F][K], K-major); optionally also gu[M][2F] = x W_gu^T.
+cudaError_t gemm_swiglu_bf16(const void* A, const void* Wgu, void* H, void* GU, int M, int F, int K, long long lda,
+                             long long ldb, long long ldh, long long ldgu, int num_sms, cudaStream_t stream,
+                             bool is_fp16) {
+  if (M <= 0 || F <= 0) return cudaSuccess;
+  if (K <= 0 || F % 128 != 0 || ldh % 8 != 0 || (GU != nullptr && ldgu % 8 != 0)) return cudaErrorInvalidValue;
+  CUtensorMap ta, tbm;
+  try {
+    ta = make_map_2d_bf16(A, M, K, lda, kBlockK, kBlockMCta);
+    tbm = make_map_2d_bf16(Wgu, 2 * (uint64_t)F, K, ldb, kBlockK, kBlockN / 2);
+  } catch (const std::exception& e) {
+    fprintf(stderr, "%s\n", e.what());
+    return cudaErrorInvalidValue;
+  }
+  GemmArgs args;
+  fill_common(args, H, nullptr, M, F, K, ldh, false, nullptr, 0, 2);
+  args.num_n_tiles = F / 128;           // each 256-wide accumulator tile yields 128 output columns
+  args.swiglu = 1; args.swiglu_F = F; args.gu_out = GU; args.ldgu = ldgu;
+  args.fp16 = is_fp16 ? 1 : 0;
+  args.dynamic = 0;                      // the gate/up row pairing relies on the static pair layout
+  carry_take(4.0 * (double)M * (double)F * (double)K, &args.carry);
+  return launch_one<2, Major::K, Major::K, 0>(ta, tbm, args, num_sms, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------

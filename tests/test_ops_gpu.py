@@ -416,3 +416,39 @@ def test_fp16_native_ops_match_fp32_reference():
     (F.silu(gr) * ur).sum().backward()
     _close(o, F.silu(gr) * ur, 4e-3, 4e-3, "fp16 swiglu")
     _close(gate.grad, gr.grad, 6e-3, 6e-3, "fp16 swiglu dgate")
+
+
+def test_gate_up_swiglu_epilogue_matches_separate_ops():
+    """gate|up GEMM with the SwiGLU activation in its epilogue vs GEMM + swiglu kernel: forward, and backward through
+    the kept pre-activation; also the checkpointed form (first pass skips the [T, 2F] write, recompute provides it)."""
+    from torch.utils.checkpoint import checkpoint
+    from torchacc_b200.ops.linear import linear
+    from torchacc_b200.ops.swiglu import activations_recomputed_later, gate_up_swiglu, swiglu
+    torch.manual_seed(3)
+    T, K, Fd = 640, 512, 1280                       # T not a multiple of 256: ragged last M tile
+    x = (torch.randn(T, K, device=_dev()) * 0.7).bfloat16().requires_grad_()
+    w = (torch.randn(2 * Fd, K, device=_dev()) * 0.06).bfloat16().requires_grad_()
+    dh = torch.randn(T, Fd, device=_dev()).bfloat16()
+    h0 = swiglu(linear(x, w))
+    h0.backward(dh)
+    gx0, gw0 = x.grad.clone(), w.grad.clone()
+    x.grad = w.grad = None
+    h1 = gate_up_swiglu(x, w)
+    _close(h1, h0, 2e-2, 2e-2, "fused fwd")          # fused applies silu to the fp32 accumulators (slightly more exact)
+    h1.backward(dh)
+    _close(x.grad, gx0, 2e-2, 2e-2 * float(gx0.abs().max()), "fused dx")
+    _close(w.grad, gw0, 2e-2, 2e-2 * float(gw0.abs().max()), "fused dw")
+    # fp32 oracle for the forward
+    g, u = (x.float() @ w.float().t()).chunk(2, -1)
+    _close(h1, F.silu(g) * u, 2e-2, 2e-2, "fused fwd vs fp32")
+    # checkpointed: the first pass runs with the flag set (no pre-activation written), backward recomputes
+    x.grad = w.grad = None
+
+    def f(a, b):
+        return gate_up_swiglu(a, b)
+    with activations_recomputed_later():
+        h2 = checkpoint(f, x, w, use_reentrant=False)
+    h2.backward(dh)
+    assert torch.equal(h2, h1)
+    _close(x.grad, gx0, 2e-2, 2e-2 * float(gx0.abs().max()), "ckpt dx")
+    _close(w.grad, gw0, 2e-2, 2e-2 * float(gw0.abs().max()), "ckpt dw")

@@ -26,7 +26,7 @@ from ..ops.cross_entropy import cross_entropy, fused_linear_cross_entropy
 from ..ops.linear import linear
 from ..ops.rmsnorm import rmsnorm
 from ..ops.rope import rope_qkv_, rope_tables
-from ..ops.swiglu import swiglu
+from ..ops.swiglu import gate_up_swiglu, swiglu
 
 
 @dataclass
@@ -168,7 +168,9 @@ class LlamaMLP(nn.Module):
             m = row_parallel_linear(swiglu(column_parallel_linear(x, self.gate_up_proj.weight, None, tp)),
                                     self.down_proj.weight, tp)
             return m if residual is None else residual + m
-        return linear(swiglu(linear(x, self.gate_up_proj.weight)), self.down_proj.weight, residual=residual)
+        # gate|up GEMM with the SwiGLU activation in its epilogue (no [T, 2F] round trip), down projection with the
+        # residual add in its epilogue
+        return linear(gate_up_swiglu(x, self.gate_up_proj.weight), self.down_proj.weight, residual=residual)
 
 
 class LlamaDecoderLayer(nn.Module):

@@ -511,7 +511,9 @@ class ShardedUnit(nn.Module):
                 unit.needs_post_backward = False   # root-like unit: finalised by the end-of-backward callback
                 eng.register_final_callback_unit(unit)
         if self.use_gc and grad_on:
-            out = torch_checkpoint(self.module, *args, use_reentrant=False, **kwargs)
+            from ..ops.swiglu import activations_recomputed_later
+            with activations_recomputed_later():        # nothing saved in this pass survives: ops may skip it
+                out = torch_checkpoint(self.module, *args, use_reentrant=False, **kwargs)
         else:
             out = self.module(*args, **kwargs)
         eng.post_forward(unit)

@@ -29,7 +29,9 @@ class CheckpointedModule(nn.Module):
 
     def forward(self, *args, **kwargs):
         if torch.is_grad_enabled():
-            return _ckpt(self.module, *args, use_reentrant=False, **kwargs)
+            from ..ops.swiglu import activations_recomputed_later
+            with activations_recomputed_later():     # what this pass saves is dropped: fused ops skip writing it
+                return _ckpt(self.module, *args, use_reentrant=False, **kwargs)
         return self.module(*args, **kwargs)
 
 
