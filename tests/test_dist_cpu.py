@@ -580,3 +580,49 @@ def _pp_fsdp_worker(rank, world):
 
 def test_pipeline_parallel_x_fsdp_matches_single_process():
     run_distributed(_pp_fsdp_worker, 4)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _hf_cp_worker(rank, world, mode):
+    """accelerate(HF LlamaForCausalLM) with dist.sp.size = 2: sequence sharding + context-parallel attention through
+    HF's attention-interface registry reproduce the single-process loss and gradients."""
+    import torchacc_b200 as ta
+    from transformers import LlamaConfig, LlamaForCausalLM
+    hc = LlamaConfig(vocab_size=160, hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                     num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=64,
+                     attn_implementation="eager", use_cache=False)
+    torch.manual_seed(0)
+    ref_model = LlamaForCausalLM(hc)
+    ids = torch.randint(0, 160, (2, 32), generator=torch.Generator().manual_seed(5))
+    labels = ids.clone()
+    labels[0, :5] = -100                           # uneven numbers of valid labels per shard
+    ref = ref_model(input_ids=ids, labels=labels)
+    ref.loss.backward()
+    ref_grads = {n: p.grad.clone() for n, p in ref_model.named_parameters()}
+    torch.manual_seed(0)
+    model = LlamaForCausalLM(hc)
+    cfg = ta.Config()
+    cfg.dist.sp.size = 2
+    cfg.dist.sp.mode = mode
+    model = ta.accelerate(model, config=cfg)
+    out = model(input_ids=ids, labels=labels)
+    assert abs(float(out.loss) - float(ref.loss)) < 1e-4, (float(out.loss), float(ref.loss))
+    out.loss.backward()
+    eng = model.engine
+    meta = model._inner_engine_module().get_shard_metadata()
+    flat = torch.cat([g.float().reshape(-1) for g in eng.grads()])
+    off = 0
+    for u in meta["units"]:
+        for p in u["params"]:
+            name = (u["prefix"] + "." if u["prefix"] else "") + p["fqn"]
+            name = name[len("model."):] if name.startswith("model.") and name[len("model."):] in ref_grads else name
+            got = flat[off + p["offset"]:off + p["offset"] + p["numel"]]
+            want = ref_grads[name].reshape(-1)
+            assert torch.allclose(got, want, atol=3e-5, rtol=1e-3), (name, float((got - want).abs().max()))
+        off += u["padded"]
+
+
+@pytest.mark.parametrize("mode", ["ulysses", "ring"])
+def test_hf_model_context_parallel_through_accelerate(mode):
+    pytest.importorskip("transformers")
+    run_distributed(_hf_cp_worker, 2, args=(mode,))

@@ -74,12 +74,14 @@ def _make_lce_forward(orig_forward):
             return orig_forward(self, input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
                                 past_key_values=past_key_values, inputs_embeds=inputs_embeds, use_cache=use_cache,
                                 **kwargs)
+        shift = kwargs.pop("shift_labels", None)          # HF's own hook for sequence-sharded batches
         outputs = self.model(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
                              past_key_values=past_key_values, inputs_embeds=inputs_embeds, use_cache=use_cache,
                              **{k: v for k, v in kwargs.items() if k not in ("num_items_in_batch", "logits_to_keep")})
         hidden = outputs[0]
-        shift = torch.full_like(labels, -100)
-        shift[..., :-1] = labels[..., 1:]
+        if shift is None:
+            shift = torch.full_like(labels, -100)
+            shift[..., :-1] = labels[..., 1:]
         loss = fused_linear_cross_entropy(hidden.reshape(-1, hidden.shape[-1]), self.lm_head.weight,
                                           shift.reshape(-1))
         from transformers.modeling_outputs import CausalLMOutputWithPast

@@ -385,11 +385,16 @@ def parallelize_model(model: nn.Module, config, mesh) -> nn.Module:
                        config.dist.fsdp.fused_collectives)
         shard_llama_for_tp(model, tp)
     if config.dist.sp.size > 1:
-        if not hasattr(model, "model") or not hasattr(model.model, "pctx"):
-            raise NotImplementedError("context parallelism hooks exist for the native model families; call "
-                                      "torchacc_b200.ops.context_parallel.* directly from custom attention modules")
-        model.model.pctx.cp_mesh = mesh
-        model.model.pctx.cp_mode = config.dist.sp.mode
+        if hasattr(model, "model") and hasattr(model.model, "pctx"):
+            model.model.pctx.cp_mesh = mesh
+            model.model.pctx.cp_mode = config.dist.sp.mode
+        else:
+            from ..ops.context_parallel.hf_hook import HFContextParallel, is_hf_causal_lm
+            if not is_hf_causal_lm(model):
+                raise NotImplementedError(
+                    "context parallelism is wired for the native model families and for HuggingFace causal LMs; call "
+                    "torchacc_b200.ops.context_parallel.* directly from custom attention modules")
+            core = HFContextParallel(model, mesh, config.dist.sp.mode)
     return core
 
 
