@@ -410,3 +410,85 @@ def test_sliding_window_model_matches_masked_reference():
     ref = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2), kk.transpose(1, 2), vv.transpose(1, 2),
                                                            attn_mask=band).transpose(1, 2)
     assert torch.allclose(out, ref, atol=1e-5)
+
+
+# ---- fx tracing + parameter lifting (reference utils/trace.py:21-175) ----------------------------------------------
+class _TraceToy(torch.nn.Module):
+
+    def __init__(self):
+        super().__init__()
+        self.a, self.b = torch.nn.Linear(8, 8), torch.nn.Linear(8, 8)
+        self.scale = torch.nn.Parameter(torch.randn(8))
+        self.register_buffer("shift", torch.randn(8))
+
+    def forward(self, x, flag=None):
+        h = self.a(x) + self.shift
+        return self.b(h) * self.scale
+
+
+def _split_at(gm, target):
+    from torch.fx.passes.split_module import split_module
+    stage, cur = {}, 0
+    for n in gm.graph.nodes:
+        if n.op == "call_module" and n.target == target:
+            cur = 1
+        stage[n] = cur
+    return split_module(gm, gm, lambda n: stage[n])
+
+
+def test_trace_and_lift_single_use_params():
+    from torchacc_b200.utils.trace import lift_single_use_params, trace
+    torch.manual_seed(0)
+    m = _TraceToy()
+    x = torch.randn(3, 8)
+    want = m(x)
+    gm = trace(m, ["x"])
+    split = _split_at(gm, "b")
+    assert sum(n.op == "get_attr" for n in split.graph.nodes) == 2
+    qmap = lift_single_use_params(split)
+    assert qmap == {"submod_0.lifted_shift": "shift", "submod_1.lifted_scale": "scale"}
+    assert not any(n.op == "get_attr" for n in split.graph.nodes)       # every stage owns its tensors now
+    assert "submod_1.lifted_scale" in dict(split.named_parameters())
+    assert "submod_0.lifted_shift" in dict(split.named_buffers())
+    assert torch.allclose(split(x), want)
+    split(x).sum().backward()
+    assert split.submod_1.lifted_scale.grad is not None
+
+
+def test_trace_hf_llama_block_level():
+    """HF forwards cannot be traced whole (kwargs decorators, mask control flow): the block-level trace keeps decoder
+    layers as leaves, reproduces the logits, and splits into stages that own their parameters."""
+    pytest.importorskip("transformers")
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from torchacc_b200.utils.patch import unpatch_all
+    from torchacc_b200.utils.trace import lift_single_use_params, trace
+    hc = LlamaConfig(vocab_size=160, hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                     num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=64,
+                     attn_implementation="eager", use_cache=False)
+    torch.manual_seed(0)
+    m = LlamaForCausalLM(hc)
+    ids = torch.randint(0, 160, (2, 16))
+    pos = torch.arange(16)[None].expand(2, 16)
+    want = m(input_ids=ids, position_ids=pos).logits
+    try:
+        gm = trace(m, ["input_ids", "position_ids"])
+        layer_calls = [n.target for n in gm.graph.nodes if n.op == "call_module" and ".layers." in n.target]
+        assert layer_calls == ["model.model.layers.0", "model.model.layers.1"]
+        assert torch.allclose(gm(ids, pos), want, atol=1e-5)
+        split = _split_at(gm, "model.model.layers.1")
+        qmap = lift_single_use_params(split)
+        assert qmap == {"submod_1.lifted_model_model_norm_weight": "model.model.norm.weight"}
+        assert torch.allclose(split(ids, pos), want, atol=1e-5)
+    finally:
+        unpatch_all()
+
+
+def test_trace_failure_is_loud():
+    from torchacc_b200.utils.trace import trace
+
+    class Bad(torch.nn.Module):
+        def forward(self, x):
+            return x if x.sum() > 0 else -x
+
+    with pytest.raises(Exception):
+        trace(Bad(), ["x"])
