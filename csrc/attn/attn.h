@@ -7,6 +7,31 @@
 
 namespace tb {
 
+// Fixed-length batches only: sequence b starts at token b * q_bs + q_off (keys: b * k_bs + k_off) of the flat token
+// space; a stride of 0 means "dense" (q_bs = Sq, k_bs = Sk).  Blockwise (ring) attention uses it to address the second
+// half of every query sequence or one half of a K/V block in place.
+struct BlockView {
+  int q_bs = 0, q_off = 0, k_bs = 0, k_off = 0;
+};
+
+// Blockwise forward: with `acc` (fp32 [Tq, Hq, D]) the epilogue merges the block into the running (acc, lse) pair and
+// writes the merged result to o; acc_init != 0 for the first block of a row range.
+cudaError_t flash_attn_fwd_ex(const void* q, const void* k, const void* v, void* o, float* lse, const int* cu_q,
+                              const int* cu_k, int B, int Sq, int Sk, int Hq, int Hk, int D, long long q_ts,
+                              long long k_ts, long long v_ts, long long o_ts, float scale, bool causal, int wl, int wr,
+                              long long Tq, long long Tk, int max_q_len, bool is_bf16, const float* alibi_slopes,
+                              int alibi_batch_stride, BlockView view, float* acc, int acc_init, cudaStream_t stream);
+
+// Blockwise backward: phases bit 0 = preprocess (delta = rowsum(dO o O), dq_acc = 0), bit 1 = main kernel (dK/dV of the
+// visited keys, dQ reduce-added into dq_acc), bit 2 = dq = cast(dq_acc).  A ring step runs bit 1 only.
+cudaError_t flash_attn_bwd_ex(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                              const float* lse, void* dq, void* dk, void* dv, float* dq_acc, float* delta,
+                              const int* cu_q, const int* cu_k, int B, int Sq, int Sk, int Hq, int Hk, int D,
+                              long long q_ts, long long k_ts, long long v_ts, long long do_ts, float scale, bool causal,
+                              int wl, int wr, long long Tq, long long Tk, long long dq_ts, long long dk_ts,
+                              long long dv_ts, int num_sms, bool is_bf16, const float* alibi_slopes,
+                              int alibi_batch_stride, BlockView view, int phases, cudaStream_t stream);
+
 cudaError_t flash_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const int* cu_q,
                            const int* cu_k, int B, int Sq, int Sk, int Hq, int Hk, int D, long long q_ts,
                            long long k_ts, long long v_ts, long long o_ts, float scale, bool causal, int wl, int wr,

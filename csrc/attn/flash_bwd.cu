@@ -45,6 +45,7 @@ struct BwdArgs {
   long long dk_ts, dv_ts;
   float scale_log2, scale;
   int causal, wl, wr;
+  int q_bs, q_off, k_bs, k_off;   // fixed-length addressing (attn.h BlockView)
   long long* trace;   // optional [64 iterations][16 slots] clock64 stamps of CTA (0,0,0) (debug / profiling)
 };
 
@@ -88,9 +89,9 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t lane = lane_id();
   const int b = blockIdx.z, hk = blockIdx.y, jt = blockIdx.x;
   const int group = args.Hq / args.Hk;
-  const int q_start = args.cu_q ? args.cu_q[b] : b * args.Sq;
+  const int q_start = args.cu_q ? args.cu_q[b] : b * args.q_bs + args.q_off;
   const int q_len = args.cu_q ? (args.cu_q[b + 1] - q_start) : args.Sq;
-  const int k_start = args.cu_k ? args.cu_k[b] : b * args.Sk;
+  const int k_start = args.cu_k ? args.cu_k[b] : b * args.k_bs + args.k_off;
   const int k_len = args.cu_k ? (args.cu_k[b + 1] - k_start) : args.Sk;
   const int n0 = jt * kTile;
   if (n0 >= k_len) return;
@@ -524,11 +525,23 @@ cudaError_t flash_attn_bwd(const void* q, const void* k, const void* v, const vo
                            int wl, int wr, long long Tq, long long Tk, long long dq_ts, long long dk_ts,
                            long long dv_ts, int num_sms, bool is_bf16, const float* alibi_slopes,
                            int alibi_batch_stride, cudaStream_t stream) {
+  return flash_attn_bwd_ex(q, k, v, o, dout, lse, dq, dk, dv, dq_acc, delta, cu_q, cu_k, B, Sq, Sk, Hq, Hk, D, q_ts, k_ts,
+                           v_ts, do_ts, scale, causal, wl, wr, Tq, Tk, dq_ts, dk_ts, dv_ts, num_sms, is_bf16,
+                           alibi_slopes, alibi_batch_stride, BlockView{}, 7, stream);
+}
+
+cudaError_t flash_attn_bwd_ex(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                              const float* lse, void* dq, void* dk, void* dv, float* dq_acc, float* delta,
+                              const int* cu_q, const int* cu_k, int B, int Sq, int Sk, int Hq, int Hk, int D,
+                              long long q_ts, long long k_ts, long long v_ts, long long do_ts, float scale, bool causal,
+                              int wl, int wr, long long Tq, long long Tk, long long dq_ts, long long dk_ts,
+                              long long dv_ts, int num_sms, bool is_bf16, const float* alibi_slopes,
+                              int alibi_batch_stride, BlockView view, int phases, cudaStream_t stream) {
   if (B == 0 || Tq == 0 || Tk == 0) return cudaSuccess;
   if (D != 64 && D != 128) return cudaErrorInvalidValue;
   if (Hq % Hk != 0) return cudaErrorInvalidValue;
   // 1) delta = rowsum(dO o O), dq_acc = 0
-  {
+  if (phases & 1) {
     const long long warps = Tq * Hq;
     const long long blocks = (warps * 32 + 255) / 256;
 #define TB_PRE(DD, BF)                                                                                       \
@@ -541,6 +554,8 @@ cudaError_t flash_attn_bwd(const void* q, const void* k, const void* v, const vo
     if (e != cudaSuccess) return e;
   }
   // 2) main kernel
+  cudaError_t e = cudaSuccess;
+  if (phases & 2) {
   CUtensorMap mq, mk, mv, mdo, mdq;
   try {
     mq = make_map_thd_b(q, Tq, Hq, D, q_ts, is_bf16);
@@ -570,9 +585,10 @@ cudaError_t flash_attn_bwd(const void* q, const void* k, const void* v, const vo
   a.causal = causal ? 1 : 0;
   a.wl = wl; a.wr = wr;
   a.trace = g_bwd_trace;
+  a.q_bs = view.q_bs > 0 ? view.q_bs : Sq; a.q_off = view.q_off;
+  a.k_bs = view.k_bs > 0 ? view.k_bs : Sk; a.k_off = view.k_off;
   const int max_k = cu_k ? (int)Tk : Sk;
   const int num_k_tiles = (max_k + kTile - 1) / kTile;
-  cudaError_t e;
   if (is_bf16)
     e = (D == 128) ? launch_bwd<128, true>(mq, mk, mv, mdo, mdq, a, num_k_tiles, stream)
                    : launch_bwd<64, true>(mq, mk, mv, mdo, mdq, a, num_k_tiles, stream);
@@ -580,8 +596,9 @@ cudaError_t flash_attn_bwd(const void* q, const void* k, const void* v, const vo
     e = (D == 128) ? launch_bwd<128, false>(mq, mk, mv, mdo, mdq, a, num_k_tiles, stream)
                    : launch_bwd<64, false>(mq, mk, mv, mdo, mdq, a, num_k_tiles, stream);
   if (e != cudaSuccess) return e;
+  }
   // 3) dq = bf16(dq_acc)
-  {
+  if (phases & 4) {
     const long long n = Tq * (long long)(Hq * D / 4);
     long long blocks = (n + 255) / 256;
     if (blocks > (long long)num_sms * 16) blocks = (long long)num_sms * 16;

@@ -44,6 +44,13 @@ struct FwdArgs {
   float scale_log2;
   int causal, wl, wr;
   int num_q_tiles;
+  // fixed-length addressing: sequence b starts at token b * q_bs + q_off (q_bs == Sq, q_off == 0 for a dense batch);
+  // lets ring attention run on the second half of every sequence, or on half of a K/V block, without copies
+  int q_bs, q_off, k_bs, k_off;
+  // blockwise (ring) attention: when non-null, the epilogue merges this block into the running fp32 accumulator
+  // acc [Tq, Hq, D] / lse in place (log-sum-exp merge) and writes the merged output to o; acc_init: first block
+  float* acc;
+  int acc_init;
   long long* trace;   // optional [64 tiles][16 slots] clock64 stamps of the first CTA (debug / profiling)
 };
 
@@ -92,12 +99,13 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const int b = blockIdx.z, h = blockIdx.y;
   const int hk = h / (args.Hq / args.Hk);
   const int tile = args.num_q_tiles - 1 - (int)blockIdx.x;  // heavy (late) causal tiles first
-  const int q_start = args.cu_q ? args.cu_q[b] : b * args.Sq;
+  const int q_start = args.cu_q ? args.cu_q[b] : b * args.q_bs + args.q_off;
   const int q_len = args.cu_q ? (args.cu_q[b + 1] - q_start) : args.Sq;
-  const int k_start = args.cu_k ? args.cu_k[b] : b * args.Sk;
+  const int k_start = args.cu_k ? args.cu_k[b] : b * args.k_bs + args.k_off;
   const int k_len = args.cu_k ? (args.cu_k[b + 1] - k_start) : args.Sk;
   const int m0 = tile * kBM;
   if (m0 >= q_len) return;
+  const bool merging = args.acc != nullptr;
 
   // KV tile range touched by this query tile
   int lo_first, hi_first, lo_last, hi_last;
@@ -109,10 +117,19 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const int j_hi = (kmax < 0 || kmax < kmin) ? j_lo : (kmax / kBN + 1);
   const int n_tiles = j_hi - j_lo;
 
-  if (n_tiles <= 0) {  // nothing visible: O = 0, LSE = -inf
+  if (n_tiles <= 0) {  // nothing visible: O = 0, LSE = -inf (merging: the running result is unchanged)
     for (int r = threadIdx.x; r < min(kBM, q_len - m0); r += blockDim.x) {
       uint16_t* op = args.o + (long long)(q_start + m0 + r) * args.o_ts + (long long)h * D;
+      if (merging && !args.acc_init) {
+        const float* ap = args.acc + ((long long)(q_start + m0 + r) * args.Hq + h) * D;
+        for (int d = 0; d < D; d += 2) *reinterpret_cast<uint32_t*>(op + d) = pack_h2<kBf16>(ap[d], ap[d + 1]);
+        continue;
+      }
       for (int d = 0; d < D; ++d) op[d] = 0;
+      if (merging) {
+        float* ap = args.acc + ((long long)(q_start + m0 + r) * args.Hq + h) * D;
+        for (int d = 0; d < D; ++d) ap[d] = 0.f;
+      }
       args.lse[(long long)h * args.Tq + q_start + m0 + r] = -INFINITY;
     }
     return;
@@ -257,6 +274,10 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const float slope_l2 = has_alibi ? args.alibi[(long long)b * args.alibi_bs + h] * 1.4426950408889634f : 0.f;
     const float sl2 = has_alibi ? 1.f : args.scale_log2;
     const int pos_q = min(row, q_len - 1) + (k_len - q_len);
+    // running LSE of the previous blocks: read before anybody (group 0 of this row) overwrites it in the epilogue;
+    // the per-tile bar.sync exchanges order this load before that store
+    float lse_prev = -INFINITY;
+    if (merging && !args.acc_init && row < q_len) lse_prev = args.lse[(long long)h * args.Tq + q_start + row];
 
     for (int t = 0; t < n_tiles; ++t) {
       const int n0 = (j_lo + t) * kBN + grp * 64;   // first key column owned by this thread
@@ -380,28 +401,76 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     tc_fence_after();
     const float inv_l = (l_run > 0.f) ? (1.f / l_run) : 0.f;
     const bool valid = row < q_len;
+    const float lse_blk = (l_run > 0.f) ? (m_used + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
     uint16_t* op = args.o + (long long)(q_start + row) * args.o_ts + (long long)h * D + grp * (D / 2);
+    if (!merging) {
 #pragma unroll
-    for (int c = 0; c < D / 64; ++c) {
-      uint32_t ov[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_off + kTmemO + grp * (D / 2) + c * 32, ov);
-      tmem_ld_wait();
-      if (valid) {
+      for (int c = 0; c < D / 64; ++c) {
+        uint32_t ov[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_off + kTmemO + grp * (D / 2) + c * 32, ov);
+        tmem_ld_wait();
+        if (valid) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          uint4 w;
-          w.x = pack_h2<kBf16>(__uint_as_float(ov[8 * u + 0]) * inv_l, __uint_as_float(ov[8 * u + 1]) * inv_l);
-          w.y = pack_h2<kBf16>(__uint_as_float(ov[8 * u + 2]) * inv_l, __uint_as_float(ov[8 * u + 3]) * inv_l);
-          w.z = pack_h2<kBf16>(__uint_as_float(ov[8 * u + 4]) * inv_l, __uint_as_float(ov[8 * u + 5]) * inv_l);
-          w.w = pack_h2<kBf16>(__uint_as_float(ov[8 * u + 6]) * inv_l, __uint_as_float(ov[8 * u + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(op + c * 32 + u * 8) = w;
+          for (int u = 0; u < 4; ++u) {
+            uint4 w;
+            w.x = pack_h2<kBf16>(__uint_as_float(ov[8 * u + 0]) * inv_l, __uint_as_float(ov[8 * u + 1]) * inv_l);
+            w.y = pack_h2<kBf16>(__uint_as_float(ov[8 * u + 2]) * inv_l, __uint_as_float(ov[8 * u + 3]) * inv_l);
+            w.z = pack_h2<kBf16>(__uint_as_float(ov[8 * u + 4]) * inv_l, __uint_as_float(ov[8 * u + 5]) * inv_l);
+            w.w = pack_h2<kBf16>(__uint_as_float(ov[8 * u + 6]) * inv_l, __uint_as_float(ov[8 * u + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(op + c * 32 + u * 8) = w;
+          }
         }
+        __syncwarp();
       }
-      __syncwarp();
+      if (valid && grp == 0) args.lse[(long long)h * args.Tq + q_start + row] = lse_blk;
+    } else {
+      // log-sum-exp merge with the running result: out = acc * w_old + (O / l) * w_new
+      const float mx = fmaxf(lse_prev, lse_blk);
+      float w_old = 0.f, w_new = 0.f, lse_out = -INFINITY;
+      if (mx != -INFINITY) {
+        const float e_old = __expf(lse_prev - mx), e_new = __expf(lse_blk - mx);   // exp(-inf) == 0
+        const float den = e_old + e_new;
+        lse_out = mx + __logf(den);
+        w_old = e_old / den;
+        w_new = inv_l * e_new / den;
+      }
+      float* ap = args.acc + ((long long)(q_start + row) * args.Hq + h) * D + grp * (D / 2);
+      const bool read_acc = !args.acc_init;
+#pragma unroll
+      for (int c = 0; c < D / 64; ++c) {
+        uint32_t ov[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_off + kTmemO + grp * (D / 2) + c * 32, ov);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+            if (read_acc) {
+              a0 = *reinterpret_cast<const float4*>(ap + c * 32 + u * 8);
+              a1 = *reinterpret_cast<const float4*>(ap + c * 32 + u * 8 + 4);
+            }
+            a0.x = fmaf(a0.x, w_old, __uint_as_float(ov[8 * u + 0]) * w_new);
+            a0.y = fmaf(a0.y, w_old, __uint_as_float(ov[8 * u + 1]) * w_new);
+            a0.z = fmaf(a0.z, w_old, __uint_as_float(ov[8 * u + 2]) * w_new);
+            a0.w = fmaf(a0.w, w_old, __uint_as_float(ov[8 * u + 3]) * w_new);
+            a1.x = fmaf(a1.x, w_old, __uint_as_float(ov[8 * u + 4]) * w_new);
+            a1.y = fmaf(a1.y, w_old, __uint_as_float(ov[8 * u + 5]) * w_new);
+            a1.z = fmaf(a1.z, w_old, __uint_as_float(ov[8 * u + 6]) * w_new);
+            a1.w = fmaf(a1.w, w_old, __uint_as_float(ov[8 * u + 7]) * w_new);
+            *reinterpret_cast<float4*>(ap + c * 32 + u * 8) = a0;
+            *reinterpret_cast<float4*>(ap + c * 32 + u * 8 + 4) = a1;
+            uint4 w;
+            w.x = pack_h2<kBf16>(a0.x, a0.y);
+            w.y = pack_h2<kBf16>(a0.z, a0.w);
+            w.z = pack_h2<kBf16>(a1.x, a1.y);
+            w.w = pack_h2<kBf16>(a1.z, a1.w);
+            *reinterpret_cast<uint4*>(op + c * 32 + u * 8) = w;
+          }
+        }
+        __syncwarp();
+      }
+      if (valid && grp == 0) args.lse[(long long)h * args.Tq + q_start + row] = lse_out;
     }
-    if (valid && grp == 0)
-      args.lse[(long long)h * args.Tq + q_start + row] =
-          (l_run > 0.f) ? (m_used + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
   }
 
   __syncwarp();
@@ -446,6 +515,17 @@ cudaError_t flash_attn_fwd(const void* q, const void* k, const void* v, void* o,
                            long long k_ts, long long v_ts, long long o_ts, float scale, bool causal, int wl, int wr,
                            long long Tq, long long Tk, int max_q_len, bool is_bf16, const float* alibi_slopes,
                            int alibi_batch_stride, cudaStream_t stream) {
+  return flash_attn_fwd_ex(q, k, v, o, lse, cu_q, cu_k, B, Sq, Sk, Hq, Hk, D, q_ts, k_ts, v_ts, o_ts, scale, causal, wl,
+                           wr, Tq, Tk, max_q_len, is_bf16, alibi_slopes, alibi_batch_stride, BlockView{}, nullptr, 0,
+                           stream);
+}
+
+cudaError_t flash_attn_fwd_ex(const void* q, const void* k, const void* v, void* o, float* lse, const int* cu_q,
+                              const int* cu_k, int B, int Sq, int Sk, int Hq, int Hk, int D, long long q_ts,
+                              long long k_ts, long long v_ts, long long o_ts, float scale, bool causal, int wl, int wr,
+                              long long Tq, long long Tk, int max_q_len, bool is_bf16, const float* alibi_slopes,
+                              int alibi_batch_stride, BlockView view, float* acc, int acc_init,
+                              cudaStream_t stream) {
   if (B == 0 || Tq == 0) return cudaSuccess;
   if (D != 64 && D != 128) return cudaErrorInvalidValue;
   if (Hq % Hk != 0) return cudaErrorInvalidValue;
@@ -472,6 +552,9 @@ cudaError_t flash_attn_fwd(const void* q, const void* k, const void* v, void* o,
   a.causal = causal ? 1 : 0;
   a.wl = wl; a.wr = wr;
   a.trace = g_fwd_trace;
+  a.q_bs = view.q_bs > 0 ? view.q_bs : Sq; a.q_off = view.q_off;
+  a.k_bs = view.k_bs > 0 ? view.k_bs : Sk; a.k_off = view.k_off;
+  a.acc = acc; a.acc_init = acc_init;
   const int mq_len = cu_q ? (max_q_len > 0 ? max_q_len : (int)Tq) : Sq;
   a.num_q_tiles = (mq_len + kBM - 1) / kBM;
   if (is_bf16) {

@@ -122,6 +122,34 @@ TB_API int tb_flash_attn_bwd(uint64_t q, uint64_t k, uint64_t v, uint64_t o, uin
                                  P<float>(alibi), alibi_bs, S(stream));
 }
 
+// Blockwise (ring) variants: BlockView addressing + in-kernel (out, lse) merge / phased backward (csrc/attn/attn.h).
+TB_API int tb_flash_attn_block_fwd(uint64_t q, uint64_t k, uint64_t v, uint64_t o, uint64_t lse, uint64_t cu_q,
+                                   uint64_t cu_k, int B, int Sq, int Sk, int Hq, int Hk, int D, long long q_ts,
+                                   long long k_ts, long long v_ts, long long o_ts, float scale, int causal, int wl,
+                                   int wr, long long Tq, long long Tk, uint64_t stream, int is_bf16, int q_bs, int q_off,
+                                   int k_bs, int k_off, uint64_t acc, int acc_init) {
+  tb::BlockView view;
+  view.q_bs = q_bs; view.q_off = q_off; view.k_bs = k_bs; view.k_off = k_off;
+  return (int)tb::flash_attn_fwd_ex(P<void>(q), P<void>(k), P<void>(v), P<void>(o), P<float>(lse), P<int>(cu_q),
+                                    P<int>(cu_k), B, Sq, Sk, Hq, Hk, D, q_ts, k_ts, v_ts, o_ts, scale, causal != 0, wl,
+                                    wr, Tq, Tk, 0, is_bf16 != 0, nullptr, 0, view, P<float>(acc), acc_init, S(stream));
+}
+TB_API int tb_flash_attn_block_bwd(uint64_t q, uint64_t k, uint64_t v, uint64_t o, uint64_t dout, uint64_t lse,
+                                   uint64_t dq, uint64_t dk, uint64_t dv, uint64_t dq_acc, uint64_t delta,
+                                   uint64_t cu_q, uint64_t cu_k, int B, int Sq, int Sk, int Hq, int Hk, int D,
+                                   long long q_ts, long long k_ts, long long v_ts, long long do_ts, float scale,
+                                   int causal, int wl, int wr, long long Tq, long long Tk, long long dq_ts,
+                                   long long dk_ts, long long dv_ts, int num_sms, uint64_t stream, int is_bf16, int q_bs,
+                                   int q_off, int k_bs, int k_off, int phases) {
+  tb::BlockView view;
+  view.q_bs = q_bs; view.q_off = q_off; view.k_bs = k_bs; view.k_off = k_off;
+  return (int)tb::flash_attn_bwd_ex(P<void>(q), P<void>(k), P<void>(v), P<void>(o), P<void>(dout), P<float>(lse),
+                                    P<void>(dq), P<void>(dk), P<void>(dv), P<float>(dq_acc), P<float>(delta),
+                                    P<int>(cu_q), P<int>(cu_k), B, Sq, Sk, Hq, Hk, D, q_ts, k_ts, v_ts, do_ts, scale,
+                                    causal != 0, wl, wr, Tq, Tk, dq_ts, dk_ts, dv_ts, num_sms, is_bf16 != 0, nullptr, 0,
+                                    view, phases, S(stream));
+}
+
 // ---- symmetric-memory communication ------------------------------------------------------------------------
 TB_API int tb_symm_alloc(long long bytes, uint64_t* out_ptr) {
   void* p = nullptr;

@@ -175,3 +175,78 @@ def test_flash_attn_long_sequence(S):
     _check(q.grad, qf.grad, "dq", 3e-2, 3e-2)
     _check(k.grad, kf.grad, "dk", 3e-2, 3e-2)
     _check(v.grad, vf.grad, "dv", 3e-2, 3e-2)
+
+
+# ---- blockwise (ring) kernels: every rank of a cp-way ring simulated on one GPU ---------------------------------------
+def _shard(x, r, cp, zigzag):
+    if zigzag:
+        c = x.chunk(2 * cp, dim=1)
+        return torch.cat([c[r], c[2 * cp - 1 - r]], 1).contiguous()
+    return x.chunk(cp, dim=1)[r].contiguous()
+
+
+def _unshard(parts, cp, zigzag):
+    if not zigzag:
+        return torch.cat(parts, 1)
+    chunks = [None] * (2 * cp)
+    for r, p in enumerate(parts):
+        a, b = p.chunk(2, dim=1)
+        chunks[r], chunks[2 * cp - 1 - r] = a, b
+    return torch.cat(chunks, 1)
+
+
+RING_CASES = [
+    # cp, S_total, Hq, Hk, D, causal, zigzag, varlen
+    (4, 2048, 4, 2, 128, True, True, False),
+    (4, 1536, 4, 2, 128, True, True, False),       # half-chunk of 192 rows: tiles straddle the in-place half views
+    (2, 512, 4, 4, 64, True, True, False),
+    (4, 1024, 4, 2, 128, True, False, False),      # contiguous layout: rank r visits r + 1 blocks
+    (4, 1024, 4, 2, 128, False, False, False),
+    (4, 1024, 4, 2, 128, False, False, True),      # non-causal with per-sequence key lengths (packed cu_seqlens path)
+]
+
+
+@pytest.mark.parametrize("cp,S,Hq,Hk,D,causal,zigzag,varlen", RING_CASES)
+def test_ring_blockwise_kernels_match_full_attention(cp, S, Hq, Hk, D, causal, zigzag, varlen):
+    """ring_forward_native / ring_backward_native (in-kernel merge, in-place half-block views, phased backward with
+    one shared dQ accumulator) for every rank of the ring vs one full-sequence fp32 attention."""
+    from torchacc_b200 import _native as nat
+    from torchacc_b200.ops import attention as A
+    from torchacc_b200.ops.context_parallel import ring as R
+    A.set_attention_backend("native")
+    B = 2
+    q, k, v, do = _rand(B, S, Hq, D, 1), _rand(B, S, Hk, D, 2), _rand(B, S, Hk, D, 3), _rand(B, S, Hq, D, 4)
+    scale = 1.0 / math.sqrt(D)
+    k_lens = torch.tensor([S, S * 5 // 8 + 37], device=DEV, dtype=torch.int32) if varlen else None
+    qf, kf, vf = (t.detach().float().requires_grad_() for t in (q, k, v))
+    if varlen:
+        mask = (torch.arange(S, device=DEV)[None] < k_lens[:, None])
+        g = Hq // Hk
+        s = torch.einsum("bqhd,bkhd->bhqk", qf, kf.repeat_interleave(g, 2)) * scale
+        s = s.masked_fill(~mask[:, None, None, :], float("-inf"))
+        ref = torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s, -1), vf.repeat_interleave(g, 2))
+    else:
+        ref, _ = A.attention_reference(qf, kf, vf, scale, causal, (-1, -1))
+    ref.backward(do.float())
+    assert R.native_blockwise_ok(q, k, v)
+    zig = zigzag and causal
+    blocks = [torch.stack([_shard(k, j, cp, zig), _shard(v, j, cp, zig)], 0) for j in range(cp)]
+    outs, dqs, dkv_sum = [], [], None
+    for r in range(cp):
+        steps = R._plan(r, cp, causal, zig)
+        q_r, do_r = _shard(q, r, cp, zig), _shard(do, r, cp, zig)
+        n0 = nat.LAUNCHES
+        out_r, lse_r = R.ring_forward_native(q_r, blocks, steps, scale, k_lens=k_lens)
+        assert nat.LAUNCHES - n0 == len(steps), "one kernel launch per ring step"
+        dq_r, dkv_r = R.ring_backward_native(do_r, q_r, out_r, lse_r, blocks, steps, scale, k_lens=k_lens)
+        outs.append(out_r)
+        dqs.append(dq_r)
+        dkv_sum = dkv_r.float() if dkv_sum is None else dkv_sum + dkv_r.float()
+    out = _unshard(outs, cp, zig)
+    dq = _unshard(dqs, cp, zig)
+    dk = _unshard([dkv_sum[j, 0] for j in range(cp)], cp, zig)
+    dv = _unshard([dkv_sum[j, 1] for j in range(cp)], cp, zig)
+    _check(out, ref, "out")
+    _check(dq, qf.grad, "dq")
+    _check(dk, kf.grad, "dk")
+    _check(dv, vf.grad, "dv")

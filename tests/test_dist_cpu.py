@@ -626,3 +626,36 @@ def _hf_cp_worker(rank, world, mode):
 def test_hf_model_context_parallel_through_accelerate(mode):
     pytest.importorskip("transformers")
     run_distributed(_hf_cp_worker, 2, args=(mode,))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _fp32_grad_worker(rank, world):
+    """dist.fsdp.grad_dtype='fp32': the flat gradient buffer (wgrad output, micro-batch accumulation, reduce-scatter
+    wire) is fp32 under bf16 compute.  Four identical micro-batches scaled by 1/4 (exact in bf16) reproduce the
+    single-batch gradient to fp32 rounding, and the result agrees with the default bf16 buffer to bf16 precision.
+    (The GPU tier checks the wgrad-epilogue accumulation itself: tests/test_model_gpu.py.)"""
+    import torchacc_b200 as ta
+    ids = _data(B=2, S=16, seed=3 + rank)
+
+    def grads(grad_dtype, micro):
+        model = _tiny()
+        cfg = ta.Config()
+        cfg.compute.bf16 = True
+        cfg.dist.fsdp.size = world
+        cfg.dist.fsdp.wrap_layer_cls = {"LlamaDecoderLayer"}
+        cfg.dist.fsdp.grad_dtype = grad_dtype
+        model = ta.accelerate(model, config=cfg)
+        eng = model.engine
+        assert eng.grad_wire_dtype == (torch.float32 if grad_dtype == "fp32" else torch.bfloat16)
+        for _ in range(micro):
+            (model(ids, labels=ids)["loss"] / micro).backward()
+        return torch.cat([g.float().reshape(-1) for g in eng.grads()])
+
+    one, four = grads("fp32", 1), grads("fp32", 4)
+    assert float((one - four).norm() / one.norm()) < 1e-5
+    one_lp = grads("compute", 1)
+    assert float((one - one_lp).norm() / one.norm()) < 2e-2
+
+
+def test_fsdp_fp32_gradient_buffer():
+    run_distributed(_fp32_grad_worker, 2)

@@ -205,6 +205,7 @@ class FSDPConfig(Section):
 
     ``reduce_dtype``: wire/accumulate dtype of the gradient reduce-scatter (reference eager path reduces in
     fp32, dist/fsdp.py:204-208; our peer-memory kernel reads bf16 partials and accumulates in fp32).
+    ``grad_dtype``: dtype of the flat gradient buffer / accumulation / wire (see the inline comment).
     ``fused_collectives``: use the symmetric-memory kernels (all-gather / reduce-scatter over NVLink peer
     memory, fused with cast and the optimizer hand-off) instead of NCCL calls.
     ``reshard_after_forward``: see the inline comment (torch FSDP's FULL_SHARD vs SHARD_GRAD_OP trade-off).
@@ -218,6 +219,11 @@ class FSDPConfig(Section):
         "use_spmd": (False, ) + _bool,
         "shard_output_callable": (None, lambda v: v is None or callable(v), "must be None or callable"),
         "reduce_dtype": ("fp32", lambda v: v in ("fp32", "bf16"), "must be 'fp32' or 'bf16'"),
+        # dtype of the FLAT gradient buffer: what the wgrad GEMM epilogues write, what micro-batches accumulate in and
+        # what travels on the reduce-scatter wire.  "compute" (default) = bf16/fp16 buffer, fp32 accumulation at the
+        # destination; "fp32" = fp32 end to end like the reference's fp32 reduce (dist/fsdp.py:204-208) at twice the
+        # gradient bytes (the wgrad GEMM accumulates into the fp32 buffer straight from tensor memory).
+        "grad_dtype": ("compute", lambda v: v in ("compute", "fp32"), "must be 'compute' or 'fp32'"),
         "fused_collectives": (True, ) + _bool,
         "prefetch": (1, lambda v: isinstance(v, int) and v >= 0, "must be an int >= 0"),
         # None = auto: keep the gathered bf16 parameters of every unit resident from the forward through the backward

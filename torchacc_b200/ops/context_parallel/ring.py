@@ -10,7 +10,15 @@ fp32.  Differences from the reference:
 * backward: per-block flash backward with the GLOBAL out/lse, dQ accumulated locally, the dK/dV contributions are
   returned to their owners with one reduce-scatter (fp32 accumulate) instead of a second ring;
 * the causal flag is only applied to the diagonal block (the reference's lazy path passes ``causal`` to every
-  block, Appendix B #5) and dq keeps the input dtype (the reference hard-codes bf16).
+  block, Appendix B #5) and dq keeps the input dtype (the reference hard-codes bf16);
+* on the GPU every ring step is ONE kernel launch: the flash forward kernel merges its block into the running
+  (fp32 out, lse) pair in its epilogue (``tb_flash_attn_block_fwd``; the reference runs ~8 elementwise kernels per
+  step for the merge, utils.py:302-343), half-blocks of the zigzag layout are addressed in place (``BlockView``: no
+  ``.contiguous()`` copies), the backward runs delta / dQ-zero once, one main kernel per step that reduce-adds dQ into
+  one fp32 accumulator and writes dK/dV straight into the owner's slot, and one cast at the end;
+* variable-length K (``k_lens``) runs on the same kernels through ``cu_seqlens`` (valid keys packed first); nothing
+  materialises an [S, S] score matrix.  With ``causal=True`` valid queries never see a padded key (keys at or before a
+  valid query are valid), so ``k_lens`` only matters for non-causal attention.
 """
 from __future__ import annotations
 
@@ -20,6 +28,7 @@ from typing import List, Optional, Tuple
 import torch
 import torch.distributed as dist
 
+from ... import _native as nat
 from .. import attention as A
 from .comm import _all_gather_dim, _coll, _rank, _world
 
@@ -97,6 +106,140 @@ def merge_out_lse(out, lse, blk_out, blk_lse):
     return out * w_old + blk_out.float() * w_new, new_lse
 
 
+# ---- native blockwise kernels (csrc/attn: BlockView addressing, in-kernel merge, phased backward) --------------
+nat.register_signatures({
+    "tb_flash_attn_block_fwd": ([nat.u64] * 7 + [nat.i32] * 6 + [nat.i64] * 4 + [nat.f32, nat.i32, nat.i32, nat.i32,
+                                nat.i64, nat.i64, nat.u64, nat.i32, nat.i32, nat.i32, nat.i32, nat.i32, nat.u64,
+                                nat.i32], nat.i32),
+    "tb_flash_attn_block_bwd": ([nat.u64] * 13 + [nat.i32] * 6 + [nat.i64] * 4 + [nat.f32, nat.i32, nat.i32, nat.i32,
+                                nat.i64, nat.i64, nat.i64, nat.i64, nat.i64, nat.i32, nat.u64, nat.i32, nat.i32,
+                                nat.i32, nat.i32, nat.i32, nat.i32], nat.i32),
+})
+
+
+def native_blockwise_ok(q, k, v) -> bool:
+    L = nat.lib()
+    return (L is not None and hasattr(L, "tb_flash_attn_block_fwd") and A.native_supported(q, k, v, 0.0, None)
+            and A.get_attention_backend() in ("auto", "native") and q.shape[-1] in (64, 128))
+
+
+def _blk_fwd(q3, k3, v3, o3, lse, acc, first, B, Sq, Sk, scale, causal, window=(-1, -1), view=(0, 0, 0, 0),
+             cu_k=None):
+    """One ring step: attention of the addressed q rows against the addressed keys, merged into (acc, lse, o3)."""
+    Tq, Hq, D = q3.shape
+    Tk, Hk = k3.shape[0], k3.shape[1]
+    L = nat.require()
+    nat.check(
+        L.tb_flash_attn_block_fwd(q3.data_ptr(), k3.data_ptr(), v3.data_ptr(), o3.data_ptr(), lse.data_ptr(), 0,
+                                  nat.ptr(cu_k), B, Sq, Sk, Hq, Hk, D, q3.stride(0), k3.stride(0), v3.stride(0),
+                                  o3.stride(0), scale, int(causal), window[0], window[1], Tq, Tk, nat.stream(),
+                                  int(q3.dtype == torch.bfloat16), view[0], view[1], view[2], view[3], acc.data_ptr(),
+                                  int(first)), "tb_flash_attn_block_fwd")
+    nat.count_launch()
+
+
+def _blk_bwd(do3, q3, k3, v3, o3, lse, dq3, dk3, dv3, dq_acc, delta, B, Sq, Sk, scale, causal, window, view, phases,
+             cu_k=None):
+    Tq, Hq, D = q3.shape
+    Tk, Hk = k3.shape[0], k3.shape[1]
+    L = nat.require()
+    nat.check(
+        L.tb_flash_attn_block_bwd(q3.data_ptr(), k3.data_ptr(), v3.data_ptr(), o3.data_ptr(), do3.data_ptr(),
+                                  lse.data_ptr(), dq3.data_ptr(), dk3.data_ptr(), dv3.data_ptr(), dq_acc.data_ptr(),
+                                  delta.data_ptr(), 0, nat.ptr(cu_k), B, Sq, Sk, Hq, Hk, D, q3.stride(0), k3.stride(0),
+                                  v3.stride(0), do3.stride(0), scale, int(causal), window[0], window[1], Tq, Tk,
+                                  dq3.stride(0), dk3.stride(0), dv3.stride(0), nat.num_sms(), nat.stream(),
+                                  int(q3.dtype == torch.bfloat16), view[0], view[1], view[2], view[3], phases),
+        "tb_flash_attn_block_bwd")
+    nat.count_launch()
+
+
+def _pack_valid_keys(kv, lens, S):
+    """kv: [2, B*S, Hk, D]; lens: [B] valid keys per sequence (a prefix).  Returns (packed kv with the valid tokens
+    first, int32 cu_seqlens [B+1], the permutation) -- no host sync."""
+    B = lens.shape[0]
+    invalid = (torch.arange(S, device=kv.device)[None] >= lens[:, None]).reshape(-1)
+    order = torch.argsort(invalid, stable=True)
+    cu = torch.zeros(B + 1, dtype=torch.int32, device=kv.device)
+    cu[1:] = torch.cumsum(lens, 0)
+    return kv[:, order].contiguous(), cu, order
+
+
+def ring_forward_native(q, blocks, steps, scale, window=(-1, -1), k_lens=None):
+    """q: [B, S, Hq, D]; blocks[j]: [2, B, S, Hk, D] (K and V of owner j); steps: output of ``_plan``.
+    Returns (out [B, S, Hq, D] in q.dtype, lse [Hq, B*S] fp32).  One kernel per step."""
+    B, S, Hq, D = q.shape
+    T, half = B * S, S // 2
+    q3 = q.view(T, Hq, D)
+    out = torch.empty_like(q)
+    o3 = out.view(T, Hq, D)
+    acc = torch.empty((T, Hq, D), dtype=torch.float32, device=q.device)
+    lse = torch.empty((Hq, T), dtype=torch.float32, device=q.device)
+    for i, (j, mode) in enumerate(steps):
+        kv = blocks[j].reshape(2, T, -1, D)
+        k3, v3 = kv[0], kv[1]
+        if mode == "diag":
+            _blk_fwd(q3, k3, v3, o3, lse, acc, i == 0, B, S, S, scale, True, window)
+        elif mode == "full":
+            if k_lens is not None:
+                lens = (k_lens.to(q.device) - j * S).clamp(0, S)
+                pk, cu, _ = _pack_valid_keys(kv, lens, S)
+                _blk_fwd(q3, pk[0], pk[1], o3, lse, acc, i == 0, B, S, S, scale, False, cu_k=cu)
+            else:
+                _blk_fwd(q3, k3, v3, o3, lse, acc, i == 0, B, S, S, scale, False)
+        elif mode == "kv_first_half":
+            _blk_fwd(q3, k3, v3, o3, lse, acc, i == 0, B, S, half, scale, False, view=(0, 0, S, 0))
+        else:  # q_second_half
+            _blk_fwd(q3, k3, v3, o3, lse, acc, i == 0, B, half, S, scale, False, view=(S, half, 0, 0))
+    return out, lse
+
+
+def ring_backward_native(do, q, out, lse, blocks, steps, scale, window=(-1, -1), k_lens=None):
+    """Returns (dq [B, S, Hq, D] in q.dtype, dkv [cp, 2, B, S, Hk, D] in q.dtype: this rank's contribution to every
+    owner's dK/dV, zero where nothing was visited)."""
+    B, S, Hq, D = q.shape
+    T, half = B * S, S // 2
+    cp = len(blocks)
+    Hk = blocks[0].shape[3]
+    q3, o3 = q.view(T, Hq, D), out.view(T, Hq, D)
+    do3 = do.contiguous().view(T, Hq, D)
+    dq = torch.empty_like(q)
+    dq3 = dq.view(T, Hq, D)
+    dq_acc = torch.empty((T, Hq, D), dtype=torch.float32, device=q.device)
+    delta = torch.empty((Hq, T), dtype=torch.float32, device=q.device)
+    dkv = torch.zeros((cp, 2, T, Hk, D), dtype=q.dtype, device=q.device)
+    kv0 = blocks[0].reshape(2, T, Hk, D)
+    none = (0, 0, 0, 0)
+    _blk_bwd(do3, q3, kv0[0], kv0[1], o3, lse, dq3, dkv[0, 0], dkv[0, 1], dq_acc, delta, B, S, S, scale, False,
+             (-1, -1), none, 1)                                         # delta = rowsum(dO o O), dq_acc = 0
+    for j, mode in steps:
+        kv = blocks[j].reshape(2, T, Hk, D)
+        k3, v3 = kv[0], kv[1]
+        if mode == "diag":
+            _blk_bwd(do3, q3, k3, v3, o3, lse, dq3, dkv[j, 0], dkv[j, 1], dq_acc, delta, B, S, S, scale, True, window,
+                     none, 2)
+        elif mode == "full":
+            if k_lens is not None:
+                lens = (k_lens.to(q.device) - j * S).clamp(0, S)
+                pk, cu, order = _pack_valid_keys(kv, lens, S)
+                dpk = torch.zeros_like(pk)
+                _blk_bwd(do3, q3, pk[0], pk[1], o3, lse, dq3, dpk[0], dpk[1], dq_acc, delta, B, S, S, scale, False,
+                         (-1, -1), none, 2, cu_k=cu)
+                dkv[j].index_copy_(1, order, dpk)
+            else:
+                _blk_bwd(do3, q3, k3, v3, o3, lse, dq3, dkv[j, 0], dkv[j, 1], dq_acc, delta, B, S, S, scale, False,
+                         (-1, -1), none, 2)
+        elif mode == "kv_first_half":
+            _blk_bwd(do3, q3, k3, v3, o3, lse, dq3, dkv[j, 0], dkv[j, 1], dq_acc, delta, B, S, half, scale, False,
+                     (-1, -1), (0, 0, S, 0), 2)
+        else:
+            _blk_bwd(do3, q3, k3, v3, o3, lse, dq3, dkv[j, 0], dkv[j, 1], dq_acc, delta, B, half, S, scale, False,
+                     (-1, -1), (S, half, 0, 0), 2)
+    _blk_bwd(do3, q3, kv0[0], kv0[1], o3, lse, dq3, dkv[0, 0], dkv[0, 1], dq_acc, delta, B, S, S, scale, False,
+             (-1, -1), none, 4)                                         # dq = cast(dq_acc)
+    return dq, dkv.view(cp, 2, B, S, Hk, D)
+
+
 # ---- schedule -------------------------------------------------------------------------------------------------
 def _plan(rank: int, cp: int, causal: bool, zigzag: bool) -> List[Tuple[int, str]]:
     """Which K/V owner is visited and how: 'diag' (causal on the local block), 'full', 'kv_first_half',
@@ -136,9 +279,18 @@ class _RingAttnFn(torch.autograd.Function):
                 blocks = [allkv[j] for j in range(cp)]
         else:
             blocks = [torch.stack([k, v], 0)]
+        steps = _plan(rank, cp, causal, zig)
+        ctx.native = native_blockwise_ok(q, k, v)
+        if ctx.native:
+            # valid queries of a causal mask never see padded keys: k_lens only matters for non-causal attention
+            lens = None if causal else k_lens
+            out_lp, lse_t = ring_forward_native(q, blocks, steps, scale, window, lens)
+            ctx.save_for_backward(q, out_lp, lse_t, *blocks)
+            ctx.cfg = (scale, causal, window, group, zig, cp, rank, lens)
+            return out_lp
         out, lse = None, None
         half = S // 2
-        for j, mode in _plan(rank, cp, causal, zig):
+        for j, mode in steps:
             kj, vj = blocks[j][0], blocks[j][1]
             lens_j = None
             if k_lens is not None:
@@ -170,6 +322,14 @@ class _RingAttnFn(torch.autograd.Function):
         B, S, Hq, D = q.shape
         half = S // 2
         do = do.contiguous()
+        if ctx.native:
+            dq, dkv = ring_backward_native(do, q, out, lse, blocks, _plan(rank, cp, causal, zig), scale, window, k_lens)
+            if cp > 1:
+                mine = torch.empty(dkv.shape[1:], dtype=dkv.dtype, device=dkv.device)
+                _coll(group, q.device).reduce_scatter(dkv.reshape(-1), mine.reshape(-1))   # fp32 accumulation inside
+            else:
+                mine = dkv[0]
+            return dq, mine[0], mine[1], None, None, None, None, None, None, None
         dq = torch.zeros(q.shape, dtype=torch.float32, device=q.device)
         Hk = blocks[0].shape[3]
         dkv = torch.zeros((cp, 2, B, S, Hk, D), dtype=torch.float32, device=q.device)

@@ -97,8 +97,8 @@ class GlooCollectives(Collectives):
         ins = list(inp.reshape(self.world, -1).unbind(0))
         outs = [torch.empty_like(c) for c in ins]
         if inp.dtype == torch.bfloat16:
-            ins = [c.view(torch.int16).contiguous() for c in ins]
-            outs = [c.view(torch.int16) for c in outs]
+            ins = [c.view(torch.float16).contiguous() for c in ins]
+            outs = [c.view(torch.float16) for c in outs]
         work = []
         # gloo has no all_to_all: pairwise exchange
         for r in range(self.world):
@@ -115,10 +115,10 @@ class GlooCollectives(Collectives):
         out.reshape(-1).view(flat.dtype).copy_(flat)
 
     def all_gather(self, shard, full):
-        if full.dtype == torch.bfloat16:  # gloo has no bf16 kernels on every build: move as int16 bit patterns
-            parts = [torch.empty_like(shard.view(torch.int16)) for _ in range(self.world)]
-            dist.all_gather(parts, shard.view(torch.int16).contiguous(), group=self.group)
-            full.view(torch.int16).copy_(torch.cat(parts))
+        if full.dtype == torch.bfloat16:  # gloo has no bf16 kernels on every build: move as fp16 bit patterns (pure copies)
+            # gathered straight into views of the destination (no torch.cat: it trips CPU autocast with fp16 inputs)
+            parts = list(full.view(torch.float16).reshape(-1).chunk(self.world))
+            dist.all_gather(parts, shard.view(torch.float16).contiguous().reshape(-1), group=self.group)
         else:
             parts = [torch.empty_like(shard) for _ in range(self.world)]
             dist.all_gather(parts, shard.contiguous(), group=self.group)

@@ -320,7 +320,7 @@ class FlatParamUnit:
         keep = self.grad_accumulated and eng.accumulate_in_flat
         for info in self.infos:
             t = info.tensor
-            if info.is_gemm_weight and eng.grad_wire_dtype == torch.bfloat16 and t.requires_grad:
+            if info.is_gemm_weight and t.requires_grad and eng.compute_dtype == torch.bfloat16:
                 t._tb_grad_view = self.grad_full[info.offset:info.offset + info.numel].view(info.shape)
                 t._tb_grad_ready = keep
             else:
@@ -552,7 +552,7 @@ class ShardingEngine:
     def __init__(self, device: torch.device, shard_group=None, replica_group=None, compute_dtype=torch.bfloat16,
                  strategy: str = "FULL_SHARD", sync_module_states: bool = False, reduce_dtype: str = "fp32",
                  prefetch: int = 1, prefer_symm: bool = True, grad_mode: str = "compat",
-                 reshard_after_forward: Optional[bool] = None, model_numel: int = 0):
+                 reshard_after_forward: Optional[bool] = None, model_numel: int = 0, grad_dtype: str = "compute"):
         self.device = device
         self.compute_dtype = compute_dtype
         self.strategy = strategy
@@ -594,6 +594,10 @@ class ShardingEngine:
         self.replica_coll: Collectives = make_collectives(replica_group, device, prefer_symm)
         # bf16 on the wire, fp32 accumulation at the destination (our kernels); plain fp32 training keeps fp32
         self.grad_wire_dtype = torch.float32 if compute_dtype == torch.float32 else compute_dtype
+        # grad_dtype == "fp32": fp32 flat buffer = fp32 wgrad output, fp32 micro-batch accumulation, fp32 wire
+        self.grad_flat_fp32 = grad_dtype == "fp32" and compute_dtype != torch.float32
+        if self.grad_flat_fp32:
+            self.grad_wire_dtype = torch.float32
         self.grad_shard_dtype = torch.float32 if reduce_dtype == "fp32" else self.grad_wire_dtype
         self.units: List[FlatParamUnit] = []
         self.lp_pool = _BufferPool(device, depth=2 + prefetch)
@@ -610,7 +614,7 @@ class ShardingEngine:
         self._params_published_for = -1
         import os as _os1
         self.reduce_delay = max(0, int(_os1.environ.get("TORCHACC_B200_REDUCE_DELAY", "2")))
-        if cuda and self.reshard and self.replica_world == 1:
+        if cuda and self.reshard and self.replica_world == 1 and not self.grad_flat_fp32:   # carried reduce: bf16 slices
             from .carry import make_carry
             self.carry = make_carry(self.shard_coll, device)
         self.grad_pool = _BufferPool(device, depth=2 + (self.reduce_delay if self.carry is not None else 0),

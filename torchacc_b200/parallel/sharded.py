@@ -68,7 +68,8 @@ class _EngineModule(ParallelModule):
                                      reduce_dtype=c.dist.fsdp.reduce_dtype, prefetch=c.dist.fsdp.prefetch,
                                      prefer_symm=c.dist.fsdp.fused_collectives,
                                      reshard_after_forward=getattr(c.dist.fsdp, "reshard_after_forward", None),
-                                     model_numel=sum(p.numel() for p in model.parameters()))
+                                     model_numel=sum(p.numel() for p in model.parameters()),
+                                     grad_dtype=getattr(c.dist.fsdp, "grad_dtype", "compute"))
         root = shard_model(model, self.engine, wrap, gc_cls, c.memory.gc_cnt)
         last_stage = self.mesh.get_pp_num() == 1 or self.mesh.is_last_stage()
         self.model = _AutocastModel(root, compute_dtype if compute_dtype != torch.float32 else None, self.device.type,
