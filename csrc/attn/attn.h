@@ -12,6 +12,10 @@ namespace tb {
 // half of every query sequence or one half of a K/V block in place.
 struct BlockView {
   int q_bs = 0, q_off = 0, k_bs = 0, k_off = 0;
+  // attention dropout (csrc/attn/dropout.cuh): probability and the 64-bit seed that keys the counter-based mask; the
+  // backward must be called with the same values
+  float p_drop = 0.f;
+  unsigned long long seed = 0;
 };
 
 // Blockwise forward: with `acc` (fp32 [Tq, Hq, D]) the epilogue merges the block into the running (acc, lse) pair and

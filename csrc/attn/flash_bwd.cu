@@ -23,6 +23,7 @@
 #include "../common/ptx.cuh"
 #include "../common/tensormap.h"
 #include "attn.h"
+#include "dropout.cuh"
 
 namespace tb {
 
@@ -46,6 +47,7 @@ struct BwdArgs {
   float scale_log2, scale;
   int causal, wl, wr;
   int q_bs, q_off, k_bs, k_off;   // fixed-length addressing (attn.h BlockView)
+  DropoutParams drop;             // used by the kDrop instantiations only
   long long* trace;   // optional [64 iterations][16 slots] clock64 stamps of CTA (0,0,0) (debug / profiling)
 };
 
@@ -73,7 +75,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int D, bool kBf16>
+template <int D, bool kBf16, bool kDrop>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
@@ -240,6 +242,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t lane_off = (q4 * 32u) << 16;
     const float sl2 = args.scale_log2, sc = args.scale;
     const bool key_ok = key < k_len;
+    const uint32_t drop_key = kDrop ? drop_key_part(args.drop.seed_hi, (uint32_t)key) : 0u;
     // group 0 prefetches the row statistics of the next query tile
     float lse_next = 0.f, delta_next = 0.f;
     auto fetch_stats = [&](int it) {
@@ -273,6 +276,8 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
       // ---- phase 1: P^T = exp2(S^T * scale - LSE) for this group's 64 query columns (needs only S^T) ----
       uint32_t sv[2][32];
+      uint32_t keep_bits[2] = {0xffffffffu, 0xffffffffu};
+      const uint32_t drop_head = kDrop ? drop_head_part(args.drop.seed_lo, (uint32_t)(b * args.Hq + h)) : 0u;
       tmem_ld_32x32b_x32(tmem_base + lane_off + R0 + (2 * grp) * 32, sv[0]);
       tmem_ld_32x32b_x32(tmem_base + lane_off + R0 + (2 * grp + 1) * 32, sv[1]);
       tmem_ld_wait();
@@ -313,8 +318,26 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           }
         }
         uint32_t pk[16];
+        if constexpr (kDrop) {
+          // dV += (P o mask / (1-p))^T dO: the dropped P^T goes to the tensor core, sv keeps the undropped P^T for dS
+          uint32_t bits = 0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = pack_h2<kBf16>(__uint_as_float(sv[cc][2 * i]), __uint_as_float(sv[cc][2 * i + 1]));
+          for (int i = 0; i < 32; ++i) {
+            const uint32_t rowp = drop_row_part(drop_head, (uint32_t)(m0 + c * 32 + i));
+            bits |= (drop_keep(rowp, drop_key, args.drop.thresh24) ? 1u : 0u) << i;
+          }
+          keep_bits[cc] = bits;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float a0 = ((bits >> (2 * i)) & 1u) ? __uint_as_float(sv[cc][2 * i]) * args.drop.rp : 0.f;
+            const float a1 = ((bits >> (2 * i + 1)) & 1u) ? __uint_as_float(sv[cc][2 * i + 1]) * args.drop.rp : 0.f;
+            pk[i] = pack_h2<kBf16>(a0, a1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            pk[i] = pack_h2<kBf16>(__uint_as_float(sv[cc][2 * i]), __uint_as_float(sv[cc][2 * i + 1]));
+        }
         tmem_st_32x32b_x16(tmem_base + lane_off + R0 + c * 16, pk);   // P^T chunk -> TMEM R0 columns [16c, 16c+16)
       }
       if (warp_idx == 4 && lane == 0) TB_TRACE(10);   // phase 1 done (P^T stores issued)
@@ -338,6 +361,11 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         tmem_ld_32x32b_x32(tmem_base + lane_off + R1 + c * 32, dpv);
         tmem_ld_wait();
         const float4* dl4 = reinterpret_cast<const float4*>(stat + kTile + c * 32);
+        if constexpr (kDrop) {   // d(dropped P) -> dP: the same mask and 1/(1-p)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            dpv[i] = ((keep_bits[cc] >> i) & 1u) ? __float_as_uint(__uint_as_float(dpv[i]) * args.drop.rp) : 0u;
+        }
         uint32_t dsk[16];
 #pragma unroll
         for (int g4 = 0; g4 < 8; ++g4) {
@@ -501,12 +529,12 @@ static CUtensorMap make_map_thd_b(const void* base, long long tokens, int heads,
                          strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int D, bool kBf16>
+template <int D, bool kBf16, bool kDrop>
 static cudaError_t launch_bwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
                               const CUtensorMap& mdo, const CUtensorMap& mdq, const BwdArgs& a, int num_k_tiles,
                               cudaStream_t stream) {
   using S = BwdSmem<D>;
-  auto kern = flash_bwd_kernel<D, kBf16>;
+  auto kern = flash_bwd_kernel<D, kBf16, kDrop>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
@@ -589,12 +617,22 @@ cudaError_t flash_attn_bwd_ex(const void* q, const void* k, const void* v, const
   a.k_bs = view.k_bs > 0 ? view.k_bs : Sk; a.k_off = view.k_off;
   const int max_k = cu_k ? (int)Tk : Sk;
   const int num_k_tiles = (max_k + kTile - 1) / kTile;
-  if (is_bf16)
-    e = (D == 128) ? launch_bwd<128, true>(mq, mk, mv, mdo, mdq, a, num_k_tiles, stream)
-                   : launch_bwd<64, true>(mq, mk, mv, mdo, mdq, a, num_k_tiles, stream);
-  else
-    e = (D == 128) ? launch_bwd<128, false>(mq, mk, mv, mdo, mdq, a, num_k_tiles, stream)
-                   : launch_bwd<64, false>(mq, mk, mv, mdo, mdq, a, num_k_tiles, stream);
+  const bool drop = view.p_drop > 0.f;
+  if (drop) {
+    if (view.p_drop >= 1.f) return cudaErrorInvalidValue;
+    a.drop.thresh24 = (uint32_t)((double)view.p_drop * 16777216.0 + 0.5);   // mirrored in dropout_keep_mask
+    a.drop.rp = 1.f / (1.f - view.p_drop);
+    a.drop.seed_lo = (uint32_t)(view.seed & 0xffffffffull);
+    a.drop.seed_hi = (uint32_t)(view.seed >> 32);
+  } else {
+    a.drop = DropoutParams{0u, 1.f, 0u, 0u};
+  }
+#define TB_BWD(DD, BF)                                                                            \
+  (drop ? launch_bwd<DD, BF, true>(mq, mk, mv, mdo, mdq, a, num_k_tiles, stream)                  \
+        : launch_bwd<DD, BF, false>(mq, mk, mv, mdo, mdq, a, num_k_tiles, stream))
+  if (is_bf16) e = (D == 128) ? TB_BWD(128, true) : TB_BWD(64, true);
+  else e = (D == 128) ? TB_BWD(128, false) : TB_BWD(64, false);
+#undef TB_BWD
   if (e != cudaSuccess) return e;
   }
   // 3) dq = bf16(dq_acc)

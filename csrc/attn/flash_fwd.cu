@@ -21,6 +21,7 @@
 #include "../common/ptx.cuh"
 #include "../common/tensormap.h"
 #include "attn.h"
+#include "dropout.cuh"
 
 namespace tb {
 
@@ -51,6 +52,7 @@ struct FwdArgs {
   // acc [Tq, Hq, D] / lse in place (log-sum-exp merge) and writes the merged output to o; acc_init: first block
   float* acc;
   int acc_init;
+  DropoutParams drop;   // used by the kDrop instantiations only
   long long* trace;   // optional [64 tiles][16 slots] clock64 stamps of the first CTA (debug / profiling)
 };
 
@@ -84,7 +86,7 @@ __device__ __forceinline__ void key_bounds(int row, int q_len, int k_len, int ca
   lo = (wl < 0) ? 0 : max(0, pos - wl);
 }
 
-template <int D, bool kBf16>
+template <int D, bool kBf16, bool kDrop>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const FwdArgs args) {
@@ -278,6 +280,9 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // the per-tile bar.sync exchanges order this load before that store
     float lse_prev = -INFINITY;
     if (merging && !args.acc_init && row < q_len) lse_prev = args.lse[(long long)h * args.Tq + q_start + row];
+    // dropout: P is masked and rescaled on its way to the PV MMA; the softmax statistics use the undropped P
+    const uint32_t drop_row = kDrop ? drop_row_part(drop_head_part(args.drop.seed_lo, (uint32_t)(b * args.Hq + h)),
+                                                    (uint32_t)row) : 0u;
 
     for (int t = 0; t < n_tiles; ++t) {
       const int n0 = (j_lo + t) * kBN + grp * 64;   // first key column owned by this thread
@@ -345,9 +350,15 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[c][2 * i]), sl2, -mref));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[c][2 * i + 1]), sl2, -mref));
+          float p0 = fast_exp2(fmaf(__uint_as_float(sv[c][2 * i]), sl2, -mref));
+          float p1 = fast_exp2(fmaf(__uint_as_float(sv[c][2 * i + 1]), sl2, -mref));
           psum += p0 + p1;
+          if constexpr (kDrop) {
+            const uint32_t k0 = (uint32_t)(n0 + c * 32 + 2 * i);
+            p0 = drop_keep(drop_row, drop_key_part(args.drop.seed_hi, k0), args.drop.thresh24) ? p0 * args.drop.rp : 0.f;
+            p1 = drop_keep(drop_row, drop_key_part(args.drop.seed_hi, k0 + 1), args.drop.thresh24) ? p1 * args.drop.rp
+                                                                                                 : 0.f;
+          }
           pk[c][i] = pack_h2<kBf16>(p0, p1);
         }
       l_part = l_part * alpha + psum;
@@ -494,11 +505,11 @@ static CUtensorMap make_map_thd(const void* base, long long tokens, int heads, i
                          strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int D, bool kBf16>
+template <int D, bool kBf16, bool kDrop>
 static cudaError_t launch_fwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const FwdArgs& a,
                               int max_q_len, cudaStream_t stream) {
   using S = FwdSmem<D>;
-  auto kern = flash_fwd_kernel<D, kBf16>;
+  auto kern = flash_fwd_kernel<D, kBf16, kDrop>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
@@ -557,12 +568,22 @@ cudaError_t flash_attn_fwd_ex(const void* q, const void* k, const void* v, void*
   a.acc = acc; a.acc_init = acc_init;
   const int mq_len = cu_q ? (max_q_len > 0 ? max_q_len : (int)Tq) : Sq;
   a.num_q_tiles = (mq_len + kBM - 1) / kBM;
-  if (is_bf16) {
-    if (D == 128) return launch_fwd<128, true>(mq, mk, mv, a, mq_len, stream);
-    return launch_fwd<64, true>(mq, mk, mv, a, mq_len, stream);
+  const bool drop = view.p_drop > 0.f;
+  if (drop) {
+    if (view.p_drop >= 1.f) return cudaErrorInvalidValue;
+    a.drop.thresh24 = (uint32_t)((double)view.p_drop * 16777216.0 + 0.5);   // mirrored in dropout_keep_mask
+    a.drop.rp = 1.f / (1.f - view.p_drop);
+    a.drop.seed_lo = (uint32_t)(view.seed & 0xffffffffull);
+    a.drop.seed_hi = (uint32_t)(view.seed >> 32);
+  } else {
+    a.drop = DropoutParams{0u, 1.f, 0u, 0u};
   }
-  if (D == 128) return launch_fwd<128, false>(mq, mk, mv, a, mq_len, stream);
-  return launch_fwd<64, false>(mq, mk, mv, a, mq_len, stream);
+#define TB_FWD(DD, BF)                                                                  \
+  (drop ? launch_fwd<DD, BF, true>(mq, mk, mv, a, mq_len, stream)                       \
+        : launch_fwd<DD, BF, false>(mq, mk, mv, a, mq_len, stream))
+  if (is_bf16) return (D == 128) ? TB_FWD(128, true) : TB_FWD(64, true);
+  return (D == 128) ? TB_FWD(128, false) : TB_FWD(64, false);
+#undef TB_FWD
 }
 
 }  // namespace tb

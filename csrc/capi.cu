@@ -122,6 +122,36 @@ TB_API int tb_flash_attn_bwd(uint64_t q, uint64_t k, uint64_t v, uint64_t o, uin
                                  P<float>(alibi), alibi_bs, S(stream));
 }
 
+// Attention with dropout: the base signatures + (p_drop, seed); the mask is a pure function of (seed, head, q, k)
+// (csrc/attn/dropout.cuh), so the backward regenerates it from the same two values.
+TB_API int tb_flash_attn_fwd_dropout(uint64_t q, uint64_t k, uint64_t v, uint64_t o, uint64_t lse, uint64_t cu_q,
+                                     uint64_t cu_k, int B, int Sq, int Sk, int Hq, int Hk, int D, long long q_ts,
+                                     long long k_ts, long long v_ts, long long o_ts, float scale, int causal, int wl,
+                                     int wr, long long Tq, long long Tk, int max_q_len, uint64_t stream, int is_bf16,
+                                     uint64_t alibi, int alibi_bs, float p_drop, uint64_t seed) {
+  tb::BlockView view;
+  view.p_drop = p_drop; view.seed = seed;
+  return (int)tb::flash_attn_fwd_ex(P<void>(q), P<void>(k), P<void>(v), P<void>(o), P<float>(lse), P<int>(cu_q),
+                                    P<int>(cu_k), B, Sq, Sk, Hq, Hk, D, q_ts, k_ts, v_ts, o_ts, scale, causal != 0, wl,
+                                    wr, Tq, Tk, max_q_len, is_bf16 != 0, P<float>(alibi), alibi_bs, view, nullptr, 0,
+                                    S(stream));
+}
+TB_API int tb_flash_attn_bwd_dropout(uint64_t q, uint64_t k, uint64_t v, uint64_t o, uint64_t dout, uint64_t lse,
+                                     uint64_t dq, uint64_t dk, uint64_t dv, uint64_t dq_acc, uint64_t delta,
+                                     uint64_t cu_q, uint64_t cu_k, int B, int Sq, int Sk, int Hq, int Hk, int D,
+                                     long long q_ts, long long k_ts, long long v_ts, long long do_ts, float scale,
+                                     int causal, int wl, int wr, long long Tq, long long Tk, long long dq_ts,
+                                     long long dk_ts, long long dv_ts, int num_sms, uint64_t stream, int is_bf16,
+                                     uint64_t alibi, int alibi_bs, float p_drop, uint64_t seed) {
+  tb::BlockView view;
+  view.p_drop = p_drop; view.seed = seed;
+  return (int)tb::flash_attn_bwd_ex(P<void>(q), P<void>(k), P<void>(v), P<void>(o), P<void>(dout), P<float>(lse),
+                                    P<void>(dq), P<void>(dk), P<void>(dv), P<float>(dq_acc), P<float>(delta),
+                                    P<int>(cu_q), P<int>(cu_k), B, Sq, Sk, Hq, Hk, D, q_ts, k_ts, v_ts, do_ts, scale,
+                                    causal != 0, wl, wr, Tq, Tk, dq_ts, dk_ts, dv_ts, num_sms, is_bf16 != 0,
+                                    P<float>(alibi), alibi_bs, view, 7, S(stream));
+}
+
 // Blockwise (ring) variants: BlockView addressing + in-kernel (out, lse) merge / phased backward (csrc/attn/attn.h).
 TB_API int tb_flash_attn_block_fwd(uint64_t q, uint64_t k, uint64_t v, uint64_t o, uint64_t lse, uint64_t cu_q,
                                    uint64_t cu_k, int B, int Sq, int Sk, int Hq, int Hk, int D, long long q_ts,

@@ -250,3 +250,47 @@ def test_ring_blockwise_kernels_match_full_attention(cp, S, Hq, Hk, D, causal, z
     _check(dq, qf.grad, "dq")
     _check(dk, kf.grad, "dk")
     _check(dv, vf.grad, "dv")
+
+
+# ---- dropout: counter-based mask regenerated by the backward -----------------------------------------------------------
+DROPOUT_CASES = [
+    # B, Sq, Sk, Hq, Hk, D, causal, p
+    (2, 256, 256, 4, 2, 128, True, 0.17),
+    (1, 200, 328, 4, 4, 64, False, 0.1),          # ragged tiles, Sq != Sk
+    (2, 384, 384, 8, 2, 128, True, 0.5),
+]
+
+
+@pytest.mark.parametrize("B,Sq,Sk,Hq,Hk,D,causal,p", DROPOUT_CASES)
+def test_flash_attn_dropout_matches_reference_with_the_same_mask(B, Sq, Sk, Hq, Hk, D, causal, p):
+    """Native attention dropout (reference flash_attn.py:313-355 keeps a Philox state; ours is a counter-based hash of
+    (seed, head, q, k), csrc/attn/dropout.cuh): forward and backward agree with the fp32 reference that applies the
+    SAME keep mask (rebuilt in PyTorch by dropout_keep_mask), and the mask drops about p of the entries."""
+    from torchacc_b200 import _native as nat
+    from torchacc_b200.ops import attention as A
+    A.set_attention_backend("native")
+    q, k, v, do = _rand(B, Sq, Hq, D, 1), _rand(B, Sk, Hk, D, 2), _rand(B, Sk, Hk, D, 3), _rand(B, Sq, Hq, D, 4)
+    q.requires_grad_(); k.requires_grad_(); v.requires_grad_()
+    torch.manual_seed(1234)
+    n0 = nat.LAUNCHES
+    out, lse, keep = A.flash_attn_func(q, k, v, dropout_p=p, causal=causal, return_attn_probs=True)
+    assert nat.LAUNCHES > n0, "native attention kernel was not launched"
+    assert keep.shape == (B, Hq, Sq, Sk) and keep.dtype == torch.bool
+    frac = float((~keep).float().mean())
+    assert abs(frac - p) < 0.01, frac
+    out.backward(do)
+    qf, kf, vf = (t.detach().float().requires_grad_() for t in (q, k, v))
+    ref, lse_ref = A.attention_reference(qf, kf, vf, None, causal, (-1, -1), None, p, keep_mask=keep)
+    ref.backward(do.float())
+    _check(out, ref, "out")
+    fin = torch.isfinite(lse_ref)
+    _check(lse[fin], lse_ref[fin], "lse", 1e-2, 1e-2)          # the statistics are those of the undropped softmax
+    _check(v.grad, vf.grad, "dv")
+    _check(k.grad, kf.grad, "dk")
+    _check(q.grad, qf.grad, "dq")
+    # same seed -> same result; a different seed -> a different mask
+    torch.manual_seed(1234)
+    again = A.flash_attn_func(q.detach(), k.detach(), v.detach(), dropout_p=p, causal=causal)
+    assert torch.equal(again, out.detach())
+    other = A.flash_attn_func(q.detach(), k.detach(), v.detach(), dropout_p=p, causal=causal)
+    assert not torch.equal(other, out.detach())

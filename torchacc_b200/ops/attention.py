@@ -51,6 +51,12 @@ nat.register_signatures({
                           [nat.i64, nat.i64, nat.i32, nat.i32, nat.u64, nat.i32, nat.u64, nat.i32], nat.i32),
     "tb_flash_attn_bwd": ([nat.u64] * 13 + [nat.i32] * 6 + [nat.i64] * 4 + [nat.f32] + [nat.i32] * 3 +
                           [nat.i64] * 5 + [nat.i32, nat.u64, nat.i32, nat.u64, nat.i32], nat.i32),
+    "tb_flash_attn_fwd_dropout": ([nat.u64] * 7 + [nat.i32] * 6 + [nat.i64] * 4 + [nat.f32] + [nat.i32] * 3 +
+                                  [nat.i64, nat.i64, nat.i32, nat.u64, nat.i32, nat.u64, nat.i32, nat.f32, nat.u64],
+                                  nat.i32),
+    "tb_flash_attn_bwd_dropout": ([nat.u64] * 13 + [nat.i32] * 6 + [nat.i64] * 4 + [nat.f32] + [nat.i32] * 3 +
+                                  [nat.i64] * 5 + [nat.i32, nat.u64, nat.i32, nat.u64, nat.i32, nat.f32, nat.u64],
+                                  nat.i32),
 })
 
 
@@ -60,9 +66,10 @@ def native_supported(q, k, v, dropout_p, alibi_slopes, pad_ok: bool = False) -> 
         return False
     D = q.shape[-1]
     # head dims other than 64 / 128 are zero-padded up to the next supported size by the callers (_pad_head_dim);
-    # ALiBi and fp16 are native; dropout is not
+    # ALiBi, fp16 and dropout (counter-based mask, csrc/attn/dropout.cuh) are native
     d_ok = D in (64, 128) or (pad_ok and D <= 128 and D % 8 == 0)
-    return (q.is_cuda and q.dtype in (torch.bfloat16, torch.float16) and d_ok and dropout_p == 0.0
+    drop_ok = dropout_p == 0.0 or (0.0 < dropout_p < 1.0 and hasattr(L, "tb_flash_attn_fwd_dropout"))
+    return (q.is_cuda and q.dtype in (torch.bfloat16, torch.float16) and d_ok and drop_ok
             and q.stride(-1) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1)
 
 
@@ -87,7 +94,7 @@ def _mask_for(sq, sk, causal, window, device):
 
 
 def attention_reference(q, k, v, softmax_scale=None, causal=False, window_size=(-1, -1), alibi_slopes=None,
-                        dropout_p=0.0):
+                        dropout_p=0.0, keep_mask=None):
     """q: [B, Sq, Hq, D], k/v: [B, Sk, Hk, D] -> (out [B,Sq,Hq,D] in q.dtype, lse [B,Hq,Sq] fp32)."""
     B, Sq, Hq, D = q.shape
     Sk, Hk = k.shape[1], k.shape[2]
@@ -108,7 +115,9 @@ def attention_reference(q, k, v, softmax_scale=None, causal=False, window_size=(
     lse = torch.logsumexp(s, dim=-1)
     p = torch.exp(s - lse.unsqueeze(-1))
     p = torch.nan_to_num(p, nan=0.0)  # fully-masked rows -> zeros (FA2 semantics)
-    if dropout_p > 0:
+    if keep_mask is not None:       # explicit mask [B, Hq, Sq, Sk] (the kernels' counter-based mask: dropout_keep_mask)
+        p = p * keep_mask.to(p.dtype) / (1.0 - dropout_p)
+    elif dropout_p > 0:
         p = F.dropout(p, dropout_p)
     o = torch.matmul(p, vf).permute(0, 2, 1, 3)
     return o.to(q.dtype), lse
@@ -125,14 +134,56 @@ def _alibi_args(alibi, Hq):
     return alibi.data_ptr(), (Hq if alibi.dim() == 2 else 0)
 
 
-def _native_fwd(q3, k3, v3, cu_q, cu_k, B, Sq, Sk, scale, causal, window, alibi=None):
-    """q3: [Tq, Hq, D] strided view (token stride arbitrary, head stride D); returns (o [Tq,Hq,D], lse [Hq,Tq])."""
+def new_dropout_seed() -> int:
+    """64-bit seed for one attention call, drawn from torch's CPU generator (``torch.manual_seed`` makes it
+    reproducible, activation checkpointing restores the generator state so the recomputed forward draws the same
+    value) -- no device sync."""
+    return int(torch.empty((), dtype=torch.int64).random_().item()) & 0x7FFFFFFFFFFFFFFF
+
+
+def _mix32(x):
+    x = x & 0xFFFFFFFF
+    x = x ^ (x >> 16)
+    x = (x * 0x7FEB352D) & 0xFFFFFFFF
+    x = x ^ (x >> 15)
+    x = (x * 0x846CA68B) & 0xFFFFFFFF
+    return x ^ (x >> 16)
+
+
+def dropout_keep_mask(seed: int, p_drop: float, B: int, Hq: int, Sq: int, Sk: int, device="cpu") -> torch.Tensor:
+    """Bit-exact PyTorch mirror of csrc/attn/dropout.cuh: bool [B, Hq, Sq, Sk], True = kept.  Test oracle (and the
+    S_dmask a caller may ask for); the kernels never materialise it."""
+    M = 0xFFFFFFFF
+    lo, hi = seed & M, (seed >> 32) & M
+    bh = torch.arange(B * Hq, dtype=torch.int64, device=device).view(B, Hq, 1, 1)
+    qi = torch.arange(Sq, dtype=torch.int64, device=device).view(1, 1, Sq, 1)
+    ki = torch.arange(Sk, dtype=torch.int64, device=device).view(1, 1, 1, Sk)
+    head = lo ^ ((bh * 0x9E3779B1) & M)
+    row = ((head ^ ((qi * 0x85EBCA77) & M)) * 0xC2B2AE3D) & M
+    key = (hi + ki * 0x27D4EB2F) & M
+    x = _mix32(row ^ key)
+    p32 = torch.tensor(p_drop, dtype=torch.float32).item()          # the kernels receive p as a C float
+    return (x >> 8) >= int(p32 * 16777216.0 + 0.5)
+
+
+def _native_fwd(q3, k3, v3, cu_q, cu_k, B, Sq, Sk, scale, causal, window, alibi=None, dropout=None):
+    """q3: [Tq, Hq, D] strided view (token stride arbitrary, head stride D); returns (o [Tq,Hq,D], lse [Hq,Tq]).
+    ``dropout`` = (p, seed) or None."""
     Tq, Hq, D = q3.shape
     ap, abs_ = _alibi_args(alibi, Hq)
     Tk, Hk = k3.shape[0], k3.shape[1]
     o = torch.empty((Tq, Hq, D), dtype=q3.dtype, device=q3.device)
     lse = torch.empty((Hq, Tq), dtype=torch.float32, device=q3.device)
     L = nat.require()
+    if dropout is not None:
+        nat.check(
+            L.tb_flash_attn_fwd_dropout(q3.data_ptr(), k3.data_ptr(), v3.data_ptr(), o.data_ptr(), lse.data_ptr(),
+                                        nat.ptr(cu_q), nat.ptr(cu_k), B, Sq, Sk, Hq, Hk, D, q3.stride(0), k3.stride(0),
+                                        v3.stride(0), o.stride(0), scale, int(causal), window[0], window[1], Tq, Tk, 0,
+                                        nat.stream(), int(q3.dtype == torch.bfloat16), ap, abs_, float(dropout[0]),
+                                        int(dropout[1])), "tb_flash_attn_fwd_dropout")
+        nat.count_launch()
+        return o, lse
     nat.check(
         L.tb_flash_attn_fwd(q3.data_ptr(), k3.data_ptr(), v3.data_ptr(), o.data_ptr(), lse.data_ptr(), nat.ptr(cu_q),
                             nat.ptr(cu_k), B, Sq, Sk, Hq, Hk, D, q3.stride(0), k3.stride(0), v3.stride(0), o.stride(0),
@@ -144,13 +195,24 @@ def _native_fwd(q3, k3, v3, cu_q, cu_k, B, Sq, Sk, scale, causal, window, alibi=
 
 
 def _native_bwd(do3, q3, k3, v3, o3, lse, cu_q, cu_k, B, Sq, Sk, scale, causal, window, dq3, dk3, dv3,
-                deterministic=False, alibi=None):
+                deterministic=False, alibi=None, dropout=None):
     Tq, Hq, D = q3.shape
     ap, abs_ = _alibi_args(alibi, Hq)
     Tk, Hk = k3.shape[0], k3.shape[1]
     dq_acc = torch.empty((Tq, Hq, D), dtype=torch.float32, device=q3.device)
     delta = torch.empty((Hq, Tq), dtype=torch.float32, device=q3.device)
     L = nat.require()
+    if dropout is not None:
+        nat.check(
+            L.tb_flash_attn_bwd_dropout(q3.data_ptr(), k3.data_ptr(), v3.data_ptr(), o3.data_ptr(), do3.data_ptr(),
+                                        lse.data_ptr(), dq3.data_ptr(), dk3.data_ptr(), dv3.data_ptr(),
+                                        dq_acc.data_ptr(), delta.data_ptr(), nat.ptr(cu_q), nat.ptr(cu_k), B, Sq, Sk,
+                                        Hq, Hk, D, q3.stride(0), k3.stride(0), v3.stride(0), do3.stride(0), scale,
+                                        int(causal), window[0], window[1], Tq, Tk, dq3.stride(0), dk3.stride(0),
+                                        dv3.stride(0), nat.num_sms(), nat.stream(), int(q3.dtype == torch.bfloat16),
+                                        ap, abs_, float(dropout[0]), int(dropout[1])), "tb_flash_attn_bwd_dropout")
+        nat.count_launch(3)
+        return
     nat.check(
         L.tb_flash_attn_bwd(q3.data_ptr(), k3.data_ptr(), v3.data_ptr(), o3.data_ptr(), do3.data_ptr(),
                             lse.data_ptr(), dq3.data_ptr(), dk3.data_ptr(), dv3.data_ptr(), dq_acc.data_ptr(),
@@ -166,10 +228,12 @@ class _FlashAttnFn(torch.autograd.Function):
     """Token-flattened attention.  q: [Tq,Hq,D], k/v: [Tk,Hk,D] (strided views allowed)."""
 
     @staticmethod
-    def forward(ctx, q3, k3, v3, cu_q, cu_k, B, Sq, Sk, scale, causal, window, deterministic, alibi=None):
-        o, lse = _native_fwd(q3, k3, v3, cu_q, cu_k, B, Sq, Sk, scale, causal, window, alibi)
+    def forward(ctx, q3, k3, v3, cu_q, cu_k, B, Sq, Sk, scale, causal, window, deterministic, alibi=None,
+                dropout=None):
+        o, lse = _native_fwd(q3, k3, v3, cu_q, cu_k, B, Sq, Sk, scale, causal, window, alibi, dropout)
         ctx.save_for_backward(q3, k3, v3, o, lse, cu_q, cu_k)
         ctx.alibi = alibi
+        ctx.dropout = dropout                     # (p, seed): the backward regenerates the mask from it
         ctx.cfg = (B, Sq, Sk, scale, causal, window, deterministic)
         ctx.mark_non_differentiable(lse)
         return o, lse
@@ -182,8 +246,9 @@ class _FlashAttnFn(torch.autograd.Function):
         dq = torch.empty(q3.shape, dtype=q3.dtype, device=q3.device)
         dk = torch.empty(k3.shape, dtype=k3.dtype, device=k3.device)
         dv = torch.empty(v3.shape, dtype=v3.dtype, device=v3.device)
-        _native_bwd(do, q3, k3, v3, o, lse, cu_q, cu_k, B, Sq, Sk, scale, causal, window, dq, dk, dv, det, ctx.alibi)
-        return dq, dk, dv, None, None, None, None, None, None, None, None, None, None
+        _native_bwd(do, q3, k3, v3, o, lse, cu_q, cu_k, B, Sq, Sk, scale, causal, window, dq, dk, dv, det, ctx.alibi,
+                    ctx.dropout)
+        return dq, dk, dv, None, None, None, None, None, None, None, None, None, None, None
 
 
 class _FlashAttnQKVPackedFn(torch.autograd.Function):
@@ -289,10 +354,14 @@ def flash_attn_func(q, k, v, dropout_p=0.0, softmax_scale=None, causal=False, wi
         k3 = kp.reshape(B * Sk, Hk, Dp) if kp.is_contiguous() else kp.contiguous().view(B * Sk, Hk, Dp)
         v3 = vp.reshape(B * Sk, Hk, Dp) if vp.is_contiguous() else vp.contiguous().view(B * Sk, Hk, Dp)
         alibi = alibi_slopes.float().contiguous() if alibi_slopes is not None else None
-        o, lse = _FlashAttnFn.apply(q3, k3, v3, None, None, B, Sq, Sk, scale, causal, window, deterministic, alibi)
+        dropout = (float(dropout_p), new_dropout_seed()) if dropout_p > 0.0 else None
+        o, lse = _FlashAttnFn.apply(q3, k3, v3, None, None, B, Sq, Sk, scale, causal, window, deterministic, alibi,
+                                    dropout)
         out = o.view(B, Sq, Hq, Dp)[..., :D0]
         if return_attn_probs:
-            return out, lse.view(Hq, B, Sq).transpose(0, 1).contiguous(), None
+            # like flash-attn, the third value is only meaningful for testing: the keep mask [B, Hq, Sq, Sk]
+            dmask = dropout_keep_mask(dropout[1], dropout[0], B, Hq, Sq, Sk, q.device) if dropout else None
+            return out, lse.view(Hq, B, Sq).transpose(0, 1).contiguous(), dmask
         return out
     if backend == "sdpa":
         out, lse = _sdpa(q, k, v, scale, causal, window, alibi_slopes, dropout_p)
@@ -328,15 +397,20 @@ def flash_attn_qkvpacked_tokens(qkv, num_q_heads, num_kv_heads, head_dim, batch,
     return out.reshape(T, hq * d)
 
 
-def flash_attn_varlen_cu(q3, k3, v3, cu_q, cu_k, scale, causal, window, return_lse=False):
+def flash_attn_varlen_cu(q3, k3, v3, cu_q, cu_k, scale, causal, window, return_lse=False, dropout_p=0.0,
+                         alibi_slopes=None):
     """Packed sequences: q3 [Tq,Hq,D], k3/v3 [Tk,Hk,D], cu_* int32 [B+1]."""
-    backend = _pick_backend(q3, k3, v3, 0.0, None, pad_ok=True)
+    backend = _pick_backend(q3, k3, v3, dropout_p, alibi_slopes, pad_ok=True)
     Bn = cu_q.numel() - 1
     if backend == "native":
         (qp, kp, vp), D0 = _pad_head_dim(q3, k3, v3)
-        o, lse = _FlashAttnFn.apply(qp, kp, vp, cu_q.int(), cu_k.int(), Bn, 0, 0, scale, causal, window, False)
+        alibi = alibi_slopes.float().contiguous() if alibi_slopes is not None else None
+        dropout = (float(dropout_p), new_dropout_seed()) if dropout_p > 0.0 else None
+        o, lse = _FlashAttnFn.apply(qp, kp, vp, cu_q.int(), cu_k.int(), Bn, 0, 0, scale, causal, window, False, alibi,
+                                    dropout)
         o = o[..., :D0]
         return (o, lse) if return_lse else o
+    assert dropout_p == 0.0 and alibi_slopes is None, "the per-sequence fallback handles plain attention only"
     outs, lses = [], []
     cq, ck = cu_q.tolist(), cu_k.tolist()
     for b in range(Bn):
@@ -371,11 +445,13 @@ def flash_attn_varlen_func(q, k, v, attention_mask, dropout_p=0.0, softmax_scale
     q3 = q.reshape(B * Sq, Hq, D).index_select(0, idx)
     k3 = k.reshape(B * Sk, Hk, D).index_select(0, idx)
     v3 = v.reshape(B * Sk, Hk, D).index_select(0, idx)
-    if dropout_p > 0 or alibi_slopes is not None:
+    if (dropout_p > 0 or alibi_slopes is not None) and _pick_backend(q3, k3, v3, dropout_p, alibi_slopes,
+                                                                      pad_ok=True) != "native":
         _warn_once("varlen-extra", "varlen attention with dropout/ALiBi runs on the reference path")
         o4, lse4 = attention_reference_masked(q, k, v, mask, scale, causal, window_size, alibi_slopes, dropout_p)
         return (o4, lse4, None) if return_attn_probs else o4
-    res = flash_attn_varlen_cu(q3, k3, v3, cu, cu, scale, causal, tuple(window_size), return_lse=return_attn_probs)
+    res = flash_attn_varlen_cu(q3, k3, v3, cu, cu, scale, causal, tuple(window_size), return_lse=return_attn_probs,
+                               dropout_p=dropout_p, alibi_slopes=alibi_slopes)
     o3 = res[0] if return_attn_probs else res
     out = torch.zeros((B * Sq, Hq, D), dtype=q.dtype, device=q.device).index_copy(0, idx, o3).view(B, Sq, Hq, D)
     if return_attn_probs:
