@@ -16,17 +16,24 @@ T=""   # torchrun prefix with a fresh rendezvous port (set by `nextport`; must r
 nextport() { PORT=$((PORT+1)); T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $PORT"; }
 
 if [ "$N" -eq 1 ]; then
-  run gpu_tests      600 python -m pytest tests -q -m gpu
+  run gpu_tests      700 python -m pytest tests -q -m gpu
   run smoke          200 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')"
-  run gemm_ab        200 build/gemm_test 2 1 1
   run bench_n1       300 python bench.py --steps 5 --warmup 3
+  # ncu --set full on the round-2 kernels (one launch each after a warm-up launch): summaries go to profiles/
+  run ncu_r2         400 ncu --set full --clock-control none --import-source on \
+      -k "regex:gemm_mxfp8_kernel|gemm_bf16_kernel|flash_fwd_kernel" --launch-skip 7 --launch-count 4 \
+      -f -o "$OUT/ncu_r2" python tools/ncu_targets.py
 else
   nextport; run multigpu_tests 400 $T -m pytest tests/test_multigpu.py -m multigpu -q
-  nextport; run pp_tour        120 $T examples/parallelism_tour.py --mode pp
-  nextport; run fused_tp       200 $T benchmarks/fused_tp_bench.py
-  nextport; run overlap        200 $T benchmarks/overlap_bench.py
-  nextport; run bench          300 $T bench.py --gpus "$N" --steps 5 --warmup 3 --trace "$OUT/trace_n$N.json"
-  nextport; TORCHACC_B200_SPLIT_HEAD=1 run bench_split_head 300 $T bench.py --gpus "$N" --steps 5 --warmup 3 --no-e2e
-  gzip -f "$OUT"/trace_*.json 2>/dev/null
+  nextport; run bench          300 $T bench.py --gpus "$N" --steps 5 --warmup 3
+  # compute-sanitizer on the peer-memory kernels (rank-local tools: synccheck = barrier misuse, racecheck = smem hazards)
+  nextport; run synccheck      150 $T --no-python compute-sanitizer --tool synccheck --log-file "$OUT/synccheck.%p.txt" \
+      python -m pytest tests/test_multigpu.py -m multigpu -q -k "symm_collectives or carried or fused_tp"
+  if [ "${VALIDATE_EXTRA:-0}" = "1" ]; then
+    nextport; run pp_tour        120 $T examples/parallelism_tour.py --mode pp
+    nextport; run fused_tp       200 $T benchmarks/fused_tp_bench.py
+    nextport; run bench_trace    300 $T bench.py --gpus "$N" --steps 5 --warmup 3 --trace "$OUT/trace_n$N.json"
+    gzip -f "$OUT"/trace_*.json 2>/dev/null
+  fi
 fi
 echo "logs: $OUT/"
