@@ -34,6 +34,7 @@ def main():
     p.add_argument("--hq", type=int, default=32)
     p.add_argument("--hk", type=int, default=8)
     p.add_argument("--d", type=int, default=128)
+    p.add_argument("--only", default="", help="native: skip the library paths")
     a = p.parse_args()
     from torchacc_b200.ops import attention as A
     B, S, Hq, Hk, D = a.batch, a.seq, a.hq, a.hk, a.d
@@ -59,6 +60,9 @@ def main():
 
     A.set_attention_backend("native")
     bench("tb_native", lambda: A.flash_attn_func(q, k, v, causal=True))
+    if a.only == "native":
+        print(json.dumps({"shape": [B, S, Hq, Hk, D], "results": res}))
+        return
     A.set_attention_backend("sdpa")
     bench("torch_sdpa", lambda: A.flash_attn_func(q, k, v, causal=True))
     try:

@@ -15,7 +15,7 @@ import torch
 
 _LIB: Optional[ctypes.CDLL] = None
 _TRIED = False
-_SO = Path(__file__).resolve().parent / "_C.so"
+_SO = Path(os.environ.get("TORCHACC_B200_NATIVE_LIB") or (Path(__file__).resolve().parent / "_C.so"))   # env: A/B builds
 
 u64, i32, i64, f32 = ctypes.c_uint64, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
 
