@@ -20,14 +20,14 @@ if [ "$N" -eq 1 ]; then
   run smoke          200 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')"
   run bench_n1       300 python bench.py --steps 5 --warmup 3
   # ncu --set full on the round-2 kernels (one launch each after a warm-up launch): summaries go to profiles/
-  run ncu_r2         400 ncu --set full --clock-control none --import-source on \
+  [ "${VALIDATE_NCU:-0}" = "1" ] && run ncu_r2         400 ncu --set full --clock-control none --import-source on \
       -k "regex:gemm_mxfp8_kernel|gemm_bf16_kernel|flash_fwd_kernel" --launch-skip 7 --launch-count 4 \
       -f -o "$OUT/ncu_r2" python tools/ncu_targets.py
 else
   nextport; run multigpu_tests 400 $T -m pytest tests/test_multigpu.py -m multigpu -q
   nextport; run bench          300 $T bench.py --gpus "$N" --steps 5 --warmup 3
   # compute-sanitizer on the peer-memory kernels (rank-local tools: synccheck = barrier misuse, racecheck = smem hazards)
-  nextport; run synccheck      150 $T --no-python compute-sanitizer --tool synccheck --log-file "$OUT/synccheck.%p.txt" \
+  [ "${VALIDATE_SANITIZER:-0}" = "1" ] && nextport && run synccheck      150 $T --no-python compute-sanitizer --tool synccheck --log-file "$OUT/synccheck.%p.txt" \
       python -m pytest tests/test_multigpu.py -m multigpu -q -k "symm_collectives or carried or fused_tp"
   if [ "${VALIDATE_EXTRA:-0}" = "1" ]; then
     nextport; run pp_tour        120 $T examples/parallelism_tour.py --mode pp
