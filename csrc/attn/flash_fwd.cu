@@ -56,7 +56,6 @@ struct FwdArgs {
   float* acc;
   int acc_init;
   DropoutParams drop;   // used by the kDrop instantiations only
-  int v2_flags;         // forward v2 experiments: bit 0 = polynomial exp2 for 1/4 of the entries, bit 1 = release P in two halves
   long long* trace;   // optional [64 tiles][16 slots] clock64 stamps of the first CTA (debug / profiling)
 };
 
@@ -908,15 +907,6 @@ static cudaError_t launch_fwd2(const CUtensorMap& mq, const CUtensorMap& mk, con
 
 // 1 = always the one-tile kernel, 2 = the two-tile kernel whenever it applies (default), read once from
 // TORCHACC_B200_ATTN_FWD
-static int fwd2_flags() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TORCHACC_B200_ATTN_FLAGS");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
-
 static int fwd_version() {
   static int v = -1;
   if (v < 0) {
@@ -971,7 +961,6 @@ cudaError_t flash_attn_fwd_ex(const void* q, const void* k, const void* v, void*
   a.q_bs = view.q_bs > 0 ? view.q_bs : Sq; a.q_off = view.q_off;
   a.k_bs = view.k_bs > 0 ? view.k_bs : Sk; a.k_off = view.k_off;
   a.acc = acc; a.acc_init = acc_init;
-  a.v2_flags = fwd2_flags();
   const int mq_len = cu_q ? (max_q_len > 0 ? max_q_len : (int)Tq) : Sq;
   a.num_q_tiles = (mq_len + kBM - 1) / kBM;
   const bool drop = view.p_drop > 0.f;
