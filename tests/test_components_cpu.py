@@ -1,6 +1,7 @@
 """CPU unit tests: AsyncLoader bucketing, PP schedules, checkpoint surgery, reference-path ops, amp, offload API."""
 import math
 import os
+import sys
 
 import pytest
 import torch
@@ -492,3 +493,23 @@ def test_trace_failure_is_loud():
 
     with pytest.raises(Exception):
         trace(Bad(), ["x"])
+
+
+def test_graft_entry_build_compiles_library_and_harnesses():
+    """``__graft_entry__.build()`` is the driver's build check: the in-tree library AND the stand-alone nvcc harnesses have
+    to compile and link on a GPU-less host (the harness silently stopped linking once when the GEMM gained a dependency)."""
+    import shutil
+    if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    harness = os.path.join(root, "build", "gemm_test")
+    if os.path.exists(harness):
+        os.remove(harness)                      # force the link step
+    sys.path.insert(0, root)
+    try:
+        import __graft_entry__ as g
+        g.build()
+    finally:
+        sys.path.remove(root)
+    assert os.path.exists(harness)
+    assert os.path.exists(os.path.join(root, "torchacc_b200", "_C.so"))
