@@ -105,8 +105,7 @@ def main():
         # weights of this stage vs the single-GPU model, and both halves run directly on the captured input
         ref_l1 = ref_model.model.layers[1]
         ref_l1 = getattr(ref_l1, "module", ref_l1)
-        for (n1, p1), (n2, p2) in zip(inner.layers[0].named_parameters(recurse=True) if False else
-                                       [(i.fqn, i.tensor) for i in model.engine.units[-1].infos],
+        for (n1, p1), (n2, p2) in zip([(i.fqn, i.tensor) for i in model.engine.units[-1].infos],
                                        [(i.fqn, i.tensor) for u in eng.units for i in u.infos
                                         if (u.prefix + "." + i.fqn).startswith("model.layers.1") or u.prefix == ""
                                         and ("norm" in i.fqn or "lm_head" in i.fqn)]):

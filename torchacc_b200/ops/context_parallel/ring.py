@@ -37,10 +37,8 @@ from .comm import _all_gather_dim, _coll, _rank, _world
 def _block_fwd(q, k, v, scale, causal, window, k_lens=None):
     """(out [B,Sq,H,D] in q.dtype, lse [B,H,Sq] fp32)."""
     if k_lens is not None:
-        B, Sq = q.shape[0], q.shape[1]
         mask_k = (torch.arange(k.shape[1], device=q.device)[None] < k_lens[:, None])
-        o, l = A.attention_reference(q, k, v, scale, causal, window) if False else _masked_block(q, k, v, scale, mask_k)
-        return o, l
+        return _masked_block(q, k, v, scale, mask_k)
     out, lse, _ = A.flash_attn_func(q, k, v, softmax_scale=scale, causal=causal, window_size=window,
                                     return_attn_probs=True)
     return out, lse

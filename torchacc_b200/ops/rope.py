@@ -129,8 +129,7 @@ class _RopeQKVFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, hq, hk, d, cos, sin, positions, seq_len):
         T = qkv.shape[0]
-        q = qkv[:, :hq * d].view(T, hq, d) if False else qkv.as_strided((T, hq, d), (qkv.stride(0), d, 1),
-                                                                       qkv.storage_offset())
+        q = qkv.as_strided((T, hq, d), (qkv.stride(0), d, 1), qkv.storage_offset())
         k = qkv.as_strided((T, hk, d), (qkv.stride(0), d, 1), qkv.storage_offset() + hq * d)
         _apply_inplace(q, cos, sin, positions, seq_len, False)
         _apply_inplace(k, cos, sin, positions, seq_len, False)
