@@ -88,6 +88,20 @@ class SymmBuffer:
     def contains(self, t: torch.Tensor) -> bool:
         return self.ptr <= t.data_ptr() and t.data_ptr() + t.numel() * t.element_size() <= self.ptr + self.nbytes
 
+    def close(self) -> None:
+        """Unmap the peers' allocations and free ours.  Only through ``SymmDomain.close`` (a collective): a peer must not
+        still be reading this buffer, and no tensor view of it may be used afterwards."""
+        if self.ptr == 0:
+            return
+        L = nat.require()
+        for q in self._opened:
+            L.tb_symm_close_handle(q)
+        self._opened = []
+        self.bytes = None
+        self._holder = None
+        L.tb_symm_free(self.ptr)
+        self.ptr = 0
+
 
 class SymmDomain:
     _domains: Dict[int, "SymmDomain"] = {}
@@ -111,6 +125,26 @@ class SymmDomain:
         if key not in cls._domains:
             cls._domains[key] = SymmDomain(group, device)
         return cls._domains[key]
+
+    def close(self) -> None:
+        """Collective teardown of the domain: device work drained on every rank, then every mapping is closed and every
+        allocation freed.  Engines / collectives built on the domain must not be used afterwards.  Not called
+        automatically (the reference's NCCL communicators are not destroyed at exit either); long-lived services that
+        rebuild their process groups call it before dropping a group."""
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group, device_ids=[self.device.index])
+        for b in self.buffers + [self.pad]:
+            b.close()
+        self.buffers = []
+        for key, d in list(SymmDomain._domains.items()):
+            if d is self:
+                del SymmDomain._domains[key]
+
+    @classmethod
+    def close_all(cls) -> None:
+        for d in list(cls._domains.values()):
+            d.close()
 
     def alloc(self, numel: int, dtype: torch.dtype) -> torch.Tensor:
         """Collective: every rank must call with the same size, in the same order."""
