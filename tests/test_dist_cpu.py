@@ -583,9 +583,10 @@ def test_pipeline_parallel_x_fsdp_matches_single_process():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def _hf_cp_worker(rank, world, mode):
-    """accelerate(HF LlamaForCausalLM) with dist.sp.size = 2: sequence sharding + context-parallel attention through
-    HF's attention-interface registry reproduce the single-process loss and gradients."""
+def _hf_cp_worker(rank, world, mode, fsdp=1):
+    """accelerate(HF LlamaForCausalLM) with dist.sp.size > 1: sequence sharding + context-parallel attention through
+    HF's attention-interface registry reproduce the single-process loss and gradients (optionally composed with FSDP:
+    sp ranks are replicas of each parameter shard)."""
     import torchacc_b200 as ta
     from transformers import LlamaConfig, LlamaForCausalLM
     hc = LlamaConfig(vocab_size=160, hidden_size=64, intermediate_size=128, num_hidden_layers=2,
@@ -602,15 +603,30 @@ def _hf_cp_worker(rank, world, mode):
     torch.manual_seed(0)
     model = LlamaForCausalLM(hc)
     cfg = ta.Config()
-    cfg.dist.sp.size = 2
+    cfg.dist.sp.size = world // fsdp
     cfg.dist.sp.mode = mode
+    if mode == "2d":
+        cfg.dist.sp.ulysses_size = 2
+    if fsdp > 1:
+        cfg.dist.fsdp.size = fsdp
+        cfg.dist.fsdp.wrap_layer_cls = {"LlamaDecoderLayer"}
     model = ta.accelerate(model, config=cfg)
     out = model(input_ids=ids, labels=labels)
     assert abs(float(out.loss) - float(ref.loss)) < 1e-4, (float(out.loss), float(ref.loss))
     out.loss.backward()
     eng = model.engine
     meta = model._inner_engine_module().get_shard_metadata()
-    flat = torch.cat([g.float().reshape(-1) for g in eng.grads()])
+    # gradient shards of this rank -> full flat gradient (all-gather over the fsdp group when sharded)
+    shards = [g.float().reshape(-1) for g in eng.grads()]
+    if fsdp > 1:
+        import torch.distributed as dist
+        full = []
+        for sh in shards:
+            parts = [torch.empty_like(sh) for _ in range(fsdp)]
+            dist.all_gather(parts, sh.contiguous(), group=eng.shard_group)
+            full.append(torch.cat(parts))
+        shards = full
+    flat = torch.cat(shards)
     off = 0
     for u in meta["units"]:
         for p in u["params"]:
@@ -626,6 +642,18 @@ def _hf_cp_worker(rank, world, mode):
 def test_hf_model_context_parallel_through_accelerate(mode):
     pytest.importorskip("transformers")
     run_distributed(_hf_cp_worker, 2, args=(mode,))
+
+
+def test_hf_model_context_parallel_2d():
+    """4 ranks: Ulysses inside pairs x ring across the pairs (reference context_parallel_2d.py) on an HF model."""
+    pytest.importorskip("transformers")
+    run_distributed(_hf_cp_worker, 4, args=("2d",))
+
+
+def test_hf_model_context_parallel_with_fsdp():
+    """sp2 x fsdp2 on 4 ranks: the sp ranks replicate every parameter shard; gradients equal the single-process ones."""
+    pytest.importorskip("transformers")
+    run_distributed(_hf_cp_worker, 4, args=("ulysses", 2))
 
 
 # ---------------------------------------------------------------------------------------------------------------
