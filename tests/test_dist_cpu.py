@@ -687,3 +687,10 @@ def _fp32_grad_worker(rank, world):
 
 def test_fsdp_fp32_gradient_buffer():
     run_distributed(_fp32_grad_worker, 2)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_ring_attention_p2p_overlapped_ring_on_4_ranks(causal):
+    """impl='p2p' with the next transfer in flight (_LazyRing): 4 ranks, causal without zig-zag so that the plan SKIPS blocks
+    which the ring still has to forward to the ranks behind."""
+    run_distributed(_cp_worker, 4, args=("ring_p2p", causal))

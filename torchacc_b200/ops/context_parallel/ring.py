@@ -5,8 +5,8 @@ fp32.  Differences from the reference:
 * **causal load balancing**: with ``zigzag=True`` rank r holds sequence chunks ``r`` and ``2cp-1-r``; every step then
   costs half a block on every rank (the reference skips blocks, so rank r does r+1 of them -- SURVEY 5.7);
 * K/V movement: on one NVSwitch domain all K/V blocks are fetched with ONE peer-memory all-gather (GQA K/V are
-  small) and the loop runs without per-step communication; ``impl="p2p"`` keeps the classic isend/irecv ring that
-  overlaps each transfer with the previous block's attention;
+  small) and the loop runs without per-step communication; ``impl="p2p"`` keeps the classic isend/irecv ring with
+  the next transfer always in flight while the current block is attended to (``_LazyRing``);
 * backward: per-block flash backward with the GLOBAL out/lse, dQ accumulated locally, the dK/dV contributions are
   returned to their owners with one reduce-scatter (fp32 accumulate) instead of a second ring;
 * the causal flag is only applied to the diagonal block (the reference's lazy path passes ``causal`` to every
@@ -271,7 +271,7 @@ class _RingAttnFn(torch.autograd.Function):
         if cp > 1:
             kv = torch.stack([k, v], 0).contiguous()                       # [2, B, S, Hk, D]
             if impl == "p2p":
-                blocks = _ring_exchange(kv, group)
+                blocks = _LazyRing(kv, group)
             else:
                 allkv = _all_gather_dim(kv.unsqueeze(0), 0, group)         # [cp, 2, B, S, Hk, D]
                 blocks = [allkv[j] for j in range(cp)]
@@ -283,6 +283,8 @@ class _RingAttnFn(torch.autograd.Function):
             # valid queries of a causal mask never see padded keys: k_lens only matters for non-causal attention
             lens = None if causal else k_lens
             out_lp, lse_t = ring_forward_native(q, blocks, steps, scale, window, lens)
+            if isinstance(blocks, _LazyRing):
+                blocks = blocks.all()
             ctx.save_for_backward(q, out_lp, lse_t, *blocks)
             ctx.cfg = (scale, causal, window, group, zig, cp, rank, lens)
             return out_lp
@@ -309,7 +311,9 @@ class _RingAttnFn(torch.autograd.Function):
                 out = torch.cat([out[:, :half], o2], 1)
                 lse = torch.cat([lse[:, :, :half], l2], 2)
         out_lp = out.to(q.dtype)
-        ctx.save_for_backward(q, out_lp, lse, *[b for b in blocks])
+        if isinstance(blocks, _LazyRing):
+            blocks = blocks.all()
+        ctx.save_for_backward(q, out_lp, lse, *blocks)
         ctx.cfg = (scale, causal, window, group, zig, cp, rank, k_lens)
         return out_lp
 
@@ -378,24 +382,52 @@ def _masked_diag(q, k, v, scale, lens):
     return torch.matmul(p, vf).permute(0, 2, 1, 3).to(q.dtype), lse
 
 
-def _ring_exchange(kv: torch.Tensor, group) -> List[torch.Tensor]:
-    """Classic ring: cp-1 rounds of isend/irecv; returns the blocks indexed by owner rank."""
-    cp, rank = _world(group), _rank(group)
-    blocks: List[Optional[torch.Tensor]] = [None] * cp
-    blocks[rank] = kv
-    send_to = dist.get_global_rank(group, (rank + 1) % cp)
-    recv_from = dist.get_global_rank(group, (rank - 1) % cp)
-    cur = kv
-    for s in range(1, cp):
-        nxt = torch.empty_like(cur)
-        ops = [dist.P2POp(dist.isend, cur, send_to, group), dist.P2POp(dist.irecv, nxt, recv_from, group)]
-        if rank % 2:
+class _LazyRing:
+    """Classic ring exchange with the NEXT transfer always in flight: block ``(rank - s) % cp`` arrives in round ``s``, and
+    as soon as the consumer asks for it the block is forwarded to the next rank, so that transfer overlaps the consumer's
+    attention on the block (the reference overlaps the same way with its RingComm, context_parallel/utils.py:398-415;
+    round 1 of this file waited for every transfer before computing anything)."""
+
+    def __init__(self, kv: torch.Tensor, group):
+        self.group = group
+        self.cp, self.rank = _world(group), _rank(group)
+        self.blocks: List[Optional[torch.Tensor]] = [None] * self.cp
+        self.blocks[self.rank] = kv
+        self.send_to = dist.get_global_rank(group, (self.rank + 1) % self.cp)
+        self.recv_from = dist.get_global_rank(group, (self.rank - 1) % self.cp)
+        self.cur, self.round, self.pending = kv, 0, None
+        self._post()
+
+    def _post(self) -> None:
+        if self.round + 1 >= self.cp:
+            self.pending = None
+            return
+        nxt = torch.empty_like(self.cur)
+        ops = [dist.P2POp(dist.isend, self.cur, self.send_to, self.group),
+               dist.P2POp(dist.irecv, nxt, self.recv_from, self.group)]
+        if self.rank % 2:
             ops.reverse()
-        for w in dist.batch_isend_irecv(ops):
+        self.pending = (dist.batch_isend_irecv(ops), nxt)
+
+    def _advance(self) -> None:
+        works, nxt = self.pending
+        for w in works:
             w.wait()
-        blocks[(rank - s) % cp] = nxt
-        cur = nxt
-    return blocks
+        self.round += 1
+        self.blocks[(self.rank - self.round) % self.cp] = nxt
+        self.cur = nxt
+        self._post()
+
+    def __getitem__(self, j: int) -> torch.Tensor:
+        while self.blocks[j] is None:
+            self._advance()
+        return self.blocks[j]
+
+    def all(self) -> List[torch.Tensor]:
+        """Finish the ring (blocks the plan skipped still have to travel on) and return every block by owner."""
+        while self.round + 1 < self.cp:
+            self._advance()
+        return self.blocks
 
 
 def zigzag_split(x: torch.Tensor, seq_dim: int, group) -> torch.Tensor:
