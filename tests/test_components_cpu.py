@@ -513,3 +513,26 @@ def test_graft_entry_build_compiles_library_and_harnesses():
         sys.path.remove(root)
     assert os.path.exists(harness)
     assert os.path.exists(os.path.join(root, "torchacc_b200", "_C.so"))
+
+
+def test_step_watchdog_dumps_stacks_of_a_hung_step(tmp_path):
+    """Fault injection for SURVEY 5.3: a step that blocks longer than its budget produces a stack dump naming the blocked
+    frame (and, with exit=True, ends the process instead of hanging the job); a step inside the budget prints nothing."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "hang.py"
+    script.write_text(
+        "import sys, time\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "from torchacc_b200.utils.watchdog import StepWatchdog\n"
+        "def fast_step():\n    time.sleep(0.05)\n"
+        "def blocked_in_collective():\n    time.sleep(30)\n"
+        "with StepWatchdog(5):\n    fast_step()\n"
+        "print('fast ok', flush=True)\n"
+        "with StepWatchdog(0.5, exit=True):\n    blocked_in_collective()\n"
+        "print('not reached', flush=True)\n")
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=60)
+    assert "fast ok" in r.stdout and "not reached" not in r.stdout
+    assert r.returncode != 0                                        # exit=True: the hung process is terminated
+    assert "blocked_in_collective" in r.stderr and "Timeout" in r.stderr
+    assert "fast_step" not in r.stderr                               # the healthy step left no dump
