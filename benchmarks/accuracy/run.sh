@@ -2,6 +2,8 @@
 # Accuracy benchmark (counterpart of reference benchmarks/accuracy/run.sh): train the same model with the sm_100a
 # kernels and with the plain-PyTorch reference ops, then assert |delta train_loss| <= 1e-2.
 #   NPROC=1 MODEL=llama3.2-1b STEPS=200 bash benchmarks/accuracy/run.sh
+#   HF=1 ...      the HuggingFace LlamaForCausalLM of the same geometry through ta.accelerate (the object the reference's
+#                 protocol wraps); SP=2 NPROC=2 ... adds Ulysses context parallelism
 set -euo pipefail
 cd "$(dirname "$0")/../.."
 NPROC=${NPROC:-1}; MODEL=${MODEL:-llama3.2-1b}; STEPS=${STEPS:-200}; SEQ=${SEQ:-1024}; BS=${BS:-4}
@@ -12,7 +14,7 @@ if [ "$NPROC" -gt 1 ]; then
 fi
 for impl in torch native; do
   $LAUNCH benchmarks/accuracy/run_clm.py --impl $impl --model "$MODEL" --steps "$STEPS" --seq_len "$SEQ" \
-      --batch_size "$BS" ${LAYERS:+--layers $LAYERS} --out "$OUT/$impl.json" 2>&1 | tee "$OUT/$impl.log"
+      --batch_size "$BS" ${LAYERS:+--layers $LAYERS} ${HF:+--hf} ${SP:+--sp_size $SP} --out "$OUT/$impl.json" 2>&1 | tee "$OUT/$impl.log"
 done
 python - "$OUT" <<'PY'
 import json, sys

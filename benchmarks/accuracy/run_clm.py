@@ -38,6 +38,10 @@ def main():
     p.add_argument("--vocab", type=int, default=4096, help="synthetic corpus vocabulary")
     p.add_argument("--device", default=None)
     p.add_argument("--fp8", action="store_true", help="native arm with Config.compute.fp8 (MX-FP8 linear layers)")
+    p.add_argument("--hf", action="store_true",
+                   help="train the HuggingFace LlamaForCausalLM of the same geometry through ta.accelerate (what the "
+                        "reference's protocol wraps: benchmarks/accuracy/llama.sh) instead of the native model definition")
+    p.add_argument("--sp_size", type=int, default=1, help="context-parallel ranks (Ulysses) -- works for --hf too")
     p.add_argument("--out", default=None)
     a = p.parse_args()
     if a.impl == "torch":
@@ -58,21 +62,36 @@ def main():
         over["num_hidden_layers"] = a.layers
     dtype = torch.bfloat16 if device.type == "cuda" else torch.float32
     torch.manual_seed(0)
-    with torch.device(device):
-        model = build_llama(llama_config(a.model, **over), dtype=dtype)
+    lc = llama_config(a.model, **over)
+    if a.hf:
+        from transformers import LlamaConfig, LlamaForCausalLM
+        hc = LlamaConfig(vocab_size=lc.vocab_size, hidden_size=lc.hidden_size, intermediate_size=lc.intermediate_size,
+                         num_hidden_layers=lc.num_hidden_layers, num_attention_heads=lc.num_attention_heads,
+                         num_key_value_heads=lc.num_key_value_heads, head_dim=lc.head_dim,
+                         max_position_embeddings=lc.max_position_embeddings, rope_theta=lc.rope_theta,
+                         rms_norm_eps=lc.rms_norm_eps, tie_word_embeddings=False, use_cache=False,
+                         attn_implementation="flash_attention_2" if device.type == "cuda" else "eager")
+        with torch.device(device):
+            model = LlamaForCausalLM(hc).to(dtype)
+    else:
+        with torch.device(device):
+            model = build_llama(lc, dtype=dtype)
     cfg = ta.Config()
     cfg.compute.bf16 = dtype == torch.bfloat16
     cfg.compute.fp8 = bool(a.fp8)
     cfg.memory.gc = True
-    cfg.dist.fsdp.size = a.fsdp_size or world
+    cfg.dist.sp.size = a.sp_size
+    cfg.dist.fsdp.size = a.fsdp_size or (world // a.sp_size)
     cfg.dist.fsdp.wrap_layer_cls = {"LlamaDecoderLayer"}
     model = ta.accelerate(model, config=cfg)
     opt = ta.optim.FusedAdamW(model.parameters(), lr=a.lr, betas=(0.9, 0.95), weight_decay=0.0)
-    stream = batches(ds, a.batch_size, rank, world, seed=1)
+    # ranks of one sp group are replicas: they consume the same batches
+    stream = batches(ds, a.batch_size, rank // a.sp_size, world // a.sp_size, seed=1)
     losses = []
     for step in range(a.steps):
         b = {k: v.to(device) for k, v in next(stream).items()}
-        loss = model(**b)["loss"]
+        out = model(**b)
+        loss = out["loss"] if isinstance(out, dict) else out.loss
         loss.backward()
         model.clip_grad_norm_(1.0)
         opt.step()
@@ -81,7 +100,7 @@ def main():
         if rank == 0 and (step % 20 == 0 or step == a.steps - 1):
             print(f"[{a.impl}] step {step:4d} loss {losses[-1]:.4f}", flush=True)
     train_loss = sum(losses[-a.avg_last:]) / min(a.avg_last, len(losses))
-    res = {"impl": a.impl + ("+fp8" if a.fp8 else ""), "train_loss": train_loss, "first_loss": losses[0], "steps": a.steps,
+    res = {"impl": a.impl + ("+fp8" if a.fp8 else "") + ("+hf" if a.hf else ""), "train_loss": train_loss, "first_loss": losses[0], "steps": a.steps,
            "optimal_loss": getattr(ds, "optimal_loss", None)}
     if rank == 0:
         print(json.dumps(res), flush=True)

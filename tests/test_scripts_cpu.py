@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 from dist_utils import _free_port
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -48,5 +50,15 @@ def test_example_train_llama_fsdp_single_process(tmp_path):
 def test_accuracy_benchmark_tiny():
     out = _run(["bash", "benchmarks/accuracy/run.sh"],
                env={"MODEL": "tiny", "LAYERS": "2", "STEPS": "12", "SEQ": "64", "BS": "2", "OUT": "/tmp/tb_acc_test"})
+    res = json.loads(out.strip().splitlines()[-1])
+    assert res["pass"] and res["abs_delta"] <= 1e-2
+
+
+def test_accuracy_benchmark_tiny_hf_model():
+    """Same protocol on the HuggingFace LlamaForCausalLM object (kernel patches + fused linear-CE through accelerate())."""
+    pytest.importorskip("transformers")
+    out = _run(["bash", "benchmarks/accuracy/run.sh"],
+               env={"MODEL": "tiny", "LAYERS": "2", "STEPS": "12", "SEQ": "64", "BS": "2", "HF": "1",
+                    "OUT": "/tmp/tb_acc_test_hf"})
     res = json.loads(out.strip().splitlines()[-1])
     assert res["pass"] and res["abs_delta"] <= 1e-2
