@@ -255,6 +255,7 @@ TB_API long long tb_carry_push(int kind, const uint64_t* src, uint64_t dst, cons
                         accumulate, stats, background, entry_channel, entry_epoch);
 }
 TB_API long long tb_carry_pending(long long job_id, int queue) { return tb::carry_pending(job_id, queue); }
+TB_API int tb_carry_take_probe(double flops, long long* out8) { return tb::carry_take_probe(flops, out8); }
 TB_API int tb_carry_flush(long long job_id, int queue, int num_sms, uint64_t stream) {
   return (int)tb::carry_flush(job_id, queue, num_sms, S(stream));
 }

@@ -142,6 +142,18 @@ int carry_take(double flops, CarryArgs* out) {
   return n;
 }
 
+int carry_take_probe(double flops, long long* out) {
+  CarryArgs ca;
+  const int n = carry_take(flops, &ca);
+  for (int i = 0; i < kCarrySlots; ++i) {
+    out[4 * i + 0] = i < n ? ca.slice[i].kind : 0;
+    out[4 * i + 1] = i < n ? ca.slice[i].chunk_begin : 0;
+    out[4 * i + 2] = i < n ? ca.slice[i].chunk_end : 0;
+    out[4 * i + 3] = i < n ? ca.slice[i].chunk_bytes : 0;
+  }
+  return n;
+}
+
 long long carry_pending(long long job_id, int queue) {
   std::lock_guard<std::mutex> lk(g_mu);
   long long c = 0;

@@ -24,6 +24,10 @@ cudaError_t symm_signal(const uint64_t* pad_ptrs, int rank, int world, int chann
 // Returns the number of slices filled (0 = nothing to carry).
 int carry_take(double flops, CarryArgs* out);
 
+// Host-only view of carry_take for tests of the queue logic (no kernel is launched; the taken chunks are CONSUMED):
+// out[4 i .. 4 i + 3] = kind, chunk_begin, chunk_end, chunk_bytes of slice i.  Returns the number of slices.
+int carry_take_probe(double flops, long long* out);
+
 // Chunks not yet handed to a kernel, for all jobs (job_id == 0) or up to and including job `job_id`, in queue
 // `queue` (0 foreground, 1 background, -1 both).
 long long carry_pending(long long job_id, int queue);

@@ -536,3 +536,66 @@ def test_step_watchdog_dumps_stacks_of_a_hung_step(tmp_path):
     assert r.returncode != 0                                        # exit=True: the hung process is terminated
     assert "blocked_in_collective" in r.stderr and "Timeout" in r.stderr
     assert "fast_step" not in r.stderr                               # the healthy step left no dump
+
+
+def test_carry_queue_slices_jobs_by_flop_budget():
+    """Host side of the carried collectives (csrc/fused/carry.cu, C++): jobs are cut into chunk ranges proportional to the
+    FLOPs of the GEMM that takes them along, foreground jobs before background jobs, at most two slices per launch, every
+    chunk handed out exactly once.  Pure host logic: runs without a GPU (pointers are never dereferenced)."""
+    import ctypes
+    from torchacc_b200 import _native as nat
+    from torchacc_b200.parallel import carry as C
+    L = nat.lib()
+    if L is None or not hasattr(L, "tb_carry_take_probe"):
+        pytest.skip("native library not built")
+    out = (nat.i64 * 8)()
+
+    def drain():
+        while L.tb_carry_take_probe(1e18, out) > 0:
+            pass
+    drain()
+    old = L.tb_carry_bytes_per_flop(1e-4)                 # 1e-4 bytes of NVLink traffic per GEMM FLOP
+    try:
+        world = 2
+        ptrs = (nat.u64 * world)(0x1000, 0x2000)
+        pads = (nat.u64 * world)(0x3000, 0x4000)
+        nbytes = 8 << 20                                   # 8 MiB shard per rank
+
+        def push(kind, background):
+            return L.tb_carry_push(kind, ptrs, 0x5000, pads, nbytes, 0, world, C.CH_GATHER, 1, 0, 0.5, 1, 1, 0, 0,
+                                   int(background), C.CH_PARAMS, 1)
+        bg = push(1, True)                                 # background gather (prefetch)
+        fg = push(2, False)                                # foreground reduce-scatter
+        assert fg > bg > 0
+        # gather: 8 KB chunks, own shard included -> 2 * 1024 chunks; reduce: (8 KB / world) per source and chunk -> 2048
+        assert L.tb_carry_pending(0, C.BACKGROUND) == 2048 and L.tb_carry_pending(0, C.FOREGROUND) == 2048
+        cost = {2: 4096 * world, 1: 8192 * (world - 1) / world}   # wire bytes per chunk: reduce / gather
+        nxt = {2: 0, 1: 0}                                           # next expected chunk of each job
+        launches = 0
+        while L.tb_carry_pending(0, C.ALL_QUEUES) > 0:
+            flops = float(1 << (34 + launches % 4))                  # GEMMs of different sizes
+            budget = flops * 1e-4
+            n = L.tb_carry_take_probe(flops, out)
+            assert 1 <= n <= 2
+            spent = 0.0
+            for i in range(n):
+                kind, lo, hi, chunk_bytes = (int(out[4 * i + k]) for k in range(4))
+                assert chunk_bytes == (4096 if kind == 2 else 8192)
+                assert lo == nxt[kind] and hi > lo                   # contiguous, every chunk exactly once
+                nxt[kind] = hi
+                spent += (hi - lo) * cost[kind]
+                if kind == 1:                                        # background work only once the foreground job is done
+                    assert nxt[2] == 2048 or i == 1                  # ... or with what is left of this launch's budget
+            assert spent <= budget                                   # never more traffic than the GEMM can hide
+            if nxt[1] < 2048:                                        # unless the queue ran dry the budget is used up
+                assert budget - spent < max(cost.values())
+            if launches == 0:
+                assert int(out[0]) == 2 and int(out[1]) == 0         # the foreground job goes first
+            launches += 1
+        assert nxt == {2: 2048, 1: 2048} and launches > 3
+        assert L.tb_carry_take_probe(1e12, out) == 0                 # empty queue: the GEMM carries nothing
+    finally:
+        drain()
+        L.tb_carry_bytes_per_flop(old)
+        stats = (nat.i64 * 4)()
+        L.tb_carry_stats(stats, 1)

@@ -31,6 +31,7 @@ nat.register_signatures({
                        ctypes.c_uint32], nat.i64),
     "tb_symm_signal": ([ctypes.POINTER(nat.u64), nat.i32, nat.i32, nat.i32, ctypes.c_uint32, nat.u64], nat.i32),
     "tb_carry_pending": ([nat.i64, nat.i32], nat.i64),
+    "tb_carry_take_probe": ([ctypes.c_double, ctypes.POINTER(nat.i64)], nat.i32),
     "tb_carry_flush": ([nat.i64, nat.i32, nat.i32, nat.u64], nat.i32),
     "tb_carry_bytes_per_flop": ([ctypes.c_double], ctypes.c_double),
     "tb_carry_stats": ([ctypes.POINTER(nat.i64), nat.i32], nat.i32),
