@@ -694,3 +694,50 @@ def test_ring_attention_p2p_overlapped_ring_on_4_ranks(causal):
     """impl='p2p' with the next transfer in flight (_LazyRing): 4 ranks, causal without zig-zag so that the plan SKIPS blocks
     which the ring still has to forward to the ranks behind."""
     run_distributed(_cp_worker, 4, args=("ring_p2p", causal))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _hf_pp_worker(rank, world):
+    """Pipeline parallelism over a HuggingFace LlamaForCausalLM: block-level fx trace (utils/trace.py), split before
+    ``model.layers.1``, parameter lifting (the final norm weight is fetched at the top level of the trace), 1F1B with the
+    loss computed by ``output_fn`` on the last stage -- 3 SGD steps track the single-process model."""
+    import torch.nn.functional as F
+    import torchacc_b200 as ta
+    from transformers import LlamaConfig, LlamaForCausalLM
+    hc = LlamaConfig(vocab_size=160, hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                     num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=64,
+                     attn_implementation="eager", use_cache=False)
+    ids = torch.randint(0, 160, (4, 16), generator=torch.Generator().manual_seed(7))
+
+    def loss_fn(logits, labels):
+        return F.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]).float(), labels[:, 1:].reshape(-1))
+
+    torch.manual_seed(0)
+    ref = LlamaForCausalLM(hc)
+    ref_opt = torch.optim.SGD(ref.parameters(), lr=0.1)
+    torch.manual_seed(0)
+    model = LlamaForCausalLM(hc)
+    cfg = ta.Config()
+    cfg.compute.bf16 = False
+    cfg.compute.disable_kernel_patches = True     # the stock HF forward (with logits) is what gets traced
+    cfg.dist.pp.size = 2
+    cfg.dist.pp.num_micro_batches = 2
+    cfg.dist.pp.split_points = ["model.layers.1"]
+    cfg.dist.pp.input_names = ["input_ids"]
+    model = ta.accelerate(model, config=cfg)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    for step in range(3):
+        loss = model.forward_backward(input_ids=ids, labels=ids, output_fn=loss_fn)
+        opt.step()
+        opt.zero_grad()
+        # reference: mean over the two micro-batches of their own means
+        ref_loss = sum(loss_fn(ref(input_ids=mb).logits, mb) for mb in ids.chunk(2)) / 2
+        ref_loss.backward()
+        ref_opt.step()
+        ref_opt.zero_grad()
+        assert abs(float(loss) - float(ref_loss)) < 2e-4, (step, float(loss), float(ref_loss))
+
+
+def test_pipeline_parallel_hf_model_through_block_level_trace():
+    pytest.importorskip("transformers")
+    run_distributed(_hf_pp_worker, 2)

@@ -9,7 +9,7 @@ import torch.distributed as dist
 
 from ...utils.utils import apply_to_tensors
 from . import schedule as S
-from .p2p import StageLink
+from .p2p import StageLink, flatten_values, unflatten_values
 from .partition import StageSpec
 
 
@@ -90,7 +90,8 @@ class PipeExecutor:
     def _forward(self, ins):
         values = dict(self.loaded.pop(ins.buffer, {}))
         if not self.is_first:
-            for name, t in zip(self.spec.recv_names, self.inputs[ins.buffer]):
+            # boundary values are tensors or flat tuples of tensors (regrouped from the flat transfer list)
+            for name, t in zip(self.spec.recv_names, unflatten_values(self.inputs[ins.buffer], self.link.recv_meta)):
                 values[name] = t
         out = self.module(**values)
         if self.is_last:
@@ -110,10 +111,10 @@ class PipeExecutor:
                 if len(self.spec.send_names) != 1:
                     raise ValueError("a stage with several outgoing values must return a dict")
                 out = {self.spec.send_names[0]: out}
-            self.outputs[ins.buffer] = [out[n] for n in self.spec.send_names]
+            self.outputs[ins.buffer], self._send_groups = flatten_values([out[n] for n in self.spec.send_names])
 
     def _send_act(self, ins):
-        self.link.send_activations(self.outputs[ins.buffer])
+        self.link.send_activations(self.outputs[ins.buffer], self._send_groups)
         if not torch.is_grad_enabled():
             self.outputs.pop(ins.buffer, None)
 

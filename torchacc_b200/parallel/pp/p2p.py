@@ -18,27 +18,65 @@ import torch.distributed as dist
 _DTYPES = [torch.float32, torch.float16, torch.bfloat16, torch.int64, torch.int32, torch.int16, torch.int8,
            torch.uint8, torch.bool, torch.float64]
 _MAX_TENSORS, _MAX_DIMS = 16, 6
-_HDR = 1 + _MAX_TENSORS * (3 + _MAX_DIMS)
+_FIELDS = 4                      # dtype id, ndim, requires_grad, group (index of the named value * 2 + member-of-a-tuple)
+_HDR = 1 + _MAX_TENSORS * (_FIELDS + _MAX_DIMS)
 
 
 class Meta:
-    __slots__ = ("shape", "dtype", "requires_grad")
+    """``group``: which named boundary value the tensor belongs to; ``in_tuple``: the value is a tuple / list of tensors
+    (e.g. the (cos, sin) pair an HF rotary-embedding module hands to every decoder layer) and this is one member."""
+    __slots__ = ("shape", "dtype", "requires_grad", "group", "in_tuple")
 
-    def __init__(self, shape, dtype, requires_grad):
+    def __init__(self, shape, dtype, requires_grad, group=0, in_tuple=False):
         self.shape, self.dtype, self.requires_grad = tuple(shape), dtype, bool(requires_grad)
+        self.group, self.in_tuple = int(group), bool(in_tuple)
 
     def __eq__(self, o):
-        return (self.shape, self.dtype, self.requires_grad) == (o.shape, o.dtype, o.requires_grad)
+        return (self.shape, self.dtype, self.requires_grad, self.group, self.in_tuple) == \
+            (o.shape, o.dtype, o.requires_grad, o.group, o.in_tuple)
 
 
-def encode_header(tensors: Sequence[torch.Tensor], device) -> torch.Tensor:
+def flatten_values(values: Sequence) -> Tuple[List[torch.Tensor], List[Tuple[int, bool]]]:
+    """Named boundary values (tensors, or one-level tuples / lists of tensors) -> flat tensor list + (group, in_tuple)."""
+    flat, groups = [], []
+    for g, v in enumerate(values):
+        if isinstance(v, (tuple, list)):
+            if not all(isinstance(t, torch.Tensor) for t in v):
+                raise TypeError("only tensors and flat tuples / lists of tensors can cross a pipeline stage boundary")
+            flat += list(v)
+            groups += [(g, True)] * len(v)
+        elif isinstance(v, torch.Tensor):
+            flat.append(v)
+            groups.append((g, False))
+        else:
+            raise TypeError(f"value of type {type(v).__name__} cannot cross a pipeline stage boundary")
+    return flat, groups
+
+
+def unflatten_values(tensors: Sequence[torch.Tensor], metas: Sequence[Meta]) -> List:
+    """Inverse of ``flatten_values`` on the receiving stage."""
+    out: List = []
+    for t, m in zip(tensors, metas):
+        if m.in_tuple:
+            if len(out) == m.group:
+                out.append([t])
+            else:
+                out[m.group].append(t)
+        else:
+            out.append(t)
+    return [tuple(v) if isinstance(v, list) else v for v in out]
+
+
+def encode_header(tensors: Sequence[torch.Tensor], device, groups: Optional[Sequence[Tuple[int, bool]]] = None) -> torch.Tensor:
     if len(tensors) > _MAX_TENSORS:
         raise ValueError(f"at most {_MAX_TENSORS} tensors per stage boundary")
     h = [len(tensors)]
-    for t in tensors:
+    for i, t in enumerate(tensors):
         if t.dim() > _MAX_DIMS:
             raise ValueError(f"at most {_MAX_DIMS}-d tensors cross a stage boundary")
-        h += [_DTYPES.index(t.dtype), t.dim(), int(t.requires_grad)] + list(t.shape) + [0] * (_MAX_DIMS - t.dim())
+        g, tup = groups[i] if groups is not None else (i, False)
+        h += [_DTYPES.index(t.dtype), t.dim(), int(t.requires_grad), 2 * g + int(tup)] + list(t.shape) + \
+            [0] * (_MAX_DIMS - t.dim())
     h += [0] * (_HDR - len(h))
     return torch.tensor(h, dtype=torch.int64, device=device)
 
@@ -47,9 +85,9 @@ def decode_header(h: torch.Tensor) -> List[Meta]:
     v = h.tolist()          # the one host sync of a shape epoch
     out, p = [], 1
     for _ in range(v[0]):
-        dt, nd, rg = v[p], v[p + 1], v[p + 2]
-        out.append(Meta(v[p + 3:p + 3 + nd], _DTYPES[dt], rg))
-        p += 3 + _MAX_DIMS
+        dt, nd, rg, grp = v[p], v[p + 1], v[p + 2], v[p + 3]
+        out.append(Meta(v[p + _FIELDS:p + _FIELDS + nd], _DTYPES[dt], rg, grp // 2, grp % 2))
+        p += _FIELDS + _MAX_DIMS
     return out
 
 
@@ -99,10 +137,11 @@ class StageLink:
         self.sent_meta = None
 
     # ---- activations: prev -> me -> next ---------------------------------------------------------------------
-    def send_activations(self, tensors: Sequence[torch.Tensor]):
-        metas = [Meta(t.shape, t.dtype, t.requires_grad) for t in tensors]
+    def send_activations(self, tensors: Sequence[torch.Tensor], groups: Optional[Sequence[Tuple[int, bool]]] = None):
+        groups = list(groups) if groups is not None else [(i, False) for i in range(len(tensors))]
+        metas = [Meta(t.shape, t.dtype, t.requires_grad, g, tup) for t, (g, tup) in zip(tensors, groups)]
         if self.sent_meta is None or self.sent_meta != metas:
-            dist.send(encode_header(tensors, self.device), self.next, group=self.group)
+            dist.send(encode_header(tensors, self.device, groups), self.next, group=self.group)
             self.sent_meta = metas
         works = [dist.isend(t.detach().contiguous(), self.next, group=self.group) for t in tensors]
         self._pending += works

@@ -57,13 +57,20 @@ def names_of_split_points(model: nn.Module, split_points: Sequence[Union[str, nn
 class _TaggingTracer(fx.Tracer):
     """Records the module path under which each node is created (``node.meta['mod_path']``)."""
 
-    def __init__(self, leaf_paths: Sequence[str] = ()):
+    def __init__(self, leaf_paths: Sequence[str] = (), leaf_classes: Sequence[type] = (),
+                 leaf_name_suffixes: Sequence[str] = ()):
         super().__init__()
         self._stack: List[str] = []
         self._leaf_paths = set(leaf_paths)
+        self._leaf_classes = tuple(leaf_classes)
+        self._leaf_suffixes = tuple(leaf_name_suffixes)
 
     def is_leaf_module(self, m, qualname):
-        return qualname in self._leaf_paths or super().is_leaf_module(m, qualname)
+        if qualname in self._leaf_paths or (self._leaf_classes and isinstance(m, self._leaf_classes)):
+            return True
+        if self._leaf_suffixes and type(m).__name__.endswith(self._leaf_suffixes):
+            return True
+        return super().is_leaf_module(m, qualname)
 
     def call_module(self, m, forward, args, kwargs):
         self._stack.append(self.path_of_module(m))
@@ -86,13 +93,25 @@ def _under(path: str, root: str) -> bool:
 
 def trace_and_split(model: nn.Module, split_names: List[str], input_names: Optional[List[str]]) -> List[StageSpec]:
     import inspect
-    sig = inspect.signature(model.forward)
-    input_names = input_names or [n for n, p in sig.parameters.items() if p.default is inspect.Parameter.empty]
-    concrete = {p.name: p.default for p in sig.parameters.values()
-                if p.name not in input_names and p.default is not inspect.Parameter.empty}
-    tracer = _TaggingTracer()
-    graph = tracer.trace(model, concrete_args=concrete)
-    gm = fx.GraphModule(model, graph)
+    from ...utils.trace import hf_trace_entry, is_hf_model, lift_single_use_params
+    if is_hf_model(model):
+        # HuggingFace forwards cannot be traced whole (kwargs decorators, cache / mask control flow): block-level trace
+        # through an explicit-input entry module (utils/trace.py).  The last stage returns the logits; the loss is the
+        # user's ``output_fn(logits, labels=...)`` like in the reference's pipeline examples.
+        input_names = list(input_names) if input_names else ["input_ids"]
+        root, leaf_classes, leaf_suffixes = hf_trace_entry(model, input_names, "logits")
+        tracer = _TaggingTracer(leaf_classes=leaf_classes, leaf_name_suffixes=leaf_suffixes)
+        graph = tracer.trace(root)
+        split_names = ["model." + n for n in split_names]
+    else:
+        sig = inspect.signature(model.forward)
+        input_names = input_names or [n for n, p in sig.parameters.items() if p.default is inspect.Parameter.empty]
+        concrete = {p.name: p.default for p in sig.parameters.values()
+                    if p.name not in input_names and p.default is not inspect.Parameter.empty}
+        root = model
+        tracer = _TaggingTracer()
+        graph = tracer.trace(model, concrete_args=concrete)
+    gm = fx.GraphModule(root, graph)
     # stage assignment: bump the stage when the first node belonging to the next split module appears
     stage_of: Dict[fx.Node, int] = {}
     cur, nxt = 0, 0
@@ -106,7 +125,9 @@ def trace_and_split(model: nn.Module, split_names: List[str], input_names: Optio
     if nxt != len(split_names):
         raise ValueError(f"split points {split_names[nxt:]} were never reached while tracing the model")
     num_stages = len(split_names) + 1
-    split = split_module(gm, model, lambda n: stage_of[n])
+    split = split_module(gm, root, lambda n: stage_of[n])
+    # parameters / buffers fetched at the top level move into the one stage that uses them (reference utils/trace.py:95-175)
+    lift_single_use_params(split)
     # top-level plumbing: placeholders, call_module(submod_k), getitem, output
     producers: Dict[str, int] = {}       # value name -> producing stage (-1 for batch inputs)
     consumers: Dict[str, List[int]] = {}

@@ -82,6 +82,30 @@ def _hf_leaf_classes(model: nn.Module) -> Tuple[type, ...]:
     return tuple({type(m) for m in model.modules() if type(m).__name__ in names})
 
 
+def is_hf_model(model: nn.Module) -> bool:
+    try:
+        from transformers import PreTrainedModel
+    except ImportError:
+        return False
+    return isinstance(model, PreTrainedModel)
+
+
+def hf_trace_entry(model: nn.Module, input_names: Sequence[str], output_attr: Optional[str] = "logits"):
+    """Prepare a HuggingFace model for block-level tracing: returns ``(entry module, leaf classes, leaf name suffixes)``.
+    The entry takes ``input_names`` positionally and addresses the original modules under the ``model.`` prefix.  Side
+    effects on ``model.config`` (kept: the traced graph relies on them): attention implementation ``"torchacc_b200"`` (no
+    dense mask is built; our kernels mask in-kernel) and ``use_cache = False``."""
+    for n in input_names:
+        if not n.isidentifier():
+            raise ValueError(f"input name {n!r} is not an identifier")
+    from .patch import patch_fa
+    patch_fa()                                            # registers the "torchacc_b200" attention interface
+    model.config._attn_implementation = "torchacc_b200"
+    if getattr(model.config, "use_cache", None) is not None:
+        model.config.use_cache = False
+    return _make_entry(model, list(input_names), output_attr), _hf_leaf_classes(model), ("RotaryEmbedding",)
+
+
 def trace(model: nn.Module, input_names: Optional[List[str]] = None, leaf_classes: Iterable[type] = (),
           output_attr: Optional[str] = None) -> fx.GraphModule:
     """GraphModule of ``model`` with ``input_names`` as placeholders.  HF models: block-level (see module docstring);
@@ -90,29 +114,14 @@ def trace(model: nn.Module, input_names: Optional[List[str]] = None, leaf_classe
     sig_names = [n for n, p in inspect.signature(model.forward).parameters.items()
                  if p.kind not in (inspect.Parameter.VAR_KEYWORD, inspect.Parameter.VAR_POSITIONAL)]
     input_names = list(input_names) if input_names else sig_names[:1]
-    for n in input_names:
-        if not n.isidentifier():
-            raise ValueError(f"input name {n!r} is not an identifier")
-    is_hf = False
-    try:
-        from transformers import PreTrainedModel
-        is_hf = isinstance(model, PreTrainedModel)
-    except ImportError:
-        pass
-    if not is_hf:
+    if not is_hf_model(model):
         tracer = BlockTracer(tuple(leaf_classes))
         graph = tracer.trace(model, concrete_args=get_concrete_args(model, input_names))
         return fx.GraphModule(model, graph)
 
-    from .patch import patch_fa
-    patch_fa()                                            # registers the "torchacc_b200" attention interface
     saved_impl = model.config._attn_implementation
-    saved_cache = getattr(model.config, "use_cache", None)
-    model.config._attn_implementation = "torchacc_b200"   # in-kernel causal masking: no dense mask in the graph
-    if saved_cache is not None:
-        model.config.use_cache = False
-    entry = _make_entry(model, input_names, output_attr if output_attr is not None else "logits")
-    tracer = BlockTracer(tuple(leaf_classes) + _hf_leaf_classes(model), ("RotaryEmbedding",))
+    entry, hf_leaves, suffixes = hf_trace_entry(model, input_names, output_attr if output_attr is not None else "logits")
+    tracer = BlockTracer(tuple(leaf_classes) + hf_leaves, suffixes)
     try:
         graph = tracer.trace(entry)
     except Exception as e:
@@ -120,9 +129,6 @@ def trace(model: nn.Module, input_names: Optional[List[str]] = None, leaf_classe
         raise RuntimeError(
             f"block-level fx trace of {type(model).__name__} failed ({type(e).__name__}: {e}); pipeline stages do not "
             f"need a trace -- cut the module tree with dist.pp.split_points instead") from e
-    finally:
-        if saved_cache is not None:
-            model.config.use_cache = saved_cache
     return fx.GraphModule(entry, graph)
 
 
