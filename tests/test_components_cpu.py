@@ -477,8 +477,9 @@ def test_trace_hf_llama_block_level():
         assert layer_calls == ["model.model.layers.0", "model.model.layers.1"]
         assert torch.allclose(gm(ids, pos), want, atol=1e-5)
         split = _split_at(gm, "model.model.layers.1")
-        qmap = lift_single_use_params(split)
-        assert qmap == {"submod_1.lifted_model_model_norm_weight": "model.model.norm.weight"}
+        # norms are leaf modules as well (their forward may be patched onto fused kernels): nothing is fetched at the top level
+        assert "model.model.norm" in [n.target for n in gm.graph.nodes if n.op == "call_module"]
+        assert lift_single_use_params(split) == {}
         assert torch.allclose(split(ids, pos), want, atol=1e-5)
     finally:
         unpatch_all()

@@ -697,7 +697,7 @@ def test_ring_attention_p2p_overlapped_ring_on_4_ranks(causal):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def _hf_pp_worker(rank, world):
+def _hf_pp_worker(rank, world, patches=False):
     """Pipeline parallelism over a HuggingFace LlamaForCausalLM: block-level fx trace (utils/trace.py), split before
     ``model.layers.1``, parameter lifting (the final norm weight is fetched at the top level of the trace), 1F1B with the
     loss computed by ``output_fn`` on the last stage -- 3 SGD steps track the single-process model."""
@@ -719,7 +719,7 @@ def _hf_pp_worker(rank, world):
     model = LlamaForCausalLM(hc)
     cfg = ta.Config()
     cfg.compute.bf16 = False
-    cfg.compute.disable_kernel_patches = True     # the stock HF forward (with logits) is what gets traced
+    cfg.compute.disable_kernel_patches = not patches   # with the liger-style patches the norms / MLPs call our ops
     cfg.dist.pp.size = 2
     cfg.dist.pp.num_micro_batches = 2
     cfg.dist.pp.split_points = ["model.layers.1"]
@@ -738,6 +738,7 @@ def _hf_pp_worker(rank, world):
         assert abs(float(loss) - float(ref_loss)) < 2e-4, (step, float(loss), float(ref_loss))
 
 
-def test_pipeline_parallel_hf_model_through_block_level_trace():
+@pytest.mark.parametrize("patches", [False, True])
+def test_pipeline_parallel_hf_model_through_block_level_trace(patches):
     pytest.importorskip("transformers")
-    run_distributed(_hf_pp_worker, 2)
+    run_distributed(_hf_pp_worker, 2, args=(patches,))

@@ -103,7 +103,8 @@ def hf_trace_entry(model: nn.Module, input_names: Sequence[str], output_attr: Op
     model.config._attn_implementation = "torchacc_b200"
     if getattr(model.config, "use_cache", None) is not None:
         model.config.use_cache = False
-    return _make_entry(model, list(input_names), output_attr), _hf_leaf_classes(model), ("RotaryEmbedding",)
+    # norm modules stay leaves too: their forward may be patched onto our fused kernels (ops/liger.py), which are opaque to fx
+    return _make_entry(model, list(input_names), output_attr), _hf_leaf_classes(model), ("RotaryEmbedding", "RMSNorm", "LayerNorm")
 
 
 def trace(model: nn.Module, input_names: Optional[List[str]] = None, leaf_classes: Iterable[type] = (),
