@@ -742,3 +742,63 @@ def _hf_pp_worker(rank, world, patches=False):
 def test_pipeline_parallel_hf_model_through_block_level_trace(patches):
     pytest.importorskip("transformers")
     run_distributed(_hf_pp_worker, 2, args=(patches,))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _hf_tp_worker(rank, world, family, fsdp=1):
+    """Tensor parallelism of an UNMODIFIED HuggingFace model through accelerate(): q/k/v, gate/up column-parallel, o/down
+    row-parallel (parallel/tp.py::shard_hf_for_tp); 3 SGD steps track the single-process model."""
+    import torchacc_b200 as ta
+    if family == "llama":
+        from transformers import LlamaConfig as C, LlamaForCausalLM as M
+    else:
+        from transformers import Qwen2Config as C, Qwen2ForCausalLM as M          # attention projections carry biases
+    hc = C(vocab_size=160, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+           num_key_value_heads=2, max_position_embeddings=64, attn_implementation="eager", use_cache=False)
+    torch.manual_seed(0)
+    ref = M(hc)
+    ref_opt = torch.optim.SGD(ref.parameters(), lr=0.1)
+    torch.manual_seed(0)
+    model = M(hc)
+    ids = torch.randint(0, 160, (4, 16), generator=torch.Generator().manual_seed(11))
+    cfg = ta.Config()
+    cfg.compute.bf16 = False
+    cfg.dist.tp.size = world // fsdp
+    if fsdp > 1:
+        cfg.dist.fsdp.size = fsdp
+        cfg.dist.fsdp.wrap_layer_cls = {type(ref.model.layers[0]).__name__}
+    model = ta.accelerate(model, config=cfg)
+    from torchacc_b200.parallel.tp import ColumnParallelLinear, RowParallelLinear
+    kinds = {type(m).__name__ for m in model.modules()}
+    assert "ColumnParallelLinear" in kinds and "RowParallelLinear" in kinds
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    # with fsdp > 1 every fsdp rank takes its own slice of the batch
+    mesh = cfg.get_mesh()
+    dp_rank, dp_world = (mesh.get_fsdp_rank(), fsdp) if fsdp > 1 else (0, 1)
+    local = ids.chunk(dp_world)[dp_rank]
+    for step in range(3):
+        loss = model(input_ids=local, labels=local).loss
+        loss.backward()
+        opt.step()
+        model.zero_grad()
+        r = ref(input_ids=ids, labels=ids).loss
+        r.backward()
+        ref_opt.step()
+        ref_opt.zero_grad()
+        if fsdp > 1:
+            import torch.distributed as dist
+            l = loss.detach().clone()
+            dist.all_reduce(l, group=mesh.get_fsdp_proc_group())
+            loss = l / fsdp
+        assert abs(float(loss) - float(r)) < 2e-4, (step, float(loss), float(r))
+
+
+@pytest.mark.parametrize("family", ["llama", "qwen2"])
+def test_hf_model_tensor_parallel_through_accelerate(family):
+    pytest.importorskip("transformers")
+    run_distributed(_hf_tp_worker, 2, args=(family,))
+
+
+def test_hf_model_tensor_parallel_with_fsdp():
+    pytest.importorskip("transformers")
+    run_distributed(_hf_tp_worker, 4, args=("llama", 2))

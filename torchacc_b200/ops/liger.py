@@ -26,6 +26,9 @@ def rms_forward(self, hidden_states):
 
 
 def mlp_forward(self, x):
+    if not all(type(m) is nn.Linear for m in (self.gate_proj, self.up_proj, self.down_proj)):
+        # tensor-parallel (or otherwise specialised) projections bring their own forward: only the activation is ours
+        return self.down_proj(swiglu_separate(self.gate_proj(x), self.up_proj(x)))
     g = linear(x, self.gate_proj.weight, self.gate_proj.bias)
     u = linear(x, self.up_proj.weight, self.up_proj.bias)
     return linear(swiglu_separate(g, u), self.down_proj.weight, self.down_proj.bias)

@@ -371,19 +371,108 @@ def shard_llama_for_tp(lm, tp: TPContext) -> None:
     lm.model.pctx.sequence_parallel = tp.sequence_parallel
 
 
+# ------------------------------------------------------------------------------------------------------------
+# HuggingFace decoder models: Megatron-style sharding of the existing nn.Linear modules
+# ------------------------------------------------------------------------------------------------------------
+class ColumnParallelLinear(nn.Linear):
+    """``nn.Linear`` holding the rows ``[rank * out/tp, (rank + 1) * out/tp)`` of the original weight; the input is
+    replicated over the tp group, the output is this rank's slice of the features (heads)."""
+
+    @classmethod
+    def from_linear(cls, lin: nn.Linear, tp: TPContext) -> "ColumnParallelLinear":
+        if lin.out_features % tp.size:
+            raise ValueError(f"out_features {lin.out_features} not divisible by the tp size {tp.size}")
+        rows = lin.out_features // tp.size
+        new = cls.__new__(cls)
+        nn.Module.__init__(new)
+        new.in_features, new.out_features = lin.in_features, rows
+        new.weight = nn.Parameter(_shard_rows(lin.weight.detach(), tp.rank, tp.size).clone(),
+                                  requires_grad=lin.weight.requires_grad)
+        new.bias = None if lin.bias is None else nn.Parameter(
+            _shard_rows(lin.bias.detach(), tp.rank, tp.size).clone(), requires_grad=lin.bias.requires_grad)
+        new.__dict__["tp"] = tp
+        return new
+
+    def forward(self, x):
+        y = column_parallel_linear(x.reshape(-1, x.shape[-1]), self.weight, self.bias, self.tp)
+        return y.view(*x.shape[:-1], self.out_features)
+
+
+class RowParallelLinear(nn.Linear):
+    """``nn.Linear`` holding the columns ``[rank * in/tp, ...)`` of the original weight: consumes the feature slice a
+    column-parallel layer produced, the partial products are summed over the tp group (bias added once, after the sum)."""
+
+    @classmethod
+    def from_linear(cls, lin: nn.Linear, tp: TPContext) -> "RowParallelLinear":
+        if lin.in_features % tp.size:
+            raise ValueError(f"in_features {lin.in_features} not divisible by the tp size {tp.size}")
+        new = cls.__new__(cls)
+        nn.Module.__init__(new)
+        new.in_features, new.out_features = lin.in_features // tp.size, lin.out_features
+        new.weight = nn.Parameter(_shard_cols(lin.weight.detach(), tp.rank, tp.size).clone(),
+                                  requires_grad=lin.weight.requires_grad)
+        new.bias = None if lin.bias is None else nn.Parameter(lin.bias.detach().clone(),
+                                                             requires_grad=lin.bias.requires_grad)
+        new.__dict__["tp"] = tp
+        return new
+
+    def forward(self, x):
+        y = row_parallel_linear(x.reshape(-1, x.shape[-1]), self.weight, self.tp).view(*x.shape[:-1], self.out_features)
+        return y if self.bias is None else y + self.bias
+
+
+_HF_COLUMN = ("q_proj", "k_proj", "v_proj", "gate_proj", "up_proj")
+_HF_ROW = ("o_proj", "down_proj")
+
+
+def shard_hf_for_tp(model: nn.Module, tp: TPContext) -> int:
+    """Tensor parallelism for HuggingFace decoder families that follow the Llama layout (Llama, Qwen2/3, Mistral, Gemma,
+    ...): q/k/v and gate/up projections become column-parallel (whole heads / FFN columns per rank), o_proj and down_proj
+    row-parallel; the residual stream, norms, embedding and lm_head stay replicated (their gradients are identical on
+    every tp rank because their inputs are).  HF attention modules infer the local head count from the projection
+    output (``view(..., -1, head_dim)``), so their forward is untouched.  Returns the number of layers rewritten.
+    The reference leaves TP of HF models to XLA's SPMD partitioner (torchacc/dist/tp.py:1-5)."""
+    cfg = getattr(model, "config", None)
+    hk = getattr(cfg, "num_key_value_heads", None) or getattr(cfg, "num_attention_heads", None)
+    hq = getattr(cfg, "num_attention_heads", None)
+    for n, name in ((hq, "num_attention_heads"), (hk, "num_key_value_heads")):
+        if n is not None and n % tp.size:
+            raise ValueError(f"{name} = {n} is not divisible by the tp size {tp.size}")
+    count = 0
+    for mod in list(model.modules()):
+        touched = False
+        for name in _HF_COLUMN:
+            lin = getattr(mod, name, None)
+            if type(lin) is nn.Linear:
+                setattr(mod, name, ColumnParallelLinear.from_linear(lin, tp))
+                touched = True
+        for name in _HF_ROW:
+            lin = getattr(mod, name, None)
+            if type(lin) is nn.Linear:
+                setattr(mod, name, RowParallelLinear.from_linear(lin, tp))
+                touched = True
+        count += int(touched)
+    if count == 0:
+        raise NotImplementedError(
+            f"{type(model).__name__}: no q_proj/k_proj/v_proj/o_proj or gate_proj/up_proj/down_proj linears found; tensor "
+            "parallelism covers the native Llama family and HuggingFace models with the Llama module layout")
+    return count
+
+
 def parallelize_model(model: nn.Module, config, mesh) -> nn.Module:
     """Apply TP and/or context parallelism to a native model (called by DistributedParallel)."""
     from .bootstrap import current_device
     device = current_device()
     core = model
     if config.dist.tp.size > 1:
-        if not hasattr(model, "config") or not hasattr(model, "model") or not hasattr(model.model, "pctx"):
-            raise NotImplementedError(
-                "tensor parallelism is implemented for the native Llama family (torchacc_b200.models); "
-                "HF modules can be converted with LlamaForCausalLM.load_hf_state_dict")
-        tp = TPContext(mesh.get_tp_proc_group(), device, config.dist.tp.sequence_parallel,
-                       config.dist.fsdp.fused_collectives)
-        shard_llama_for_tp(model, tp)
+        if hasattr(model, "config") and hasattr(model, "model") and hasattr(model.model, "pctx"):
+            tp = TPContext(mesh.get_tp_proc_group(), device, config.dist.tp.sequence_parallel,
+                           config.dist.fsdp.fused_collectives)
+            shard_llama_for_tp(model, tp)
+        else:
+            # HuggingFace layout: replicated residual stream (no sequence parallelism), see shard_hf_for_tp
+            tp = TPContext(mesh.get_tp_proc_group(), device, False, config.dist.fsdp.fused_collectives)
+            shard_hf_for_tp(model, tp)
     if config.dist.sp.size > 1:
         if hasattr(model, "model") and hasattr(model.model, "pctx"):
             model.model.pctx.cp_mesh = mesh
