@@ -4,7 +4,13 @@
 decoder-layer class name, activation checkpointing, bf16.
 
     torchrun --nproc-per-node 2 --master-addr 127.0.0.1 examples/train_hf_model.py
+    torchrun --nproc-per-node 4 --master-addr 127.0.0.1 examples/train_hf_model.py --tp 2      # tp2 x fsdp2
+    torchrun --nproc-per-node 4 --master-addr 127.0.0.1 examples/train_hf_model.py --sp 2      # Ulysses cp2 x fsdp2
+
+The same HF object also runs under tensor parallelism (projections sharded in place) and context parallelism (sequence
+sharded, attention over the sp group); ranks of one tp / sp group consume the same batch.
 """
+import argparse
 import os
 import sys
 
@@ -16,6 +22,11 @@ from transformers import LlamaConfig, LlamaForCausalLM  # noqa: E402
 
 
 def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tp", type=int, default=1)
+    ap.add_argument("--sp", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    a = ap.parse_args()
     device = ta.dist.current_device()
     hf_cfg = LlamaConfig(vocab_size=8192, hidden_size=512, intermediate_size=1408, num_hidden_layers=4,
                          num_attention_heads=8, num_key_value_heads=4, max_position_embeddings=1024,
@@ -26,16 +37,18 @@ def main():
     cfg.compute.bf16 = device.type == "cuda"
     cfg.memory.gc = True
     cfg.memory.gc_cls = {"LlamaDecoderLayer"}
-    cfg.dist.fsdp.size = ta.dist.world_size()
+    cfg.dist.tp.size, cfg.dist.sp.size = a.tp, a.sp
+    cfg.dist.fsdp.size = ta.dist.world_size() // (a.tp * a.sp)
     cfg.dist.fsdp.wrap_layer_cls = {"LlamaDecoderLayer"}
     if device.type == "cuda":
         ta.utils.patch.patch_fa()                        # HF flash_attention_2 call sites -> our attention kernels
     model = ta.accelerate(model, config=cfg)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3)  # any torch optimizer works on the flat shards
 
-    g = torch.Generator().manual_seed(ta.dist.rank())
+    # data-parallel index: ranks that differ only in their tp / sp coordinate see the same samples
+    g = torch.Generator().manual_seed(ta.dist.rank() // (a.tp * a.sp))
     ids = torch.randint(0, hf_cfg.vocab_size, (2, 256), generator=g).to(device)
-    for step in range(20):
+    for step in range(a.steps):
         out = model(input_ids=ids, labels=ids)
         out.loss.backward()
         model.clip_grad_norm_(1.0)
