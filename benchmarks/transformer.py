@@ -44,6 +44,10 @@ def parse():
     p.add_argument("--profile", action="store_true", help="torch.profiler trace to ./log/profile")
     p.add_argument("--disable_loss_print", action="store_true")
     p.add_argument("--tp_no_sequence_parallel", action="store_true")
+    p.add_argument("--hf", action="store_true",
+                   help="build the HuggingFace LlamaForCausalLM of the preset's geometry instead of the native model "
+                        "(the reference benchmark uses AutoModelForCausalLM.from_config, benchmarks/transformer.py:96-102); "
+                        "tp / sp / pp / fsdp apply to it through accelerate()")
     return p.parse_args()
 
 
@@ -61,8 +65,21 @@ def main():
         else:
             from torchacc_b200.models import llama_config
             base = llama_config(a.model_name)
-            model = build_llama(a.model_name, dtype=dtype,
-                                max_position_embeddings=max(a.max_seq_length, base.max_position_embeddings))
+            max_pos = max(a.max_seq_length, base.max_position_embeddings)
+            if a.hf:
+                from transformers import LlamaConfig, LlamaForCausalLM
+                hc = LlamaConfig(vocab_size=base.vocab_size, hidden_size=base.hidden_size,
+                                 intermediate_size=base.intermediate_size, num_hidden_layers=base.num_hidden_layers,
+                                 num_attention_heads=base.num_attention_heads,
+                                 num_key_value_heads=base.num_key_value_heads, head_dim=base.head_dim,
+                                 max_position_embeddings=max_pos, rope_theta=base.rope_theta,
+                                 rms_norm_eps=base.rms_norm_eps, tie_word_embeddings=False, use_cache=False,
+                                 attn_implementation="flash_attention_2" if device.type == "cuda" else "eager")
+                model = LlamaForCausalLM(hc).to(dtype)
+            else:
+                model = build_llama(a.model_name, dtype=dtype, max_position_embeddings=max_pos)
+    if a.hf and is_gpt2:
+        raise SystemExit("--hf builds Llama-family presets")
     layer_cls = "GPT2Block" if is_gpt2 else "LlamaDecoderLayer"
     vocab = model.config.vocab_size
 
@@ -84,7 +101,9 @@ def main():
         cfg.dist.pp.num_micro_batches = a.pp_micro_batches
         cfg.dist.pp.split_points = [f"{prefix}.{per * i}" for i in range(1, a.pp_size)]
 
-    g = torch.Generator().manual_seed(rank)
+    # ranks that differ only in their pp / sp / tp coordinate work on the SAME samples (default topology: those axes vary
+    # fastest), so the data stream is seeded by the data-parallel index
+    g = torch.Generator().manual_seed(rank // (a.pp_size * a.sp_size * a.tp_size))
     batches = [{"input_ids": torch.randint(0, vocab, (a.batch_size, a.max_seq_length), generator=g)} for _ in range(8)]
     for b in batches:
         b["labels"] = b["input_ids"]
@@ -107,6 +126,10 @@ def main():
                        on_trace_ready=tensorboard_trace_handler("./log/profile"))
         prof.start()
 
+    def hf_loss(logits, labels):          # last pipeline stage of an HF model returns the logits
+        return torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]).float(),
+                                                 labels[:, 1:].reshape(-1))
+
     cuda = device.type == "cuda"
     t_ev = torch.cuda.Event(enable_timing=True) if cuda else None
     if cuda:
@@ -114,9 +137,10 @@ def main():
     t_host = time.perf_counter()
     for step, batch in enumerate(loader, 1):
         if a.pp_size > 1:
-            loss = model.forward_backward(**batch)
+            loss = model.forward_backward(**batch, output_fn=hf_loss) if a.hf else model.forward_backward(**batch)
         else:
-            loss = model(**batch)["loss"]
+            out = model(**batch)
+            loss = out["loss"] if isinstance(out, dict) else out.loss
             scaler.scale(loss).backward()
         model.clip_grad_norm_(1.0)
         scaler.step(opt)
