@@ -600,3 +600,24 @@ def test_carry_queue_slices_jobs_by_flop_budget():
         L.tb_carry_bytes_per_flop(old)
         stats = (nat.i64 * 4)()
         L.tb_carry_stats(stats, 1)
+
+
+def test_pp_boundary_header_roundtrip_with_tuple_values():
+    """Stage-boundary protocol: named values may be tensors or flat tuples of tensors (HF's rotary (cos, sin) pair); the
+    single int64 header of a shape epoch carries dtype / shape / requires_grad and the grouping."""
+    from torchacc_b200.parallel.pp import p2p
+    hidden = torch.randn(2, 5, 8, requires_grad=True)
+    cos, sin = torch.randn(1, 5, 4), torch.randn(1, 5, 4)
+    ids = torch.zeros(2, 5, dtype=torch.int64)
+    flat, groups = p2p.flatten_values([hidden, (cos, sin), ids])
+    assert len(flat) == 4 and groups == [(0, False), (1, True), (1, True), (2, False)]
+    metas = p2p.decode_header(p2p.encode_header(flat, "cpu", groups))
+    assert [m.shape for m in metas] == [(2, 5, 8), (1, 5, 4), (1, 5, 4), (2, 5)]
+    assert [m.dtype for m in metas] == [torch.float32, torch.float32, torch.float32, torch.int64]
+    assert [m.requires_grad for m in metas] == [True, False, False, False]
+    back = p2p.unflatten_values(flat, metas)
+    assert back[0] is hidden and isinstance(back[1], tuple) and back[1][0] is cos and back[1][1] is sin and back[2] is ids
+    with pytest.raises(TypeError):
+        p2p.flatten_values([hidden, {"a": cos}])
+    with pytest.raises(TypeError):
+        p2p.flatten_values([(cos, 3)])
