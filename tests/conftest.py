@@ -13,6 +13,26 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "multigpu: needs >= 2 CUDA devices")
 
 
+@pytest.hookimpl(tryfirst=True)
+def pytest_cmdline_main(config):
+    """The CPU tier (``-m "not gpu"``) is dominated by multi-process gloo tests that spend their time spawning workers
+    and importing torch: run it on 4 xdist workers when pytest-xdist is available and no ``-n`` was given
+    (``TORCHACC_B200_TEST_WORKERS=0`` keeps it serial).  The GPU tiers are never parallelised: their tests share one
+    device and the driver inspects the pytest process itself."""
+    try:
+        n = int(os.environ.get("TORCHACC_B200_TEST_WORKERS", "4"))
+    except ValueError:
+        n = 0
+    opt = config.option
+    if (n > 1 and getattr(opt, "markexpr", "") == "not gpu" and config.pluginmanager.hasplugin("xdist")
+            and not getattr(opt, "numprocesses", None) and not getattr(opt, "usepdb", False)
+            and not os.environ.get("PYTEST_XDIST_WORKER")):
+        opt.numprocesses = n
+        if getattr(opt, "dist", "no") == "no":
+            opt.dist = "load"
+    return None
+
+
 def pytest_collection_modifyitems(config, items):
     import torch
     has_gpu = torch.cuda.is_available()
