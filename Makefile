@@ -20,7 +20,7 @@ bench: build
 	$(PY) bench.py
 
 sass:
-	cuobjdump -sass torchacc_b200/_C.so | grep -oE "UTC[A-Z0-9.]*MMA[A-Z0-9.]*|UTMA[A-Z0-9.]*|LDTM[A-Z0-9.]*|STTM[A-Z0-9.]*|UTMARED[A-Z0-9.]*" | sort | uniq -c
+	cuobjdump -sass torchacc_b200/_C.so | grep -oE "UTC[A-Z0-9.]*MMA[A-Z0-9.]*|UTCCP[A-Z0-9.]*|UTMA[A-Z0-9.]*|UBLKCP[A-Z0-9.]*|LDTM[A-Z0-9.]*|STTM[A-Z0-9.]*|USETMAXREG[A-Z0-9_.]*" | sort | uniq -c
 
 # compute-sanitizer over the hand-written kernels (the reference has no sanitizer hooks at all):
 # memcheck + synccheck on the stand-alone GEMM harness (every descriptor / TMA / TMEM path, static and dynamic tile
@@ -29,5 +29,11 @@ sanitize: build
 	compute-sanitizer --tool memcheck --error-exitcode 1 build/gemm_test 3 0 1
 	compute-sanitizer --tool synccheck --error-exitcode 1 build/gemm_test 2 0 1
 	compute-sanitizer --tool memcheck --error-exitcode 1 $(PY) -m pytest tests/test_ops_gpu.py -q -m gpu -k "rmsnorm or swiglu or rope or cross_entropy or adamw"
+	compute-sanitizer --tool synccheck $(PY) tools/ncu_targets.py      # MX-FP8 GEMM, SwiGLU epilogue, blockwise / dropout attention
 
-.PHONY: build test test-gpu test-multigpu smoke bench sass sanitize
+# peer-memory collectives under the sanitizer on 2 GPUs: NCCL-free self check (NCCL's own kernels abort a synccheck run)
+sanitize-multigpu: build
+	$(PY) -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --no-python \
+		compute-sanitizer --tool synccheck $(PY) tools/symm_selfcheck.py
+
+.PHONY: build test test-gpu test-multigpu smoke bench sass sanitize sanitize-multigpu
