@@ -202,3 +202,25 @@ def test_accelerate_hf_trainer_patches_drive_ten_steps(restore_hf_classes):
     finally:
         ta.accelerate_hf_trainer(False)
     assert Trainer._clip_grad_norm.__qualname__.startswith("Trainer.")
+
+
+def test_accelerate_accepts_an_unpatched_hf_family_gpt2(restore_hf_classes):
+    """Families without class-level kernel patches (here HF GPT-2, the reference benchmark's default model,
+    benchmarks/transformer.py:37) run through accelerate() as they are: same loss, gradients on the flat shards."""
+    import torchacc_b200 as ta
+    from transformers import GPT2Config, GPT2LMHeadModel
+    gc = GPT2Config(vocab_size=160, n_positions=64, n_embd=64, n_layer=2, n_head=4, resid_pdrop=0.0, embd_pdrop=0.0,
+                    attn_pdrop=0.0)
+    torch.manual_seed(0)
+    ref = GPT2LMHeadModel(gc)
+    model = copy.deepcopy(ref)
+    ids = torch.randint(0, 160, (2, 16), generator=torch.Generator().manual_seed(2))
+    want = ref(input_ids=ids, labels=ids).loss
+    cfg = ta.Config()
+    cfg.compute.bf16 = False
+    cfg.dist.fsdp.wrap_layer_cls = {"GPT2Block"}
+    model = ta.accelerate(model, config=cfg)
+    out = model(input_ids=ids, labels=ids)
+    assert abs(float(out.loss) - float(want)) < 1e-4
+    out.loss.backward()
+    assert all(g is not None and torch.isfinite(g).all() for g in model.engine.grads())
