@@ -62,3 +62,12 @@ def test_accuracy_benchmark_tiny_hf_model():
                     "OUT": "/tmp/tb_acc_test_hf"})
     res = json.loads(out.strip().splitlines()[-1])
     assert res["pass"] and res["abs_delta"] <= 1e-2
+
+
+@pytest.mark.parametrize("flag", ["--tp", "--sp"])
+def test_example_train_hf_model_under_tp_and_sp(flag):
+    """examples/train_hf_model.py on 4 gloo ranks: an unmodified HF Llama under tp2 x fsdp2 / sp2 x fsdp2 trains (loss falls)."""
+    pytest.importorskip("transformers")
+    out = _run(_torchrun(4, _free_port(), "examples/train_hf_model.py", flag, "2", "--steps", "11"))
+    losses = [float(l.split("loss")[1]) for l in out.splitlines() if l.startswith("step ")]
+    assert len(losses) == 3 and losses[-1] < losses[0] - 1.0, losses
