@@ -479,7 +479,6 @@ def run_torch_fsdp(a):
     This is a hand-assembled stand-in, printed with ``"impl": "torch_fsdp"`` -- it never goes through
     ``--impl reference``, which stays the unmodified stock path (and is unavailable for N > 1)."""
     rank, local_rank, world = dist_env()
-    import functools
     import torch
     import torch.distributed as dist
     from transformers import LlamaForCausalLM  # noqa: F401  (before the reference import, see run_reference)

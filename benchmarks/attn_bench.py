@@ -2,7 +2,6 @@
 attention shape.  CUDA-event timing, L2 flushed between iterations."""
 import argparse
 import json
-import math
 import sys
 import os
 

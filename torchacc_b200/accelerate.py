@@ -9,7 +9,6 @@ forwards onto our sm_100a ops; deferred (meta-device) models are materialised un
 from __future__ import annotations
 
 import inspect
-import os
 from typing import Optional
 
 import torch

@@ -19,7 +19,7 @@ from __future__ import annotations
 import copy
 import json
 import os
-from typing import Any, Callable, Dict, List, Optional, Set, Union
+from typing import Any, Dict, Optional
 
 import torch
 

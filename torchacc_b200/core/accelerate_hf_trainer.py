@@ -39,7 +39,7 @@ def accelerate_hf_trainer(enable: bool = True) -> bool:
     """Install (or remove) the Trainer patches.  Returns False when ``transformers`` is unavailable."""
     global _ENABLED
     try:
-        import transformers
+        import transformers  # noqa: F401
         from transformers import Trainer
     except Exception as e:  # pragma: no cover
         logger.warning("accelerate_hf_trainer: transformers is not importable (%s)", e)

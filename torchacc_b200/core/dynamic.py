@@ -3,7 +3,7 @@ Eager CUDA kernels take runtime shapes, so this only validates its arguments and
 (``AsyncLoader`` bucketing remains the mechanism that keeps shapes in a small set)."""
 from __future__ import annotations
 
-from typing import List, Sequence, Union
+from typing import Sequence, Union
 
 import torch
 

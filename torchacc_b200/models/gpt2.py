@@ -5,7 +5,6 @@ GEMM, attention on the flash kernels, the loss on fused linear + cross-entropy; 
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Optional
 
 import torch
 import torch.nn as nn

@@ -14,15 +14,14 @@ HF checkpoints load through ``load_hf_state_dict`` (q/k/v and gate/up are concat
 """
 from __future__ import annotations
 
-import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Optional
 
 import torch
 import torch.nn as nn
 
 from ..ops import attention as attn_ops
-from ..ops.cross_entropy import cross_entropy, fused_linear_cross_entropy
+from ..ops.cross_entropy import fused_linear_cross_entropy
 from ..ops.linear import linear
 from ..ops.rmsnorm import rmsnorm
 from ..ops.rope import rope_qkv_, rope_tables

@@ -18,7 +18,6 @@ from __future__ import annotations
 
 import math
 import os
-from typing import Optional, Tuple
 
 import torch
 import torch.nn.functional as F

@@ -7,7 +7,6 @@
   On an NVSwitch domain the all-to-all is our peer-memory kernel (parallel/symm_mem.py)."""
 from __future__ import annotations
 
-from typing import Optional
 
 import torch
 import torch.distributed as dist

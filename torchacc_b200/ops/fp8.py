@@ -15,7 +15,6 @@ The reference has no fp8 mode (torchacc/config.py:27-54); BASELINE.json lists bl
 """
 from __future__ import annotations
 
-import ctypes
 from typing import Optional, Tuple
 
 import torch

@@ -14,7 +14,6 @@ The reference calls NCCL through torch FSDP / XLA for all of these
 """
 from __future__ import annotations
 
-from typing import Optional
 
 import torch
 import torch.distributed as dist

@@ -5,7 +5,6 @@ only used when there is no FSDP (with FSDP the dp axis becomes the HYBRID replic
 """
 from __future__ import annotations
 
-import torch
 import torch.nn as nn
 
 from .parallel_module import ParallelModule

@@ -34,8 +34,7 @@ import torch.distributed as dist
 import torch.nn as nn
 from torch.utils.checkpoint import checkpoint as torch_checkpoint
 
-from ..utils.logger import logger
-from .collectives import Collectives, LocalCollectives, make_collectives
+from .collectives import Collectives, make_collectives
 
 PAD_MULTIPLE = 128
 

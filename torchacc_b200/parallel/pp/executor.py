@@ -7,7 +7,6 @@ from typing import Any, Callable, Dict, List, Optional
 import torch
 import torch.distributed as dist
 
-from ...utils.utils import apply_to_tensors
 from . import schedule as S
 from .p2p import StageLink, flatten_values, unflatten_values
 from .partition import StageSpec

@@ -18,7 +18,6 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Any, Callable, Dict, List, Optional, Sequence, Union
 
-import torch
 import torch.fx as fx
 import torch.nn as nn
 from torch.fx.passes.split_module import split_module

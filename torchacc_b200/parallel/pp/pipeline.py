@@ -2,7 +2,6 @@
 from __future__ import annotations
 
 import inspect
-from typing import List
 
 import torch
 import torch.nn as nn

@@ -20,7 +20,6 @@ from __future__ import annotations
 
 import glob
 import os
-import re
 from collections import OrderedDict
 from concurrent.futures import ThreadPoolExecutor
 from typing import Any, Dict, List, Optional, Tuple

@@ -18,7 +18,6 @@ import torch
 import torch.distributed as dist
 
 from .. import _native as nat
-from ..utils.logger import logger
 from .collectives import Collectives, NcclCollectives
 
 nat.register_signatures({

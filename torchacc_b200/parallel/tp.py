@@ -18,14 +18,12 @@ runs in the CPU test tier.  ``mark_sharding`` / ``Mesh`` are kept as API aliases
 """
 from __future__ import annotations
 
-from typing import Optional
 
 import torch
 import torch.distributed as dist
 import torch.nn as nn
-import torch.nn.functional as F
 
-from ..ops.linear import gemm, linear
+from ..ops.linear import gemm
 from .collectives import Collectives, make_collectives
 from .mesh import Mesh  # noqa: F401  (reference: tp.Mesh alias)
 
